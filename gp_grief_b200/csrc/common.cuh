@@ -1,0 +1,101 @@
+// Shared helpers for the GP-GRIEF sm_100a kernels: error plumbing, PTX wrappers
+// (mbarrier, bulk async copy = the 1-D TMA path, FP64 DMMA), small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "grief_b200.h"
+
+namespace grief {
+
+// ---- error plumbing -------------------------------------------------------------------------
+// error codes: the public GRIEF_ERR_* macros of include/grief_b200.h (+ one internal code)
+#define GRIEF_ERR_NCCL 6
+
+void set_last_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define GRIEF_CUDA(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ::grief::fail(GRIEF_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, \
+                           __LINE__, cudaGetErrorString(e__));                                 \
+  } while (0)
+
+#define GRIEF_REQUIRE(cond, ...)                                               \
+  do {                                                                         \
+    if (!(cond)) return ::grief::fail(GRIEF_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+// ---- shape constants shared by host and device ------------------------------------------------
+constexpr int kMaxDims = 64;       // input dimensions
+constexpr int kMaxGrid = 64;       // grid points per dimension
+constexpr int kMaxGroups = 8;      // table groups gathered per basis column
+constexpr int kTileN = 128;        // Gram / GEMM tile edge (columns of Phi per block)
+constexpr int kChunk = 16;         // rows of Phi per pipeline stage (= one m16n8k16 K step)
+constexpr int kTableCap = 136;     // max table row width (doubles) that the pass-2 kernel keeps resident
+
+#ifdef __CUDACC__
+// ---- PTX: mbarrier + bulk async copy ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- PTX: FP64 tensor-core MMA (lowers to 8 x DMMA.8x8x4 on sm_100a) ---------------------------
+// D(16x8) += A(16x16,row) * B(16x8,col).  Fragment layout (lane = 4*g + t):
+//   a[2*ks+h] = A[g + 8h][t + 4ks],  b[ks] = B[t + 4ks][g],  c[2*hh + e] = C[g + 8hh][2t + e].
+__device__ __forceinline__ void dmma_16x8x16(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, "
+      "{%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]),
+        "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif  // __CUDACC__
+
+}  // namespace grief

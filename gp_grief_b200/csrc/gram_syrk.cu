@@ -1,0 +1,313 @@
+// G2: fused Phi-tile builder + FP64 tensor-core SYRK,  A = Phi^T Phi  (lower block triangle).
+//
+// Reference being replaced: models/gp_grief_model.py:148-149 (`Phi = kern.cov(X)[0]`,
+// `A = Phi.T.dot(Phi)`), where Phi (n x p) is materialised in host memory (328 GB at n=1e7,p=4096).
+// Here Phi never exists in HBM: every CTA streams 16-row chunks of the group table (plan.h) into
+// shared memory with bulk async copies (1-D TMA, mbarrier completion), builds the two 16 x 128
+// Phi tiles its output tile needs with G gathers + (G-1) multiplies per element, and feeds them to
+// m16n8k16 FP64 MMAs (DMMA) whose 128 x 128 accumulator tile stays in registers for the whole row
+// range.
+//
+// Work item = (row split s, output tile (bi,bj), bi >= bj).  Items are ordered split-major so the
+// ~148 CTAs running concurrently read the same table rows (L2 reuse).  Each item writes its
+// partial tile to a workspace; k_gram_reduce sums the splits in a fixed order (deterministic) and
+// mirrors the result into the full symmetric p x p matrix.
+#include "plan.h"
+
+namespace grief {
+
+constexpr int kGramThreads = 256;
+constexpr int kStages = 3;          // table-chunk ring
+constexpr int kPhiLd = 18;          // doubles per Phi-tile column in smem (16 rows + 2 pad: conflict-free LDS.128)
+
+template <int G> struct SlotPack;   // G u16 slot indices of one column, padded to a power of two
+template <> struct SlotPack<1> { static constexpr int GP = 1; };
+template <> struct SlotPack<2> { static constexpr int GP = 2; };
+template <> struct SlotPack<3> { static constexpr int GP = 4; };
+template <> struct SlotPack<4> { static constexpr int GP = 4; };
+template <> struct SlotPack<5> { static constexpr int GP = 8; };
+template <> struct SlotPack<6> { static constexpr int GP = 8; };
+template <> struct SlotPack<7> { static constexpr int GP = 8; };
+template <> struct SlotPack<8> { static constexpr int GP = 8; };
+
+template <int G>
+__device__ __forceinline__ double phi_element(const double* __restrict__ trow, const uint16_t* __restrict__ ip) {
+  constexpr int GP = SlotPack<G>::GP;
+  uint16_t s[GP];
+  if constexpr (GP == 1) {
+    s[0] = ip[0];
+  } else if constexpr (GP == 2) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(ip);
+    s[0] = w & 0xffff; s[1] = w >> 16;
+  } else if constexpr (GP == 4) {
+    const uint2 w = *reinterpret_cast<const uint2*>(ip);
+    s[0] = w.x & 0xffff; s[1] = w.x >> 16; s[2] = w.y & 0xffff; s[3] = w.y >> 16;
+  } else {
+    const uint4 w = *reinterpret_cast<const uint4*>(ip);
+    s[0] = w.x & 0xffff; s[1] = w.x >> 16; s[2] = w.y & 0xffff; s[3] = w.y >> 16;
+    s[4] = w.z & 0xffff; s[5] = w.z >> 16; s[6] = w.w & 0xffff; s[7] = w.w >> 16;
+  }
+  double v = trow[s[0]];
+#pragma unroll
+  for (int g = 1; g < G; ++g) v *= trow[s[g]];
+  return v;
+}
+
+struct GramParams {
+  const double* T;            // group table, n_pad rows x stride
+  const uint16_t* col_slot;   // p_pad x G
+  const int2* tiles;          // n_tiles (bi, bj)
+  double* ws;                 // n_items x 128 x 128 partial tiles
+  int stride;
+  int n_tiles;
+  int n_items;
+  int64_t n_chunks;           // total 16-row chunks
+  int64_t chunks_per_split;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) {
+  constexpr int GP = SlotPack<G>::GP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                       // kStages barriers (64 B reserved)
+  uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem_raw + 64);                   // 256 x GP
+  double* sT = reinterpret_cast<double*>(smem_raw + 64 + 256 * GP * sizeof(uint16_t));
+  const int stage_doubles = kChunk * prm.stride;
+  double* sPhi = sT + (size_t)kStages * stage_doubles;                           // 2 x 256 x kPhiLd
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps, warp tile 64 (M) x 32 (N)
+  const int krow = lane & 15, khalf = lane >> 4;    // Phi-tile builder: lane <-> chunk row, half-warp <-> column
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const uint32_t stage_bytes = (uint32_t)stage_doubles * sizeof(double);
+  uint64_t gchunk = 0;   // chunks consumed so far by this CTA (drives stage index and mbarrier parity)
+
+  for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+    const int split = item / prm.n_tiles;
+    const int tile = item - split * prm.n_tiles;
+    const int2 ij = prm.tiles[tile];
+    const bool diag = (ij.x == ij.y);
+    const int64_t c0 = (int64_t)split * prm.chunks_per_split;
+    const int64_t c1 = min(prm.n_chunks, c0 + prm.chunks_per_split);
+    const int nc = (int)(c1 - c0);
+    const int ncols = diag ? kTileN : 2 * kTileN;
+    const int boff = diag ? 0 : kTileN;
+
+    // slot indices of this item's columns: [0,128) <- column block bi (M side), [128,256) <- block bj
+    __syncthreads();
+    for (int e = tid; e < ncols * G; e += kGramThreads) {
+      const int c = e / G, g = e - c * G;
+      const int col = (c < kTileN ? ij.x * kTileN + c : ij.y * kTileN + (c - kTileN));
+      sIdx[c * GP + g] = prm.col_slot[(size_t)col * G + g];
+    }
+    __syncthreads();
+
+    double acc[4][4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
+
+    auto issue = [&](int lc) {   // thread 0 only
+      const uint64_t gidx = gchunk + lc;
+      const int st = (int)(gidx % kStages);
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&bars[st], stage_bytes);
+      bulk_g2s(sT + (size_t)st * stage_doubles, prm.T + (size_t)(c0 + lc) * stage_doubles, stage_bytes, &bars[st]);
+    };
+    auto build = [&](int lc) {
+      const uint64_t gidx = gchunk + lc;
+      const int st = (int)(gidx % kStages);
+      mbar_wait(&bars[st], (uint32_t)((gidx / kStages) & 1));
+      const double* trow = sT + (size_t)st * stage_doubles + (size_t)krow * prm.stride;
+      double* dst = sPhi + (size_t)(lc & 1) * (2 * kTileN * kPhiLd) + krow;
+      const int cpw = ncols >> 3;   // columns per warp
+#pragma unroll 4
+      for (int it = 0; it < cpw; it += 2) {
+        const int c = warp * cpw + it + khalf;
+        dst[c * kPhiLd] = phi_element<G>(trow, sIdx + c * GP);
+      }
+    };
+    auto mma = [&](int lc) {
+      const double* base = sPhi + (size_t)(lc & 1) * (2 * kTileN * kPhiLd);
+      const double* pa = base + (size_t)(wm * 64 + g4) * kPhiLd + 4 * t4;
+      const double* pb = base + (size_t)(boff + wn * 32 + g4) * kPhiLd + 4 * t4;
+      double b[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const double2 lo = *reinterpret_cast<const double2*>(pb + nt * 8 * kPhiLd);
+        const double2 hi = *reinterpret_cast<const double2*>(pb + nt * 8 * kPhiLd + 2);
+        b[nt][0] = lo.x; b[nt][1] = lo.y; b[nt][2] = hi.x; b[nt][3] = hi.y;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        double a[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double2 lo = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * kPhiLd);
+          const double2 hi = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * kPhiLd + 2);
+          a[0 + h] = lo.x; a[2 + h] = lo.y; a[4 + h] = hi.x; a[6 + h] = hi.y;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma_16x8x16(acc[mt][nt], a, b[nt]);
+      }
+    };
+
+    if (nc > 0) {
+      if (tid == 0)
+        for (int s = 0; s < kStages && s < nc; ++s) issue(s);
+      build(0);
+      __syncthreads();
+      if (tid == 0 && kStages < nc) issue(kStages);
+      for (int lc = 0; lc < nc; ++lc) {
+        if (lc + 1 < nc) build(lc + 1);
+        mma(lc);
+        __syncthreads();
+        if (tid == 0 && lc + 1 + kStages < nc) issue(lc + 1 + kStages);
+      }
+      gchunk += nc;
+    }
+
+    // partial tile -> workspace (row-major 128 x 128: [m][n], m indexes block bi, n block bj)
+    double* out = prm.ws + (size_t)item * (kTileN * kTileN);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int mrow = wm * 64 + mt * 16 + g4 + 8 * hh;
+          const int ncol = wn * 32 + nt * 8 + 2 * t4;
+          *reinterpret_cast<double2*>(out + (size_t)mrow * kTileN + ncol) =
+              make_double2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
+        }
+  }
+}
+
+// A[bi*128+m][bj*128+n] = sum_s ws[s][tile][m][n], mirrored across the diagonal.
+__global__ void __launch_bounds__(256)
+k_gram_reduce(const double* __restrict__ ws, const int2* __restrict__ tiles, int n_tiles, int n_splits, int p,
+              int64_t lda, double* __restrict__ A) {
+  const int tile = blockIdx.x;
+  const int2 ij = tiles[tile];
+  for (int e = threadIdx.x; e < kTileN * kTileN; e += blockDim.x) {
+    const int m = e / kTileN, n = e - m * kTileN;
+    const int row = ij.x * kTileN + m, col = ij.y * kTileN + n;
+    if (row >= p || col >= p) continue;
+    double s = 0.0;
+    for (int sp = 0; sp < n_splits; ++sp) s += ws[((size_t)sp * n_tiles + tile) * (kTileN * kTileN) + e];
+    if (ij.x != ij.y) {
+      A[(size_t)row * lda + col] = s;
+      A[(size_t)col * lda + row] = s;
+    } else if (col <= row) {        // diagonal tile: keep the lower triangle, mirror it (bit-symmetric result)
+      A[(size_t)row * lda + col] = s;
+      A[(size_t)col * lda + row] = s;
+    }
+  }
+}
+
+struct GramSchedule {
+  int nb, n_tiles, n_splits, n_items;
+  int64_t n_chunks, chunks_per_split;
+};
+
+GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
+  GramSchedule s;
+  s.nb = p_pad / kTileN;
+  s.n_tiles = s.nb * (s.nb + 1) / 2;
+  s.n_chunks = n_pad / kChunk;
+  // choose the number of row splits: fill whole waves of `sms` CTAs, keep >= 64 chunks per split
+  int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.n_chunks / 64, 4096 / std::max(1, s.n_tiles) + 1));
+  int best = 1;
+  double best_eff = -1.0;
+  for (int64_t S = 1; S <= max_splits; ++S) {
+    const int64_t items = S * s.n_tiles;
+    const int64_t waves = (items + sms - 1) / sms;
+    const double eff = (double)items / (double)(waves * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)S; }
+    if (eff >= 0.985) { best = (int)S; break; }
+  }
+  s.n_splits = best;
+  s.chunks_per_split = (s.n_chunks + best - 1) / best;
+  if (s.chunks_per_split < 1) s.chunks_per_split = 1;
+  s.n_items = s.n_splits * s.n_tiles;
+  return s;
+}
+
+size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms) {
+  GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
+  return (size_t)s.n_items * kTileN * kTileN * sizeof(double) + (size_t)s.n_tiles * sizeof(int2) + 256;
+}
+
+template <int G>
+static int launch_gram_g(const Plan* pl, const GramParams& prm, int grid, size_t smem, cudaStream_t stream) {
+  GRIEF_CUDA(cudaFuncSetAttribute(k_gram<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gram<G><<<grid, kGramThreads, smem, stream>>>(prm);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, void* workspace,
+                size_t ws_bytes, int sms, cudaStream_t stream, int* launches) {
+  GRIEF_REQUIRE(n_pad % kChunk == 0, "gram: n_pad=%lld must be a multiple of %d", (long long)n_pad, kChunk);
+  GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
+  GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
+  // workspace layout: [tiles (int2 x n_tiles) padded to 256 B][partials]
+  int2* d_tiles = reinterpret_cast<int2*>(workspace);
+  size_t tiles_bytes = ((size_t)s.n_tiles * sizeof(int2) + 255) / 256 * 256;
+  double* d_ws = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + tiles_bytes);
+  std::vector<int2> tiles(s.n_tiles);
+  int t = 0;
+  for (int bi = 0; bi < s.nb; ++bi)
+    for (int bj = 0; bj <= bi; ++bj) tiles[t++] = make_int2(bi, bj);
+  GRIEF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+  GRIEF_CUDA(cudaStreamSynchronize(stream));   // `tiles` is a host temporary
+
+  GramParams prm;
+  prm.T = T;
+  prm.col_slot = pl->d_col_slot;
+  prm.tiles = d_tiles;
+  prm.ws = d_ws;
+  prm.stride = pl->stride;
+  prm.n_tiles = s.n_tiles;
+  prm.n_items = s.n_items;
+  prm.n_chunks = s.n_chunks;
+  prm.chunks_per_split = s.chunks_per_split;
+  const int G = pl->n_groups;
+  const int GP = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
+  const size_t smem = 64 + 256 * GP * sizeof(uint16_t) + (size_t)kStages * kChunk * pl->stride * sizeof(double) +
+                      (size_t)2 * 2 * kTileN * kPhiLd * sizeof(double);
+  const int grid = std::min(sms, s.n_items);
+  int rc = GRIEF_OK;
+  if (s.n_chunks > 0) {
+    switch (G) {
+      case 1: rc = launch_gram_g<1>(pl, prm, grid, smem, stream); break;
+      case 2: rc = launch_gram_g<2>(pl, prm, grid, smem, stream); break;
+      case 3: rc = launch_gram_g<3>(pl, prm, grid, smem, stream); break;
+      case 4: rc = launch_gram_g<4>(pl, prm, grid, smem, stream); break;
+      case 5: rc = launch_gram_g<5>(pl, prm, grid, smem, stream); break;
+      case 6: rc = launch_gram_g<6>(pl, prm, grid, smem, stream); break;
+      case 7: rc = launch_gram_g<7>(pl, prm, grid, smem, stream); break;
+      case 8: rc = launch_gram_g<8>(pl, prm, grid, smem, stream); break;
+      default: return fail(GRIEF_ERR_UNSUPPORTED, "gram: %d groups", G);
+    }
+    if (rc != GRIEF_OK) return rc;
+  } else {
+    GRIEF_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)s.n_items * kTileN * kTileN * sizeof(double), stream));
+  }
+  k_gram_reduce<<<s.n_tiles, 256, 0, stream>>>(d_ws, d_tiles, s.n_tiles, s.n_splits, pl->p, lda, A);
+  GRIEF_CUDA(cudaGetLastError());
+  if (launches) *launches += 2;
+  return GRIEF_OK;
+}
+
+}  // namespace grief

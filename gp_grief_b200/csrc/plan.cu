@@ -1,0 +1,213 @@
+// Host-side construction of a grief::Plan (see plan.h) and the error-string plumbing.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <numeric>
+
+namespace grief {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+Plan::~Plan() {
+  cudaFree(d_dims);
+  cudaFree(d_grid);
+  cudaFree(d_qs);
+  cudaFree(d_slot_k);
+  cudaFree(d_slot_group);
+  cudaFree(d_group_begin);
+  cudaFree(d_col_slot);
+}
+
+static inline uint64_t mix64(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  h *= 0xff51afd7ed558ccdull;
+  h ^= h >> 33;
+  return h;
+}
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& src) {
+  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
+  if (!src.empty()) GRIEF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return GRIEF_OK;
+}
+
+int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, const double* variance,
+                const double* lengthscale, const double* grid_concat, const int32_t* u,
+                const double* qs_concat, int p, const int32_t* uinv, int width_cap) {
+  GRIEF_REQUIRE(out != nullptr, "plan_create: out is null");
+  GRIEF_REQUIRE(d >= 1 && d <= kMaxDims, "plan_create: d=%d outside [1,%d]", d, kMaxDims);
+  GRIEF_REQUIRE(p >= 1 && p <= 65535 - kTileN, "plan_create: p=%d outside [1,%d]", p, 65535 - kTileN);
+  if (width_cap <= 0 || width_cap > kTableCap) width_cap = kTableCap;
+  Plan* pl = new Plan();
+  pl->d = d;
+  pl->p = p;
+  pl->p_pad = (p + kTileN - 1) / kTileN * kTileN;
+  cudaGetDevice(&pl->device);
+  pl->dims.resize(d);
+  int goff = 0, qoff = 0, foff = 0;
+  for (int i = 0; i < d; ++i) {
+    DimDesc& dd = pl->dims[i];
+    if (m[i] < 1 || m[i] > kMaxGrid || u[i] < 1 || u[i] > m[i] || kernel_id[i] < 0 || kernel_id[i] > KERN_MATERN52) {
+      delete pl;
+      return fail(GRIEF_ERR_BAD_ARG, "plan_create: dimension %d has m=%d u=%d kernel=%d (need 1<=u<=m<=%d)", i, m[i],
+                  u[i], kernel_id[i], kMaxGrid);
+    }
+    dd.m = m[i];
+    dd.u = u[i];
+    dd.kernel = kernel_id[i];
+    dd.grid_off = goff;
+    dd.q_off = qoff;
+    dd.f_off = foff;
+    dd.variance = variance[i];
+    dd.lengthscale = lengthscale[i];
+    goff += m[i];
+    qoff += m[i] * u[i];
+    foff += u[i];
+  }
+  pl->sum_m = goff;
+  pl->sum_u = foff;
+  for (int64_t j = 0; j < (int64_t)p * d; ++j) {
+    int i = (int)(j % d);
+    if (uinv[j] < 0 || uinv[j] >= u[i]) {
+      delete pl;
+      return fail(GRIEF_ERR_BAD_ARG, "plan_create: uinv[%lld]=%d outside [0,%d)", (long long)j, uinv[j], u[i]);
+    }
+  }
+
+  // ---- distinct-sub-tuple counts of every contiguous dimension range [a,b) (hashed) ----
+  const int INF = 1 << 29;
+  std::vector<int> cost((size_t)(d + 1) * (d + 1), INF);
+  {
+    std::vector<uint64_t> h(p), tmp(p);
+    for (int a = 0; a < d; ++a) {
+      std::fill(h.begin(), h.end(), 0x1234567ull + a);
+      for (int b = a + 1; b <= d; ++b) {
+        for (int j = 0; j < p; ++j) h[j] = mix64(h[j], (uint64_t)uinv[(size_t)j * d + (b - 1)] + 1);
+        tmp = h;
+        std::sort(tmp.begin(), tmp.end());
+        int cnt = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+        cost[(size_t)a * (d + 1) + b] = cnt;
+        if (cnt + 2 > width_cap) break;  // monotone in b: longer ranges cannot fit either
+      }
+    }
+  }
+  // ---- smallest number of groups whose tables fit the cap; among those the narrowest ----
+  int bestG = -1;
+  std::vector<int> cuts;
+  {
+    const int GM = std::min(kMaxGroups, d);
+    std::vector<std::vector<int>> best(GM + 1, std::vector<int>(d + 1, INF)), arg(GM + 1, std::vector<int>(d + 1, -1));
+    best[0][0] = 0;
+    for (int g = 1; g <= GM && bestG < 0; ++g) {
+      for (int b = 1; b <= d; ++b)
+        for (int a = g - 1; a < b; ++a) {
+          if (best[g - 1][a] >= INF || cost[(size_t)a * (d + 1) + b] >= INF) continue;
+          int c = best[g - 1][a] + cost[(size_t)a * (d + 1) + b];
+          if (c < best[g][b]) { best[g][b] = c; arg[g][b] = a; }
+        }
+      if (best[g][d] + 2 <= width_cap) {
+        bestG = g;
+        cuts.assign(g + 1, 0);
+        int b = d;
+        for (int gg = g; gg >= 1; --gg) { cuts[gg] = b; b = arg[gg][b]; }
+        cuts[0] = 0;
+      }
+    }
+  }
+  if (bestG < 0) {
+    delete pl;
+    return fail(GRIEF_ERR_UNSUPPORTED,
+                "plan_create: no partition of the %d dimensions into <=%d groups fits a table of %d entries per row",
+                d, kMaxGroups, width_cap);
+  }
+  const int G = bestG;
+  pl->n_groups = G;
+  pl->group_begin = cuts;
+  pl->group_slot0.assign(G, 0);
+  pl->group_size.assign(G, 0);
+  pl->max_group_dims = 1;
+  for (int g = 0; g < G; ++g) pl->max_group_dims = std::max(pl->max_group_dims, cuts[g + 1] - cuts[g]);
+
+  // ---- exact enumeration of the distinct sub-tuples of each chosen group ----
+  pl->col_slot_h.assign((size_t)pl->p_pad * G, 0);
+  std::vector<uint8_t> slot_k;   // filled below (width x max_group_dims)
+  std::vector<int> slot_group;
+  int slot = 2;                  // slot 0 = constant 1.0, slot 1 = constant 0.0
+  std::vector<std::vector<uint8_t>> slot_rows;
+  slot_rows.push_back(std::vector<uint8_t>(pl->max_group_dims, 0));
+  slot_rows.push_back(std::vector<uint8_t>(pl->max_group_dims, 0));
+  slot_group.push_back(-1);
+  slot_group.push_back(-1);
+  std::vector<int> order(p);
+  for (int g = 0; g < G; ++g) {
+    const int a = cuts[g], b = cuts[g + 1];
+    std::iota(order.begin(), order.end(), 0);
+    auto less = [&](int x, int y) {
+      const int32_t* px = uinv + (size_t)x * d;
+      const int32_t* py = uinv + (size_t)y * d;
+      for (int i = a; i < b; ++i)
+        if (px[i] != py[i]) return px[i] < py[i];
+      return false;
+    };
+    std::stable_sort(order.begin(), order.end(), less);
+    pl->group_slot0[g] = slot;
+    for (int r = 0; r < p; ++r) {
+      const int j = order[r];
+      if (r == 0 || less(order[r - 1], j)) {
+        std::vector<uint8_t> row(pl->max_group_dims, 0);
+        for (int i = a; i < b; ++i) row[i - a] = (uint8_t)uinv[(size_t)j * d + i];
+        slot_rows.push_back(row);
+        slot_group.push_back(g);
+        ++slot;
+      }
+      pl->col_slot_h[(size_t)j * G + g] = (uint16_t)(slot - 1);
+    }
+    pl->group_size[g] = slot - pl->group_slot0[g];
+  }
+  pl->width = slot;
+  pl->stride = (slot % 2 == 1) ? slot : slot + 1;  // odd stride: conflict-free lane<->row gathers
+  // padding columns j >= p: zero slot for group 0, one slot for the rest  => Phi[:, j] = 0
+  for (int j = p; j < pl->p_pad; ++j) {
+    pl->col_slot_h[(size_t)j * G + 0] = 1;
+    for (int g = 1; g < G; ++g) pl->col_slot_h[(size_t)j * G + g] = 0;
+  }
+  slot_k.resize((size_t)pl->width * pl->max_group_dims);
+  for (int s = 0; s < pl->width; ++s)
+    std::memcpy(&slot_k[(size_t)s * pl->max_group_dims], slot_rows[s].data(), pl->max_group_dims);
+
+  // ---- upload ----
+  std::vector<double> grid(grid_concat, grid_concat + pl->sum_m);
+  std::vector<double> qs(qs_concat, qs_concat + qoff);
+  int rc = upload(&pl->d_dims, pl->dims);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_grid, grid);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_qs, qs);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_slot_k, slot_k);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_slot_group, slot_group);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_group_begin, pl->group_begin);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_col_slot, pl->col_slot_h);
+  if (rc != GRIEF_OK) {
+    delete pl;
+    return rc;
+  }
+  *out = pl;
+  return GRIEF_OK;
+}
+
+}  // namespace grief

@@ -1,0 +1,63 @@
+// grief_plan: the device-resident description of one GRIEF basis (one value of the kernel
+// hyper-parameters): per-dimension grids, kernel parameters and scaled eigenvectors, plus the
+// "group table" layout that every row kernel shares.
+//
+// Basis column j of Phi is a product over input dimensions (reference: tensors/tensors.py:116-124,
+// kern/grief_kernel.py:104).  The FP64 pipe of a B200 SM is shared by DMMA, DFMA and DMUL
+// (profiles/r01_fp64_pipes_microbench.txt), so every multiply spent building a Phi element is
+// taken from the Gram MMA.  The plan therefore partitions the dimensions into G contiguous groups
+// and enumerates, per group, the DISTINCT index sub-tuples that occur among the p columns; the
+// prepass kernel evaluates one table entry per distinct sub-tuple per data row, and the MMA
+// kernels build a Phi element with G gathers and G-1 multiplies instead of d gathers and d-1.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "common.cuh"
+
+namespace grief {
+
+enum KernelId : int { KERN_RBF = 0, KERN_EXPONENTIAL = 1, KERN_MATERN32 = 2, KERN_MATERN52 = 3 };
+
+struct DimDesc {          // one input dimension, device-visible POD
+  int m;                  // grid points
+  int u;                  // unique selected eigen-indices
+  int kernel;             // KernelId
+  int grid_off;           // offset into grid[]      (sum of m over previous dims)
+  int q_off;              // offset into qs[]        (sum of m*u over previous dims)
+  int f_off;              // offset into the per-row factor scratch (sum of u over previous dims)
+  double variance;
+  double lengthscale;
+};
+
+struct Plan {
+  // ---- host copies ----
+  int d = 0, p = 0, p_pad = 0;          // p_pad = p rounded up to kTileN
+  int n_groups = 0;                     // G
+  int width = 0;                        // table entries per row incl. the 2 constant slots
+  int stride = 0;                       // row stride in doubles (odd, >= width)
+  int sum_m = 0, sum_u = 0;
+  int max_group_dims = 0;
+  std::vector<DimDesc> dims;
+  std::vector<int> group_begin;         // G+1 dimension boundaries
+  std::vector<int> group_slot0;         // first table slot of each group
+  std::vector<int> group_size;          // distinct sub-tuples per group
+  std::vector<uint16_t> col_slot_h;     // p_pad x G slot index per column and group
+  // ---- device buffers (owned) ----
+  DimDesc* d_dims = nullptr;
+  double* d_grid = nullptr;             // concatenated grids
+  double* d_qs = nullptr;               // concatenated m_i x u_i scaled eigenvectors (row-major [g][k])
+  uint8_t* d_slot_k = nullptr;          // width x max_group_dims: unique-index of every dim of the slot's group
+  int* d_slot_group = nullptr;          // width: group of the slot (-1 for the constant slots)
+  int* d_group_begin = nullptr;         // G+1
+  uint16_t* d_col_slot = nullptr;       // p_pad x G
+  int device = 0;
+  ~Plan();
+};
+
+// Builds the plan.  uinv is p x d (row-major): uinv[j*d+i] indexes dimension i's unique list.
+// qs holds, per dimension, an m_i x u_i row-major matrix.  Returns GRIEF_OK or an error code.
+int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, const double* variance,
+                const double* lengthscale, const double* grid_concat, const int32_t* u,
+                const double* qs_concat, int p, const int32_t* uinv, int width_cap);
+
+}  // namespace grief

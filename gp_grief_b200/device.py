@@ -1,0 +1,181 @@
+"""Thin object layer over the C ABI: owns device buffers (torch tensors) and marshals pointers.
+
+Nothing here computes; every method is one or two calls into libgrief_b200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise nat.NativeLibraryError("gp_grief_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch
+
+
+def topk_kron(eig_list, n_eigs):
+    """Device top-p selection; same contract as KronMatrix.find_extremum_eigs(..., 'largest', log_expand=True).
+
+    eig_list: 1-D arrays in KronMatrix.K order.  Returns (eig_loc (p,d) int64, log_lam (p,)) as NumPy.
+    """
+    torch = _torch()
+    d = len(eig_list)
+    eig_list = [np.ascontiguousarray(e, dtype=np.float64).reshape(-1) for e in eig_list]
+    m = np.array([e.size for e in eig_list], dtype=np.int32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        logeig = np.concatenate([np.log(e) for e in eig_list])   # the reference's own call (linalg.py:86-89)
+    raw0 = eig_list[0]
+    p = int(n_eigs)
+    idx = torch.empty((p, d), dtype=torch.int32, device="cuda")
+    lam = torch.empty((p,), dtype=torch.float64, device="cuda")
+    n_out = ctypes.c_int(0)
+    nat.check(nat.lib().grief_topk_kron(d, nat.host_ptr(m), nat.host_ptr(raw0), nat.host_ptr(logeig), p,
+                                        nat.dev_ptr(idx), nat.dev_ptr(lam), ctypes.byref(n_out), nat.stream_ptr()))
+    k = n_out.value
+    return idx[:k].cpu().numpy().astype(np.int64), lam[:k].cpu().numpy()
+
+
+class DevicePlan(object):
+    """One basis on the device (grief_plan). All list arguments are in INPUT-dimension order."""
+
+    def __init__(self, kernel_names, variances, lengthscales, xg, Q, eig, eig_loc, width_cap=0):
+        _torch()
+        d = len(xg)
+        eig_loc = np.asarray(eig_loc)
+        p = eig_loc.shape[0]
+        m = np.array([np.size(g) for g in xg], dtype=np.int32)
+        kid = np.array([nat.KERNEL_IDS[k] for k in kernel_names], dtype=np.int32)
+        var = np.ascontiguousarray(variances, dtype=np.float64)
+        ls = np.ascontiguousarray(lengthscales, dtype=np.float64)
+        grid = np.concatenate([np.asarray(g, dtype=np.float64).reshape(-1) for g in xg])
+        u = np.zeros(d, dtype=np.int32)
+        uinv = np.zeros((p, d), dtype=np.int32)
+        qs = []
+        self.unique = []
+        for i in range(d):
+            uniq, inv = np.unique(eig_loc[:, i], return_inverse=True)   # tensors/selection_matrix.py:78-79
+            self.unique.append(uniq)
+            u[i] = uniq.size
+            uinv[:, i] = inv.reshape(-1)
+            lam = np.asarray(eig[i], dtype=np.float64)[uniq]
+            qs.append(np.ascontiguousarray(np.asarray(Q[i], dtype=np.float64)[:, uniq] / np.sqrt(lam)[None, :]).reshape(-1))
+        qs = np.concatenate(qs)
+        handle = ctypes.c_void_p()
+        nat.check(nat.lib().grief_plan_create(ctypes.byref(handle), d, nat.host_ptr(m), nat.host_ptr(kid),
+                                              nat.host_ptr(var), nat.host_ptr(ls), nat.host_ptr(grid), nat.host_ptr(u),
+                                              nat.host_ptr(qs), p, nat.host_ptr(np.ascontiguousarray(uinv)),
+                                              int(width_cap)))
+        self._h = handle
+        info = nat.lib().grief_plan_info
+        self.n_groups, self.width, self.stride = info(handle, 0), info(handle, 1), info(handle, 2)
+        self.p, self.p_pad, self.d = info(handle, 3), info(handle, 4), info(handle, 5)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().grief_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- row kernels ----
+    def build_tables(self, X_dev):
+        """X_dev: (n, d) float64 CUDA tensor (row-major).  Returns the (n_pad, stride) table tensor."""
+        torch = _torch()
+        assert X_dev.is_cuda and X_dev.dtype == torch.float64 and X_dev.dim() == 2 and X_dev.shape[1] == self.d
+        assert X_dev.stride(1) == 1 or X_dev.shape[0] == 0
+        n = X_dev.shape[0]
+        rows = nat.lib().grief_table_rows(n)
+        T = torch.empty((rows, self.stride), dtype=torch.float64, device=X_dev.device)
+        ldx = X_dev.stride(0) if n > 1 else self.d
+        nat.check(nat.lib().grief_build_tables(self._h, nat.dev_ptr(X_dev), ldx, n, nat.dev_ptr(T), nat.stream_ptr()))
+        return T
+
+    def phi_rows(self, T, n):
+        torch = _torch()
+        Phi = torch.empty((n, self.p), dtype=torch.float64, device=T.device)
+        nat.check(nat.lib().grief_phi_rows(self._h, nat.dev_ptr(T), n, nat.dev_ptr(Phi), nat.stream_ptr()))
+        return Phi
+
+    def gram(self, T, n, out=None, workspace=None):
+        """A = Phi^T Phi (p, p) from the tables of n rows."""
+        torch = _torch()
+        A = out if out is not None else torch.empty((self.p, self.p), dtype=torch.float64, device=T.device)
+        need = nat.lib().grief_gram_workspace_bytes(self._h, n)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty((need,), dtype=torch.uint8, device=T.device)
+        nat.check(nat.lib().grief_gram(self._h, nat.dev_ptr(T), n, nat.dev_ptr(A), A.stride(0), nat.dev_ptr(workspace),
+                                       workspace.numel(), nat.stream_ptr()))
+        return A
+
+    def gram_workspace_bytes(self, n):
+        return nat.lib().grief_gram_workspace_bytes(self._h, n)
+
+    def phi_t_vec(self, T, n, v, out=None):
+        torch = _torch()
+        out = out if out is not None else torch.empty((self.p,), dtype=torch.float64, device=T.device)
+        need = nat.lib().grief_phi_t_vec_workspace_bytes(self._h, n)
+        ws = torch.empty((max(need, 8),), dtype=torch.uint8, device=T.device)
+        nat.check(nat.lib().grief_phi_t_vec(self._h, nat.dev_ptr(T), n, nat.dev_ptr(v), nat.dev_ptr(out), nat.dev_ptr(ws),
+                                            nat.stream_ptr()))
+        return out
+
+    def phi_vec(self, T, n, v):
+        torch = _torch()
+        out = torch.empty((n,), dtype=torch.float64, device=T.device)
+        nat.check(nat.lib().grief_phi_vec(self._h, nat.dev_ptr(T), n, nat.dev_ptr(v), nat.dev_ptr(out), nat.stream_ptr()))
+        return out
+
+
+def sumsq(y_dev):
+    torch = _torch()
+    out = torch.empty((1,), dtype=torch.float64, device=y_dev.device)
+    ws = torch.empty((512,), dtype=torch.float64, device=y_dev.device)
+    nat.check(nat.lib().grief_sumsq(nat.dev_ptr(y_dev), y_dev.numel(), nat.dev_ptr(out), nat.dev_ptr(ws), nat.stream_ptr()))
+    return out
+
+
+class DeviceSolver(object):
+    """grief_ctx: the p x p stage (Cholesky, solve, LML, w / noise gradients, pass-2 operand)."""
+
+    def __init__(self):
+        _torch()
+        h = ctypes.c_void_p()
+        nat.check(nat.lib().grief_ctx_create(ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().grief_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, A, r, yty, w, noise_var, n_rows, want_grad=True, want_G2=False):
+        """Returns dict(lml, yt_alpha, logdet, grad_noise, L, b, Pinv, grad_w, G2) -- tensors stay on the device."""
+        torch = _torch()
+        p = A.shape[0]
+        dev = A.device
+        L = torch.empty((p, p), dtype=torch.float64, device=dev)
+        b = torch.empty((p,), dtype=torch.float64, device=dev)
+        Pinv = torch.empty((p, p), dtype=torch.float64, device=dev) if (want_grad or want_G2) else None
+        grad_w = torch.empty((p,), dtype=torch.float64, device=dev) if want_grad else None
+        G2 = torch.empty((p, p), dtype=torch.float64, device=dev) if want_G2 else None
+        scal = np.zeros(nat.SC_COUNT, dtype=np.float64)
+        info = ctypes.c_int(0)
+        nat.check(nat.lib().grief_solve_lml(self._h, p, nat.dev_ptr(A), A.stride(0), nat.dev_ptr(r), nat.dev_ptr(yty),
+                                            nat.dev_ptr(w), float(noise_var), int(n_rows), nat.dev_ptr(L), nat.dev_ptr(b),
+                                            nat.dev_ptr(Pinv), nat.dev_ptr(grad_w), nat.dev_ptr(G2), nat.host_ptr(scal),
+                                            ctypes.byref(info), nat.stream_ptr()))
+        return dict(lml=float(scal[nat.SC_LML]), yt_alpha=float(scal[nat.SC_YT_ALPHA]), logdet=float(scal[nat.SC_LOGDET]),
+                    grad_noise=float(scal[nat.SC_GRAD_NOISE]), L=L, b=b, Pinv=Pinv, grad_w=grad_w, G2=G2)

@@ -1,0 +1,155 @@
+/*
+ * grief_b200.h -- C ABI of the B200-native GP-GRIEF hot path (libgrief_b200.so).
+ *
+ * The reference (scwolof/gp_grief) is pure Python; it has no FFI of its own.  The boundary this
+ * library drops in behind is therefore the set of Python methods listed beside each entry point
+ * (file:line relative to the reference's gp_grief/ package).  INTEGRATION.md shows the ctypes stubs
+ * a maintainer of the reference would add at those lines.
+ *
+ * Conventions
+ *   - every function returns 0 on success or one of the GRIEF_ERR_* codes; the message of the last
+ *     failure on the calling thread is returned by grief_last_error().
+ *   - pointers named *_dev are CUDA device pointers on the current device, *_host are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - dimension order is INPUT-dimension order i = 0..d-1 everywhere in this ABI.  (The reference
+ *     stores its Kronecker factors reversed, kern/grid_kernel.py:109,174; the Python host layer does
+ *     that bookkeeping.)  The one exception is grief_topk_kron, which takes the factor list in the
+ *     order it is given, exactly like KronMatrix.find_extremum_eigs.
+ *   - all floating point data is IEEE double; matrices are dense row-major unless stated.
+ *   - the library never keeps a pointer to caller memory after a call returns.
+ */
+#ifndef GRIEF_B200_H
+#define GRIEF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRIEF_OK 0
+#define GRIEF_ERR_BAD_ARG 1      /* -> ValueError / AssertionError on the Python side            */
+#define GRIEF_ERR_CUDA 2         /* -> RuntimeError                                             */
+#define GRIEF_ERR_NOT_PD 3       /* -> numpy.linalg.LinAlgError (what scipy cho_factor raises)   */
+#define GRIEF_ERR_UNSUPPORTED 4  /* -> NotImplementedError                                      */
+#define GRIEF_ERR_LIBRARY 5      /* -> RuntimeError (cuSOLVER)                                  */
+
+#define GRIEF_KERN_RBF 0         /* kern/stationary.py:108-134 */
+#define GRIEF_KERN_EXPONENTIAL 1 /* kern/stationary.py:161-175 */
+#define GRIEF_KERN_MATERN32 2    /* kern/stationary.py:202-216 */
+#define GRIEF_KERN_MATERN52 3    /* kern/stationary.py:243-258 */
+
+/* indices into the `scalars_host` array filled by grief_solve_lml */
+#define GRIEF_SC_LML 0
+#define GRIEF_SC_YT_ALPHA 1
+#define GRIEF_SC_LOGDET 2
+#define GRIEF_SC_GRAD_NOISE 3
+#define GRIEF_SC_RTB 4
+#define GRIEF_SC_ALPHA_SQ 5
+#define GRIEF_SC_TRACE 6
+#define GRIEF_SC_COUNT 7
+
+typedef struct grief_plan grief_plan; /* one basis (one value of the kernel hyper-parameters) */
+typedef struct grief_ctx grief_ctx;   /* per-model scratch: cuSOLVER handle and workspaces     */
+
+int grief_version(void);
+const char* grief_last_error(void);
+/* number of CUDA kernels this library has launched on the calling thread since the last reset */
+int grief_launch_count(void);
+void grief_launch_count_reset(void);
+
+int grief_ctx_create(grief_ctx** ctx);
+void grief_ctx_destroy(grief_ctx* ctx);
+
+/*
+ * Top-p selection over the Kronecker product of eigenvalue vectors.
+ * Replaces KronMatrix.find_extremum_eigs(n_eigs, mode='largest', log_expand=True, sort=True)
+ * (tensors/kron_matrix.py:369-446) as called from GriefKernel._setup_inducing_cov
+ * (kern/grief_kernel.py:184).
+ *   d, m_host[d]        number of factors and their sizes (factor k <-> KronMatrix.K[k])
+ *   raw0_host[m[0]]     raw eigenvalues of factor 0 (selection key of the first step, :407)
+ *   logeig_host[sum m]  np.log of every factor's eigenvalues, concatenated, computed by the caller
+ *                       with the same NumPy call the reference uses (linalg.py:86-89)
+ *   p                   n_eigs; must not exceed prod(m)
+ *   idx_dev[p*d]        out, int32 row-major (p, d): eig_loc, column k <-> factor k
+ *   loglam_dev[p]       out: log eigenvalue products, descending
+ *   n_out_host          out: number of entries written (== p)
+ */
+int grief_topk_kron(int d, const int32_t* m_host, const double* raw0_host, const double* logeig_host, int p,
+                    int32_t* idx_dev, double* loglam_dev, int* n_out_host, void* stream);
+
+/*
+ * Describe one basis.  Replaces the state GriefKernel._setup_inducing_cov leaves behind
+ * (kern/grief_kernel.py:168-190: _Quu, _log_lam, _Sp) in the form the row kernels consume.
+ *   m[d], kernel_id[d], variance[d], lengthscale[d], grid_concat[sum m]   per input dimension
+ *   u[d]                 number of distinct selected eigen-indices of the dimension
+ *                        (SelectionMatrixSparse.unique, tensors/selection_matrix.py:78-79)
+ *   qs_concat            per dimension an (m_i, u_i) row-major matrix: column k is the Schur vector of
+ *                        the k-th unique eigen-index divided by sqrt(its eigenvalue)
+ *                        (tensors/tensors.py:118 with kern/grief_kernel.py:104 folded in per dimension)
+ *   p, uinv[p*d]         per basis column and dimension the position in the unique list
+ *                        (SelectionMatrixSparse.unique_inverse)
+ *   width_cap            0 = default; upper bound on table entries per row (testing knob)
+ * All inputs are host pointers and are copied.
+ */
+int grief_plan_create(grief_plan** plan, int d, const int32_t* m, const int32_t* kernel_id,
+                      const double* variance, const double* lengthscale, const double* grid_concat,
+                      const int32_t* u, const double* qs_concat, int p, const int32_t* uinv, int width_cap);
+void grief_plan_destroy(grief_plan* plan);
+/* layout queries: what = 0 groups G, 1 table width, 2 row stride (doubles), 3 p, 4 p_pad, 5 d */
+int grief_plan_info(const grief_plan* plan, int what);
+/* rows the table buffer must hold for n data rows (n rounded up to the MMA chunk) */
+int64_t grief_table_rows(int64_t n);
+
+/*
+ * Prepass: group tables of n data rows.  Replaces GridKernel.cov_kr (kern/grid_kernel.py:148-179),
+ * the per-dimension projection of expand_SKC (tensors/tensors.py:118) and the first levels of its
+ * product (tensors/tensors.py:120-124).
+ *   X_dev       (n, ldx) row-major inputs, column i = input dimension i
+ *   T_dev       out, (grief_table_rows(n), stride) row-major; rows >= n are written as zeros
+ */
+int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, double* T_dev, void* stream);
+
+/* Phi (n, p) row-major from the tables: GriefKernel.cov(x)[0] (kern/grief_kernel.py:68-111). Small n only. */
+int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, double* Phi_dev, void* stream);
+
+/*
+ * Fused Gram:  A = Phi^T Phi without materialising Phi (models/gp_grief_model.py:148-149).
+ *   A_dev       out, (p, lda) row-major, full symmetric matrix
+ *   workspace   device scratch of at least grief_gram_workspace_bytes(plan, n) bytes
+ */
+size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n);
+int grief_gram(const grief_plan* plan, const double* T_dev, int64_t n, double* A_dev, int64_t lda,
+               void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* out[j] = sum_n v[n] Phi[n,j]  (r = Phi^T y, models/gp_grief_model.py:234).  ws: grief_phi_t_vec_workspace_bytes */
+size_t grief_phi_t_vec_workspace_bytes(const grief_plan* plan, int64_t n);
+int grief_phi_t_vec(const grief_plan* plan, const double* T_dev, int64_t n, const double* v_dev, double* out_dev,
+                    void* workspace_dev, void* stream);
+/* out[n] = sum_j Phi[n,j] v[j]  (predictive mean Phi* alpha_p, models/gp_grief_model.py:119) */
+int grief_phi_vec(const grief_plan* plan, const double* T_dev, int64_t n, const double* v_dev, double* out_dev, void* stream);
+/* out[0] = sum_n y[n]^2 ; ws_dev >= 4096 bytes */
+int grief_sumsq(const double* y_dev, int64_t n, double* out_dev, void* ws_dev, void* stream);
+
+/*
+ * The p x p stage (models/gp_grief_model.py:152-153 cho_factor, :234 cho_solve, :243-245 log-det,
+ * :212-213 LML, :171-180 d/dw, :185-191 d/d noise_var), from the reduced statistics A, r, y^T y.
+ *   n_rows          total number of data rows (over all GPUs)
+ *   L_dev           out (p,p): Cholesky factor of P = A + diag(noise_var/w) (cuSOLVER lower, column-major)
+ *   b_dev           out (p): P^-1 r  (== alpha_p of models/gp_grief_model.py:97)
+ *   Pinv_dev        out (p,p) or NULL: P^-1 (needed for the gradients)
+ *   grad_w_dev      out (p) or NULL
+ *   G2_dev          out (p,p) or NULL: -(P^-1 + b b^T / noise_var), operand of grief_grad_pass
+ *   scalars_host    out double[GRIEF_SC_COUNT]
+ *   info_host       out: 0, or the order of the leading minor that is not positive definite
+ */
+int grief_solve_lml(grief_ctx* ctx, int p, const double* A_dev, int64_t lda, const double* r_dev,
+                    const double* yty_dev, const double* w_dev, double noise_var, int64_t n_rows, double* L_dev,
+                    double* b_dev, double* Pinv_dev, double* grad_w_dev, double* G2_dev, double* scalars_host,
+                    int* info_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIEF_B200_H */

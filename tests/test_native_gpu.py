@@ -1,0 +1,170 @@
+"""GPU parity tests of the C-ABI kernels against the CPU oracle and the reference goldens."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from conftest import load_golden, model_cases, case_inputs
+from oracle import grief_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    from gp_grief_b200 import device
+    return device
+
+
+def _plan_from_basis(c, basis, width_cap=0):
+    """Oracle basis (KronMatrix order) -> DevicePlan (input order)."""
+    d = c["d"]
+    Q = [basis.Q[d - 1 - i] for i in range(d)]
+    eig = [basis.eig[d - 1 - i] for i in range(d)]
+    loc = basis.eig_loc[:, ::-1]
+    return _dev().DevicePlan(c["names"], c["variances"], c["lengthscales"], c["xg"], Q, eig, loc, width_cap=width_cap)
+
+
+@pytest.mark.parametrize("name", ["topk_c2_d6_m10_p1024", "topk_c3_d10_m20_p4096",
+                                  "topk_c4_d32_m8_p2048", "topk_c5_d8_m16_p8192"])
+def test_topk_bit_exact_at_bench_configs(name):
+    g = load_golden(name)
+    d, p = int(g["d"]), int(g["p"])
+    eigs = [g["eigs_%d" % k] for k in range(d)]
+    loc, lam = _dev().topk_kron(eigs, p)
+    assert_array_equal(loc, g["eig_loc"].astype(np.int64))      # bit-exact indices (tie-free configs)
+    assert_array_equal(lam, g["log_lam"])                      # bit-exact values
+
+
+def test_topk_reference_kron_eigenvalue_test():
+    """tests/test_tensors/test_kron_eigenvalues.py:64-78 (log_expand=True, largest) through the device path."""
+    g = load_golden("kron_eigs_d10_m3_p5")
+    eigs = [g["eigs_%d" % i] for i in range(10)]
+    loc, lam = _dev().topk_kron(eigs, 5)
+    assert_array_equal(loc, g["loc_largest_log"])
+    assert_array_equal(lam, g["vals_largest_log"])
+    assert_allclose(np.sort(np.exp(lam)), np.sort(g["all_sorted_top"]), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("d,m,p,seed", [(1, 7, 5, 0), (1, 5, 5, 1), (3, 4, 64, 2), (3, 4, 63, 3), (6, 1, 1, 4),
+                                        (5, 3, 200, 5), (4, 9, 1000, 6), (2, 60, 3000, 7), (12, 2, 16384 // 4, 8)])
+def test_topk_random_vs_oracle(d, m, p, seed):
+    rng = np.random.default_rng(seed)
+    eigs = [rng.random(m) + 1e-3 for _ in range(d)]
+    p = int(min(p, float(m) ** d))
+    loc_o, lam_o = orc.find_extremum_eigs(eigs, p)
+    loc, lam = _dev().topk_kron(eigs, p)
+    assert_array_equal(lam, lam_o)
+    if np.all(np.diff(lam_o) != 0):
+        assert_array_equal(loc, loc_o)
+    # every returned tuple reproduces its value
+    chk = np.sum([np.log(eigs[k])[loc[:, k]] for k in range(d)], axis=0)
+    assert_allclose(chk, lam, rtol=1e-13, atol=1e-13)
+
+
+def test_topk_with_ties_is_a_valid_top_set():
+    """Aliased kernels => exact ties: multiset of values must match, indices must be valid/distinct."""
+    rng = np.random.default_rng(11)
+    e = rng.random(6) + 0.1
+    eigs = [e.copy() for _ in range(5)]
+    p = 300
+    loc_o, lam_o = orc.find_extremum_eigs(eigs, p)
+    loc, lam = _dev().topk_kron(eigs, p)
+    assert_allclose(np.sort(lam), np.sort(lam_o), rtol=0, atol=1e-13)
+    assert len({tuple(r) for r in loc}) == p
+
+
+@pytest.mark.parametrize("name", model_cases())
+@pytest.mark.parametrize("width_cap", [0, 24])
+def test_phi_and_gram_match_reference(name, width_cap):
+    import torch
+    g = load_golden(name)
+    c = case_inputs(g)
+    basis = orc.setup_inducing_cov(c["names"], c["variances"], c["lengthscales"], c["xg"], c["n_eigs"])
+    try:
+        plan = _plan_from_basis(c, basis, width_cap)
+    except NotImplementedError:
+        pytest.skip("table does not fit width_cap=%d" % width_cap)
+    Phi_o = orc.grief_phi(basis, c["names"], c["variances"], c["lengthscales"], c["xg"], c["x"])
+    n = c["x"].shape[0]
+    X = torch.from_numpy(np.ascontiguousarray(c["x"])).cuda()
+    T = plan.build_tables(X)
+    Phi = plan.phi_rows(T, n).cpu().numpy()
+    scale = np.abs(Phi_o).max()
+    assert_allclose(Phi, Phi_o, rtol=1e-11, atol=1e-13 * scale)
+    A = plan.gram(T, n).cpu().numpy()
+    A_o = Phi_o.T.dot(Phi_o)
+    assert_allclose(A, A_o, rtol=0, atol=1e-12 * np.abs(A_o).max())
+    assert_array_equal(A, A.T)
+    y = torch.from_numpy(np.ascontiguousarray(c["y"].reshape(-1))).cuda()
+    r = plan.phi_t_vec(T, n, y).cpu().numpy()
+    r_scale = float(np.abs(Phi_o).T.dot(np.abs(c["y"])).max())
+    assert_allclose(r, Phi_o.T.dot(c["y"]).reshape(-1), rtol=0, atol=1e-13 * r_scale)
+    v = np.random.default_rng(0).standard_normal(plan.p)
+    pv = plan.phi_vec(T, n, torch.from_numpy(v).cuda()).cpu().numpy()
+    assert_allclose(pv, Phi_o.dot(v), rtol=0, atol=1e-11 * np.abs(Phi_o.dot(v)).max())
+    s = _dev().sumsq(y).cpu().numpy()[0]
+    assert_allclose(s, float((c["y"] ** 2).sum()), rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", model_cases())
+def test_lml_and_adjoint_gradient_match_reference(name):
+    """LML, d/dw, d/dnoise within 1e-9 relative of the reference (BASELINE north_star tolerance)."""
+    import torch
+    g = load_golden(name)
+    c = case_inputs(g)
+    basis = orc.setup_inducing_cov(c["names"], c["variances"], c["lengthscales"], c["xg"], c["n_eigs"])
+    plan = _plan_from_basis(c, basis)
+    n = c["x"].shape[0]
+    X = torch.from_numpy(np.ascontiguousarray(c["x"])).cuda()
+    y = torch.from_numpy(np.ascontiguousarray(c["y"].reshape(-1))).cuda()
+    T = plan.build_tables(X)
+    A = plan.gram(T, n)
+    r = plan.phi_t_vec(T, n, y)
+    s = _dev().sumsq(y)
+    w = torch.from_numpy(np.ascontiguousarray(c["w"])).cuda()
+    out = _dev().DeviceSolver().solve(A, r, s, w, c["noise_var"], n, want_grad=True, want_G2=True)
+    assert_allclose(out["lml"], float(g["lml"]), rtol=1e-9)
+    assert_allclose(out["logdet"], float(g["log_det"]), rtol=1e-9)
+    if "grad_adjoint" in g:
+        ref = g["grad_adjoint"]
+        assert_allclose(out["grad_noise"], ref[0], rtol=1e-9, atol=1e-9 * abs(float(g["lml"])))
+        gw = out["grad_w"].cpu().numpy()
+        rw = ref[-c["n_eigs"]:]
+        assert_allclose(gw, rw, rtol=1e-9, atol=1e-9 * np.abs(rw).max())
+    # alpha_p == b  (models/gp_grief_model.py:97) -> predictive mean
+    if "xnew" in g:
+        Xn = torch.from_numpy(np.ascontiguousarray(g["xnew"])).cuda()
+        Tn = plan.build_tables(Xn)
+        mean = plan.phi_vec(Tn, Xn.shape[0], out["b"]).cpu().numpy()
+        assert_allclose(mean, g["yhat"], rtol=1e-9, atol=1e-9 * np.abs(g["yhat"]).max())
+
+
+def test_not_positive_definite_raises_linalgerror():
+    import torch
+    p = 8
+    A = -torch.eye(p, dtype=torch.float64, device="cuda")
+    r = torch.ones(p, dtype=torch.float64, device="cuda")
+    s = torch.ones(1, dtype=torch.float64, device="cuda")
+    w = torch.ones(p, dtype=torch.float64, device="cuda")
+    with pytest.raises(np.linalg.LinAlgError):
+        _dev().DeviceSolver().solve(A, r, s, w, 0.5, 100)
+
+
+def test_gram_larger_random_shape_vs_materialised_phi():
+    """n not a multiple of the chunk, p not a multiple of the tile, several row splits."""
+    import torch
+    rng = np.random.default_rng(5)
+    d, m, p, n = 5, 6, 300, 70001
+    xg = [np.linspace(0, 1, m) for _ in range(d)]
+    names = ["RBF"] * d
+    var, ls = [1.0] * d, [0.3 + 0.07 * i for i in range(d)]
+    basis = orc.setup_inducing_cov(names, var, ls, xg, p)
+    c = dict(d=d, names=names, variances=var, lengthscales=ls, xg=xg)
+    plan = _plan_from_basis(c, basis)
+    X = torch.from_numpy(rng.random((n, d))).cuda()
+    T = plan.build_tables(X)
+    Phi = plan.phi_rows(T, n)
+    A = plan.gram(T, n)
+    A_ref = Phi.T @ Phi
+    assert_allclose(A.cpu().numpy(), A_ref.cpu().numpy(), rtol=0, atol=1e-12 * float(A_ref.abs().max()))
+    Phi_o = orc.grief_phi(basis, names, var, ls, xg, X[:2000].cpu().numpy())
+    assert_allclose(Phi[:2000].cpu().numpy(), Phi_o, rtol=1e-11, atol=1e-13 * np.abs(Phi_o).max())
