@@ -16,14 +16,10 @@
 
 namespace grief {
 
-constexpr int kMmaWarps = 8;                      // consumers: 2 x 4 warps, warp tile 64 (M) x 32 (N)
-constexpr int kBuildWarps = 8;                    // producers: build the Phi tiles (two per SM sub-partition)
-constexpr int kGramThreads = 32 * (kMmaWarps + kBuildWarps);
+constexpr int kGramThreads = 256;                 // 8 warps, 2 x 4, warp tile 64 (M) x 32 (N)
 constexpr int kTStages = 4;                       // table-chunk ring (bulk async copies)
-constexpr int kPStages = 3;                       // Phi-tile ring (producers -> MMA warps)
 constexpr int kPhiLd = 18;                        // doubles per Phi-tile column in smem (16 rows + 2 pad: conflict-free LDS.128)
 constexpr int kPhiStageDoubles = 2 * kTileN * kPhiLd;
-constexpr int kRegsMma = 200, kRegsBuild = 56;    // setmaxnreg budgets: 256*200 + 256*56 = 512*128
 
 template <int G> struct SlotPack;   // G u16 slot indices of one column, padded to a power of two
 template <> struct SlotPack<1> { static constexpr int GP = 1; };
@@ -54,27 +50,34 @@ __device__ __forceinline__ void load_slots(const uint16_t* __restrict__ ip, int 
   for (int g = 0; g < G; ++g) s[g] = (g & 1) ? (int)(w[g >> 1] >> 16) : (int)(w[g >> 1] & 0xffffu);
 }
 
-// Builds NB Phi elements at once: all gathers are issued before the first multiply and all stores come last,
-// so the NB dependent DMUL chains overlap (the compiler cannot reorder shared-memory loads across the stores).
+// Phi elements are built in batches of NB: gather() issues every shared-memory load of the batch,
+// finish() multiplies and stores.  The MMA block of the current chunk is issued between the two, so the
+// gather latency and the dependent DMUL chain hide behind tensor work of the same warp.
 template <int G, int NB>
-__device__ __forceinline__ void build_batch(const double* __restrict__ trow, const uint16_t* __restrict__ sIdx,
-                                            double* __restrict__ dst, int c_first, int c_step) {
-  constexpr int GP = SlotPack<G>::GP;
-  int slots[NB][G];
-#pragma unroll
-  for (int e = 0; e < NB; ++e) load_slots<G>(sIdx + (c_first + e * c_step) * GP, slots[e]);
+struct PhiBatch {
   double v[NB][G];
+  __device__ __forceinline__ void gather(const double* __restrict__ trow, const uint16_t* __restrict__ sIdx, int c_first) {
+    constexpr int GP = SlotPack<G>::GP;
+    int slots[NB][G];
 #pragma unroll
-  for (int e = 0; e < NB; ++e)
+    for (int e = 0; e < NB; ++e) load_slots<G>(sIdx + (c_first + 2 * e) * GP, slots[e]);
 #pragma unroll
-    for (int g = 0; g < G; ++g) v[e][g] = trow[slots[e][g]];
+    for (int e = 0; e < NB; ++e)
 #pragma unroll
-  for (int g = 1; g < G; ++g)
+      for (int g = 0; g < G; ++g) v[e][g] = trow[slots[e][g]];
+  }
+  __device__ __forceinline__ void finish(double* __restrict__ dst, int c_first) {
+    // pairwise tree: ceil(log2 G) dependent DMUL steps, NB independent chains per step
 #pragma unroll
-    for (int e = 0; e < NB; ++e) v[e][0] *= v[e][g];
+    for (int st = 1; st < G; st *= 2)
 #pragma unroll
-  for (int e = 0; e < NB; ++e) dst[(c_first + e * c_step) * kPhiLd] = v[e][0];
-}
+      for (int g = 0; g + st < G; g += 2 * st)
+#pragma unroll
+        for (int e = 0; e < NB; ++e) v[e][g] *= v[e][g + st];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) dst[(c_first + 2 * e) * kPhiLd] = v[e][0];
+  }
+};
 
 struct GramParams {
   const double* T;            // group table, n_pad rows x stride
@@ -88,139 +91,119 @@ struct GramParams {
   int64_t chunks_per_split;
 };
 
-// Warp-specialised: warps 0..7 only issue LDS.128 + DMMA, warps 8..15 stream the table chunks in
-// (bulk async copy) and build the Phi tiles.  All hand-offs are mbarriers:
-//   t_full[s]  (tx bytes)  copy engine -> builders      t_empty[s] (8 warps) builders -> copy issuer
-//   p_full[s]  (8 warps)   builders    -> MMA warps     p_empty[s] (8 warps) MMA warps -> builders
+// Every warp does both jobs in two phases per chunk: build its share of the Phi tiles of chunk lc+1 (all
+// warps together, 8 elements in flight per lane), then the DMMAs of chunk lc.  Measured alternatives
+// (profiles/r01_gram_design_notes.md): dedicated builder warps and DMULs interleaved between DMMAs are both
+// slower, because every DMMA->DMUL switch of the shared FP64 pipe costs tens of idle cycles.
 template <int G>
 __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) {
   constexpr int GP = SlotPack<G>::GP;
+  constexpr int NB = (G <= 4) ? 8 : 4;      // Phi elements in flight per lane during the build phase
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* t_full = reinterpret_cast<uint64_t*>(smem_raw);      // 128 B reserved for 14 barriers
-  uint64_t* t_empty = t_full + kTStages;
-  uint64_t* p_full = t_empty + kTStages;
-  uint64_t* p_empty = p_full + kPStages;
-  uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem_raw + 128);                  // 256 x GP
-  double* sT = reinterpret_cast<double*>(smem_raw + 128 + 256 * GP * sizeof(uint16_t));
+  uint64_t* t_full = reinterpret_cast<uint64_t*>(smem_raw);                      // kTStages barriers (64 B reserved)
+  uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem_raw + 64);                   // 256 x GP
+  double* sT = reinterpret_cast<double*>(smem_raw + 64 + 256 * GP * sizeof(uint16_t));
   const int stage_doubles = kChunk * prm.stride;
-  double* sPhi = sT + (size_t)kTStages * stage_doubles;                          // kPStages x 256 x kPhiLd
+  double* sPhi = sT + (size_t)kTStages * stage_doubles;                          // 2 x 256 x kPhiLd
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int krow = lane & 15, khalf = lane >> 4;    // builder: lane <-> chunk row, half-warp <-> column
 
   if (tid == 0) {
-    for (int s = 0; s < kTStages; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kBuildWarps); }
-    for (int s = 0; s < kPStages; ++s) { mbar_init(&p_full[s], kBuildWarps); mbar_init(&p_empty[s], kMmaWarps); }
+    for (int s = 0; s < kTStages; ++s) mbar_init(&t_full[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
 
   const uint32_t stage_bytes = (uint32_t)stage_doubles * sizeof(double);
-  uint64_t gq = 0;   // chunks handled so far by this CTA (same sequence in every warp): ring slots + parities
+  uint64_t gq = 0;   // chunks consumed so far by this CTA (ring slot + mbarrier parity)
 
-  if (warp >= kMmaWarps) {
-    // ======================= producers: table chunks in, Phi tiles out =======================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsBuild));
-    const int pw = warp - kMmaWarps;
-    const int ptid = tid - 32 * kMmaWarps;
-    const int krow = lane & 15, khalf = lane >> 4;      // lane <-> chunk row, half-warp <-> column
-    const bool issuer = (pw == 0 && lane == 0);
-    for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-      const int split = item / prm.n_tiles;
-      const int tile = item - split * prm.n_tiles;
-      const int2 ij = prm.tiles[tile];
-      const bool diag = (ij.x == ij.y);
-      const int64_t c0 = (int64_t)split * prm.chunks_per_split;
-      const int64_t c1 = min(prm.n_chunks, c0 + prm.chunks_per_split);
-      const int nc = (int)max((int64_t)0, c1 - c0);
-      const int ncols = diag ? kTileN : 2 * kTileN;
-      // slot indices of this item's columns: [0,128) <- column block bi (M side), [128,256) <- block bj
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kBuildWarps));
-      for (int e = ptid; e < ncols * G; e += 32 * kBuildWarps) {
-        const int c = e / G, g = e - c * G;
-        const int col = (c < kTileN ? ij.x * kTileN + c : ij.y * kTileN + (c - kTileN));
-        sIdx[c * GP + g] = prm.col_slot[(size_t)col * G + g];
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kBuildWarps));
-      int issued = 0;
-      auto issue_upto = [&](int target) {      // issuer lane only
-        const int lim = min(nc, target);
-        for (; issued < lim; ++issued) {
-          const uint64_t q = gq + issued;
-          const int st = (int)(q % kTStages);
-          mbar_wait(&t_empty[st], (uint32_t)(((q / kTStages) & 1) ^ 1));
-          fence_proxy_async();
-          mbar_arrive_expect_tx(&t_full[st], stage_bytes);
-          bulk_g2s(sT + (size_t)st * stage_doubles, prm.T + (size_t)(c0 + issued) * stage_doubles, stage_bytes,
-                   &t_full[st]);
-        }
-      };
-      if (issuer) issue_upto(kTStages - 1);
-      const int cpw = ncols / kBuildWarps;     // columns per producer warp
-      for (int lc = 0; lc < nc; ++lc) {
-        const uint64_t q = gq + lc;
-        const int ts = (int)(q % kTStages), ps = (int)(q % kPStages);
-        if (issuer) issue_upto(lc + kTStages);
-        mbar_wait(&t_full[ts], (uint32_t)((q / kTStages) & 1));
-        mbar_wait(&p_empty[ps], (uint32_t)(((q / kPStages) & 1) ^ 1));
-        const double* trow = sT + (size_t)ts * stage_doubles + (size_t)krow * prm.stride;
-        double* dst = sPhi + (size_t)ps * kPhiStageDoubles + krow;
-        constexpr int NB = (G <= 4) ? 4 : 2;     // elements in flight per lane (register budget of the builders)
-        for (int it = 0; it < cpw; it += 2 * NB)
-          build_batch<G, NB>(trow, sIdx, dst, pw * cpw + it + khalf, 2);
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&p_full[ps]);
-          mbar_arrive(&t_empty[ts]);
-        }
-      }
-      gq += nc;
+  for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+    const int split = item / prm.n_tiles;
+    const int tile = item - split * prm.n_tiles;
+    const int2 ij = prm.tiles[tile];
+    const bool diag = (ij.x == ij.y);
+    const int64_t c0 = (int64_t)split * prm.chunks_per_split;
+    const int64_t c1 = min(prm.n_chunks, c0 + prm.chunks_per_split);
+    const int nc = (int)max((int64_t)0, c1 - c0);
+    const int ncols = diag ? kTileN : 2 * kTileN;
+    const int boff = diag ? 0 : kTileN;
+    const int cpw = ncols >> 3;                 // columns per warp per chunk (32, or 16 on diagonal tiles)
+
+    __syncthreads();
+    for (int e = tid; e < ncols * G; e += kGramThreads) {
+      const int c = e / G, g = e - c * G;
+      const int col = (c < kTileN ? ij.x * kTileN + c : ij.y * kTileN + (c - kTileN));
+      sIdx[c * GP + g] = prm.col_slot[(size_t)col * G + g];
     }
-  } else {
-    // ======================= consumers: LDS.128 + DMMA only =======================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsMma));
-    const int g4 = lane >> 2, t4 = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
-    for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-      const int split = item / prm.n_tiles;
-      const int tile = item - split * prm.n_tiles;
-      const int2 ij = prm.tiles[tile];
-      const bool diag = (ij.x == ij.y);
-      const int64_t c0 = (int64_t)split * prm.chunks_per_split;
-      const int64_t c1 = min(prm.n_chunks, c0 + prm.chunks_per_split);
-      const int nc = (int)max((int64_t)0, c1 - c0);
-      const int boff = diag ? 0 : kTileN;
+    __syncthreads();
 
-      double acc[4][4][4];
+    double acc[4][4][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+      for (int b = 0; b < 4; ++b)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
 
+    auto issue = [&](int lc) {   // thread 0 only; the target ring slot was released by the last __syncthreads
+      const uint64_t q = gq + lc;
+      const int st = (int)(q % kTStages);
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&t_full[st], stage_bytes);
+      bulk_g2s(sT + (size_t)st * stage_doubles, prm.T + (size_t)(c0 + lc) * stage_doubles, stage_bytes, &t_full[st]);
+    };
+
+    if (nc > 0) {
+      if (tid == 0)
+        for (int s = 0; s < kTStages - 1 && s < nc; ++s) issue(s);
+      // chunk 0 has no MMA to hide behind: plain build
+      {
+        const int st = (int)(gq % kTStages);
+        mbar_wait(&t_full[st], (uint32_t)((gq / kTStages) & 1));
+        const double* trow = sT + (size_t)st * stage_doubles + (size_t)krow * prm.stride;
+        double* dst = sPhi + krow;
+        for (int it = 0; it < cpw; it += 2 * NB) {
+          PhiBatch<G, NB> pb;
+          pb.gather(trow, sIdx, warp * cpw + it + khalf);
+          pb.finish(dst, warp * cpw + it + khalf);
+        }
+      }
+      __syncthreads();
       for (int lc = 0; lc < nc; ++lc) {
-        const uint64_t q = gq + lc;
-        const int ps = (int)(q % kPStages);
-        mbar_wait(&p_full[ps], (uint32_t)((q / kPStages) & 1));
-        // K order inside the chunk is permuted (lane t supplies rows 4t..4t+3): one LDS.128 yields two K
-        // steps.  K steps are the OUTER loop so that consecutive DMMAs hit different accumulators.
-        const double* base = sPhi + (size_t)ps * kPhiStageDoubles;
+        if (tid == 0 && lc + kTStages - 1 < nc) issue(lc + kTStages - 1);   // slot of chunk lc-1: free since last sync
+        const bool more = (lc + 1 < nc);
+        const uint64_t qn = gq + lc + 1;
+        const int stn = (int)(qn % kTStages);
+        if (more) mbar_wait(&t_full[stn], (uint32_t)((qn / kTStages) & 1));
+        const double* trow = sT + (size_t)stn * stage_doubles + (size_t)krow * prm.stride;
+        double* dst = sPhi + (size_t)((lc + 1) & 1) * kPhiStageDoubles + krow;
+        const double* base = sPhi + (size_t)(lc & 1) * kPhiStageDoubles;
         const double* pa = base + (size_t)(wm * 64 + g4) * kPhiLd + 4 * t4;
-        const double* pb = base + (size_t)(boff + wn * 32 + g4) * kPhiLd + 4 * t4;
+        const double* pbp = base + (size_t)(boff + wn * 32 + g4) * kPhiLd + 4 * t4;
+        // ---- build phase (chunk lc+1): FP64 DMULs of all warps are issued together, not mixed with DMMAs:
+        //      a DMUL that has to enter a DMMA-busy FP64 pipe stalls ~60 cycles (profiles/r01 notes) ----
+        if (more) {
+          for (int it = 0; it < cpw; it += 2 * NB) {
+            PhiBatch<G, NB> pb;
+            pb.gather(trow, sIdx, warp * cpw + it + khalf);
+            pb.finish(dst, warp * cpw + it + khalf);
+          }
+        }
+        // ---- MMA phase (chunk lc).  K order inside the chunk is permuted (lane t supplies rows 4t..4t+3):
+        //      one LDS.128 yields two K steps; K steps are outermost so consecutive DMMAs are independent ----
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           double2 av[4][2], bv[4];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) bv[nt] = *reinterpret_cast<const double2*>(pb + nt * 8 * kPhiLd + 2 * hf);
+          for (int nt = 0; nt < 4; ++nt) bv[nt] = *reinterpret_cast<const double2*>(pbp + nt * 8 * kPhiLd + 2 * hf);
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
               av[mt][h] = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * kPhiLd + 2 * hf);
-          if (hf == 1) {               // all reads of this stage are in registers: hand it back early
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_empty[ps]);
-          }
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -230,23 +213,24 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].y, av[mt][1].y, bv[nt].y);
         }
+        __syncthreads();
       }
       gq += nc;
-
-      // partial tile -> workspace (row-major 128 x 128: [m][n], m indexes block bi, n block bj)
-      double* out = prm.ws + (size_t)item * (kTileN * kTileN);
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int mrow = wm * 64 + mt * 16 + g4 + 8 * hh;
-            const int ncol = wn * 32 + nt * 8 + 2 * t4;
-            *reinterpret_cast<double2*>(out + (size_t)mrow * kTileN + ncol) =
-                make_double2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
-          }
     }
+
+    // partial tile -> workspace (row-major 128 x 128: [m][n], m indexes block bi, n block bj)
+    double* out = prm.ws + (size_t)item * (kTileN * kTileN);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int mrow = wm * 64 + mt * 16 + g4 + 8 * hh;
+          const int ncol = wn * 32 + nt * 8 + 2 * t4;
+          *reinterpret_cast<double2*>(out + (size_t)mrow * kTileN + ncol) =
+              make_double2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
+        }
   }
 }
 
@@ -341,8 +325,8 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   prm.chunks_per_split = s.chunks_per_split;
   const int G = pl->n_groups;
   const int GP = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
-  const size_t smem = 128 + 256 * GP * sizeof(uint16_t) + (size_t)kTStages * kChunk * pl->stride * sizeof(double) +
-                      (size_t)kPStages * kPhiStageDoubles * sizeof(double);
+  const size_t smem = 64 + 256 * GP * sizeof(uint16_t) + (size_t)kTStages * kChunk * pl->stride * sizeof(double) +
+                      (size_t)2 * kPhiStageDoubles * sizeof(double);
   const int grid = std::min(sms, s.n_items);
   int rc = GRIEF_OK;
   if (s.n_chunks > 0) {
