@@ -40,6 +40,12 @@ SIGNATURES = {
     "grief_phi_t_vec": (c_int, [c_void, c_void, c_i64, c_void, c_void, c_void, c_void]),
     "grief_phi_vec": (c_int, [c_void, c_void, c_i64, c_void, c_void, c_void]),
     "grief_sumsq": (c_int, [c_void, c_i64, c_void, c_void, c_void]),
+    "grief_grad_setup": (c_int, [c_void, c_int, c_void, c_void, c_void]),
+    "grief_grad_workspace_bytes": (c_size, [c_void, c_i64]),
+    "grief_grad_theta": (c_int, [c_void, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void, c_dbl, c_void,
+                                 c_void, c_size, c_void]),
+    "grief_quadform_workspace_bytes": (c_size, [c_void, c_i64]),
+    "grief_quadform_rows": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_void, c_size, c_void]),
     "grief_solve_lml": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void, c_void, c_dbl, c_i64, c_void, c_void,
                                 c_void, c_void, c_void, c_void, _P(c_int), c_void]),
 }

@@ -21,7 +21,27 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
 int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const double* logeig_host, int p, int32_t* idx_dev,
                 double* loglam_dev, int* n_out_host, cudaStream_t stream, int* launches);
 
+int grad_desc_create(GradDesc** out, const Plan* pl, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat);
+int grad_desc_n_active(const GradDesc* gd);
+int grad_desc_dt_width(const GradDesc* gd);
+int launch_dtables(const Plan* pl, const GradDesc* gd, const double* X, int64_t ldx, int64_t n_valid, int64_t rows_total, double* DT, cudaStream_t stream);
+int contract_blocks(int sms);
+int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t ldz, const double* T, const double* DT, const double* y,
+                    const double* gvec, int64_t rows, double* partial, int sms, cudaStream_t stream);
+int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream);
+int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream);
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* B, int64_t ldb, double* Z, int64_t ldz, int sms,
+                 cudaStream_t stream, int* launches);
+int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
+
 static thread_local int g_launches = 0;
+
+constexpr int64_t kRowBlock = 128;
+static int64_t slab_rows_for(int64_t n, int sms) {
+  const int64_t n128 = (n + kRowBlock - 1) / kRowBlock * kRowBlock;
+  return std::min<int64_t>(n128, (int64_t)sms * kRowBlock * 2);
+}
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
 static int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -96,7 +116,7 @@ int grief_plan_info(const grief_plan* plan, int what) {
     default: return -1;
   }
 }
-int64_t grief_table_rows(int64_t n) { return (n + kChunk - 1) / kChunk * kChunk; }
+int64_t grief_table_rows(int64_t n) { return (n + kRowBlock - 1) / kRowBlock * kRowBlock; }
 
 int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, double* T_dev, void* stream) {
   GRIEF_REQUIRE(plan && T_dev && (X_dev || n == 0), "grief_build_tables: null pointer");
@@ -153,6 +173,88 @@ int grief_solve_lml(grief_ctx* ctx, int p, const double* A_dev, int64_t lda, con
   GRIEF_REQUIRE(ctx && A_dev && r_dev && yty_dev && w_dev && L_dev && b_dev && scalars_host, "grief_solve_lml: null pointer");
   return solve_lml(ctx->solve, p, A_dev, lda, r_dev, yty_dev, w_dev, noise_var, n_rows, L_dev, b_dev, Pinv_dev, grad_w_dev,
                    G2_dev, scalars_host, info_host, (cudaStream_t)stream, &g_launches);
+}
+
+int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat) {
+  GRIEF_REQUIRE(plan && (n_active == 0 || (dims && kinds && dqs_concat)), "grief_grad_setup: null pointer");
+  Plan* pl = plan->impl;
+  if (pl->grad) { grad_desc_destroy(pl->grad); pl->grad = nullptr; }
+  return grad_desc_create(&pl->grad, pl, n_active, dims, kinds, dqs_concat);
+}
+
+size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
+  const Plan* pl = plan->impl;
+  if (!pl->grad) return 0;
+  const int sms = sm_count();
+  const int64_t slab = slab_rows_for(n, sms);
+  return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
+         align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p * sizeof(double));
+}
+
+int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev, int64_t n,
+                     const double* G2_dev, int64_t ldg, const double* b_dev, double noise_var, double* grad_dev, void* workspace_dev,
+                     size_t workspace_bytes, void* stream_) {
+  GRIEF_REQUIRE(plan && plan->impl->grad, "grief_grad_theta: call grief_grad_setup first");
+  GRIEF_REQUIRE(G2_dev && b_dev && grad_dev && workspace_dev && (n == 0 || (T_dev && X_dev && y_dev)), "grief_grad_theta: null pointer");
+  GRIEF_REQUIRE(workspace_bytes >= grief_grad_workspace_bytes(plan, n), "grief_grad_theta: workspace too small");
+  const Plan* pl = plan->impl;
+  const GradDesc* gd = pl->grad;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int sms = sm_count();
+  const int na = grad_desc_n_active(gd), dtw = grad_desc_dt_width(gd);
+  const int64_t slab = slab_rows_for(n, sms);
+  char* q = reinterpret_cast<char*>(workspace_dev);
+  double* Z = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
+  double* DT = reinterpret_cast<double*>(q); q += align256((size_t)slab * std::max(1, dtw) * sizeof(double));
+  double* partial = reinterpret_cast<double*>(q); q += align256((size_t)contract_blocks(sms) * std::max(1, na) * sizeof(double));
+  double* gvec = reinterpret_cast<double*>(q);
+  if (na == 0) return GRIEF_OK;
+  GRIEF_CUDA(cudaMemsetAsync(partial, 0, (size_t)contract_blocks(sms) * na * sizeof(double), stream));
+  int rc = launch_scale_vec(b_dev, 1.0 / noise_var, pl->p, gvec, stream);
+  if (rc != GRIEF_OK) return rc;
+  g_launches += 1;
+  const int64_t n128 = grief_table_rows(n);
+  for (int64_t r0 = 0; r0 < n128; r0 += slab) {
+    const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
+    const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, G2_dev, ldg, Z, pl->p_pad, sms, stream, &g_launches);
+    if (rc != GRIEF_OK) return rc;
+    rc = launch_dtables(pl, gd, X_dev + (size_t)r0 * ldx, ldx, rows_valid, rows_valid, DT, stream);
+    if (rc != GRIEF_OK) return rc;
+    rc = launch_contract(pl, gd, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, DT, y_dev + r0, gvec, rows_valid, partial, sms, stream);
+    if (rc != GRIEF_OK) return rc;
+    g_launches += 2;
+  }
+  rc = launch_reduce_partials(partial, contract_blocks(sms), na, grad_dev, stream);
+  if (rc == GRIEF_OK) g_launches += 1;
+  return rc;
+}
+
+size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n) {
+  const Plan* pl = plan->impl;
+  return align256((size_t)slab_rows_for(n, sm_count()) * pl->p_pad * sizeof(double));
+}
+
+int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb, double* q_dev,
+                        void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  GRIEF_REQUIRE(plan && B_dev && workspace_dev && (n == 0 || (T_dev && q_dev)), "grief_quadform_rows: null pointer");
+  GRIEF_REQUIRE(workspace_bytes >= grief_quadform_workspace_bytes(plan, n), "grief_quadform_rows: workspace too small");
+  const Plan* pl = plan->impl;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int sms = sm_count();
+  const int64_t slab = slab_rows_for(n, sms);
+  double* Z = reinterpret_cast<double*>(workspace_dev);
+  const int64_t n128 = grief_table_rows(n);
+  for (int64_t r0 = 0; r0 < n128; r0 += slab) {
+    const int64_t rows_blk = std::min(slab, n128 - r0);
+    const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, B_dev, ldb, Z, pl->p_pad, sms, stream, &g_launches);
+    if (rc != GRIEF_OK) return rc;
+    rc = launch_rowdot(pl, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, rows_valid, q_dev + r0, stream);
+    if (rc != GRIEF_OK) return rc;
+    g_launches += 1;
+  }
+  return GRIEF_OK;
 }
 
 }  // extern "C"

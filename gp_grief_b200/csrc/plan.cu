@@ -24,6 +24,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 Plan::~Plan() {
+  if (grad) grad_desc_destroy(grad);
   cudaFree(d_dims);
   cudaFree(d_grid);
   cudaFree(d_qs);

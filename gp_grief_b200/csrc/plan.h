@@ -29,6 +29,9 @@ struct DimDesc {          // one input dimension, device-visible POD
   double lengthscale;
 };
 
+struct GradDesc;
+void grad_desc_destroy(GradDesc* gd);
+
 struct Plan {
   // ---- host copies ----
   int d = 0, p = 0, p_pad = 0;          // p_pad = p rounded up to kTileN
@@ -51,6 +54,7 @@ struct Plan {
   int* d_group_begin = nullptr;         // G+1
   uint16_t* d_col_slot = nullptr;       // p_pad x G
   int device = 0;
+  GradDesc* grad = nullptr;             // set by grief_grad_setup
   ~Plan();
 };
 

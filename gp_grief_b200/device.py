@@ -133,6 +133,50 @@ class DevicePlan(object):
         return out
 
 
+    # ---- pass 2: analytic hyper-parameter gradient ----
+    def grad_setup(self, dims, kinds, dqs_list):
+        """Declare the active parameters: dims[a], kinds[a] (0 variance, 1 lengthscale), dqs_list[a] (m_i, u_i)."""
+        na = len(dims)
+        dims_a = np.ascontiguousarray(dims, dtype=np.int32)
+        kinds_a = np.ascontiguousarray(kinds, dtype=np.int32)
+        dqs = np.concatenate([np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in dqs_list]) if na else np.zeros(1)
+        nat.check(nat.lib().grief_grad_setup(self._h, na, nat.host_ptr(dims_a), nat.host_ptr(kinds_a), nat.host_ptr(dqs)))
+        self.n_active = na
+
+    def grad_theta(self, T, X_dev, y_dev, n, G2, b, noise_var):
+        torch = _torch()
+        g = torch.zeros((max(self.n_active, 1),), dtype=torch.float64, device=T.device)
+        need = nat.lib().grief_grad_workspace_bytes(self._h, n)
+        ws = torch.empty((max(need, 256),), dtype=torch.uint8, device=T.device)
+        ldx = X_dev.stride(0) if n > 1 else self.d
+        G2 = _even_ld(G2)
+        nat.check(nat.lib().grief_grad_theta(self._h, nat.dev_ptr(T), nat.dev_ptr(X_dev), ldx, nat.dev_ptr(y_dev), n,
+                                             nat.dev_ptr(G2), G2.stride(0), nat.dev_ptr(b), float(noise_var),
+                                             nat.dev_ptr(g), nat.dev_ptr(ws), ws.numel(), nat.stream_ptr()))
+        return g[:self.n_active]
+
+    def quadform_rows(self, T, n, B):
+        """q[i] = phi_i^T B phi_i for a symmetric (p, p) device matrix B."""
+        torch = _torch()
+        q = torch.empty((n,), dtype=torch.float64, device=T.device)
+        need = nat.lib().grief_quadform_workspace_bytes(self._h, n)
+        ws = torch.empty((max(need, 256),), dtype=torch.uint8, device=T.device)
+        B = _even_ld(B)
+        nat.check(nat.lib().grief_quadform_rows(self._h, nat.dev_ptr(T), n, nat.dev_ptr(B), B.stride(0), nat.dev_ptr(q),
+                                                nat.dev_ptr(ws), ws.numel(), nat.stream_ptr()))
+        return q
+
+
+def _even_ld(B):
+    """TMA needs 16-byte row strides: give an odd-sized symmetric matrix a padded copy (tiny p only)."""
+    if B.stride(0) % 2 == 0:
+        return B
+    import torch
+    pad = torch.zeros((B.shape[0], B.shape[1] + 1), dtype=B.dtype, device=B.device)
+    pad[:, :B.shape[1]] = B
+    return pad
+
+
 def sumsq(y_dev):
     torch = _torch()
     out = torch.empty((1,), dtype=torch.float64, device=y_dev.device)

@@ -1,0 +1,301 @@
+"""GP-GRIEF regression model on the B200 (reference: gp_grief/models/gp_grief_model.py).
+
+Same class, constructor and methods as the reference.  Data rows live on the GPU; one evaluation is
+    prepass tables  ->  fused Gram A = Phi^T Phi, r = Phi^T y, s = y^T y   (csrc/rows.cu, csrc/gram_syrk.cu)
+    [all-reduce of (A | r | s) when the rows are sharded over ranks]
+    Cholesky / solve / LML / d/dw / d/dnoise_var                           (csrc/solve.cu)
+    analytic d/d(kernel hyper-parameters)                                  (csrc/zgemm.cu, csrc/grad.cu)
+and Phi (n x p) is never formed.  Differences from the reference that a caller can observe:
+  * `_Phi`, `_alpha` are computed on demand (they are n-sized); `_A`, `_P`, `_Pchol` are host copies.
+  * with `opt_kernel_params=True` and distinct in-house kernels the default `grad_method` is the analytic
+    'adjoint' path; the reference can only finite-difference there (gp_grief_model.py:71-74,194-196).
+    Set `m.grad_method = 'finite_difference'` to reproduce the reference's gradient bit-for-bit in method.
+  * `predict(Xnew, compute_var='diag')` returns the marginal variances without the M x M covariance.
+There is no CPU path: constructing the model without a CUDA device raises.
+"""
+from logging import getLogger
+
+import numpy as np
+
+from ..kern import BaseKernel, GriefKernel
+from .basemodel import BaseModel
+
+logger = getLogger(__name__)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class GPGriefModel(BaseModel):
+    """GP with GRId-structured Eigen Functions."""
+
+    _CACHE_NAMES = ('_A', '_P', '_Pchol', '_alpha', '_alpha_p', '_Phi', '_X_last_pred', '_Phi_last_pred')
+
+    def __init__(self, X, Y, kern, noise_var=1., distributed=False):
+        """X (n, d), Y (n, 1), kern a GriefKernel.  With distributed=True, X and Y are this rank's row shard of a
+        torch.distributed job (NCCL); the statistics are all-reduced and every rank gets identical results."""
+        super(GPGriefModel, self).__init__()
+        assert X.ndim == 2
+        assert Y.ndim == 2
+        self.X = np.asarray(X)
+        self.Y = np.asarray(Y)
+        assert not np.any(np.isnan(Y))
+        self.num_local, self.input_dim = self.X.shape
+        if Y.shape[0] != self.num_local:
+            raise ValueError('X and Y sizes are inconsistent')
+        self.output_dim = self.Y.shape[1]
+        if self.output_dim != 1:
+            raise RuntimeError('this only deals with 1 response for now')
+        assert isinstance(kern, GriefKernel)
+        assert np.ndim(kern.kern_list) == 1
+        for ki in kern.kern_list:
+            assert isinstance(ki, BaseKernel)
+            assert ki.n_dims == 1, "currently only 1-dimensional grids allowed"
+        self.kern = kern
+        self.noise_var = np.float64(noise_var)
+
+        import torch
+        from .. import device
+        self._torch = torch
+        self._device_mod = device
+        device._torch()                                  # raises if there is no CUDA device
+        self._dist = _dist() if distributed else None
+        self.num_data = self.num_local
+        if self._dist is not None:
+            cnt = torch.tensor([self.num_local], dtype=torch.int64, device="cuda")
+            self._dist.all_reduce(cnt)
+            self.num_data = int(cnt.item())
+        self._X_dev = torch.as_tensor(np.ascontiguousarray(self.X, dtype=np.float64)).cuda()
+        self._y_dev = torch.as_tensor(np.ascontiguousarray(self.Y[:, 0], dtype=np.float64)).cuda()
+        self._solver = device.DeviceSolver()
+        self._dev = {}                                   # device-resident caches (tensors)
+        self._host = {}                                  # lazily copied host views of the caches
+
+        self.dependent_attributes = np.unique(np.concatenate(
+            (self.dependent_attributes, ['_P', '_Pchol', '_alpha_p'])))
+        if self.kern.opt_kernel_params:
+            self.dependent_attributes = np.unique(np.concatenate(
+                (self.dependent_attributes, ['_A', '_Phi', '_X_last_pred', '_Phi_last_pred'])))
+            analytic_ok = not self.kern.has_aliased_kernels()
+            self.grad_method = 'adjoint' if analytic_ok else 'finite_difference'
+        else:
+            self.grad_method = 'adjoint'
+
+    # ------------------------------------------------------------------ cache attributes of the reference
+    # The reference invalidates by `setattr(self, name, None)`; these properties route that to the device caches.
+    def __getattr__(self, name):
+        if name in GPGriefModel._CACHE_NAMES:
+            return self._get_cache(name)
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in GPGriefModel._CACHE_NAMES:
+            self._set_cache(name, value)
+        else:
+            object.__setattr__(self, name, value)
+
+    def _set_cache(self, name, value):
+        host, dev = self.__dict__.get('_host'), self.__dict__.get('_dev')
+        if host is None:
+            return
+        if value is None:
+            host.pop(name, None)
+            if name == '_A':
+                for k in ('stats', 'tables', 'plan_id'):
+                    dev.pop(k, None)
+            if name in ('_P', '_Pchol'):
+                for k in ('solve',):
+                    dev.pop(k, None)
+            if name == '_Phi_last_pred':
+                dev.pop('pred', None)
+        else:
+            host[name] = value
+
+    def _get_cache(self, name):
+        host, dev = self._host, self._dev
+        if name in host:
+            return host[name]
+        t = self._torch
+        if name == '_A':
+            if 'stats' not in dev:
+                return None
+            host[name] = dev['stats']['A'].cpu().numpy()
+        elif name == '_P':
+            if 'solve' not in dev:
+                return None
+            host[name] = self._get_cache('_A') + np.diag(self.noise_var / self._w)
+        elif name == '_Pchol':
+            if 'solve' not in dev:
+                return None
+            host[name] = (dev['solve']['L'].cpu().numpy(), False)      # upper factor, scipy cho_factor convention
+        elif name == '_alpha_p':
+            if 'solve' not in dev:
+                return None
+            host[name] = dev['solve']['b'].cpu().numpy().reshape((-1, 1))
+        elif name == '_alpha':
+            if 'solve' not in dev:
+                return None
+            plan = self.kern.device_plan()
+            fitted = plan.phi_vec(dev['tables'], self.num_local, dev['solve']['b'])
+            host[name] = ((self._y_dev - fitted) / float(self.noise_var)).cpu().numpy().reshape((-1, 1))
+        elif name == '_Phi':
+            if 'tables' not in dev:
+                return None
+            plan = self.kern.device_plan()
+            host[name] = plan.phi_rows(dev['tables'], self.num_local).cpu().numpy()
+        else:
+            return None
+        return host[name]
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, **kwargs):
+        """Reduced statistics, Cholesky of P and alpha_p = P^-1 Phi^T y (reference :78-87)."""
+        self.parameters
+        self._cov_setup()
+
+    def _stats(self):
+        """A = Phi^T Phi, r = Phi^T y, s = y^T y on the device (all-reduced over ranks), cached like `_A`."""
+        dev = self._dev
+        if 'stats' in dev:
+            return dev['stats']
+        t = self._torch
+        plan = self.kern.device_plan()
+        p = plan.p
+        T = plan.build_tables(self._X_dev)
+        buf = t.zeros((p * p + p + 1,), dtype=t.float64, device="cuda")
+        A = buf[:p * p].view(p, p)
+        r = buf[p * p:p * p + p]
+        s = buf[p * p + p:]
+        ws = dev.get('gram_ws')
+        need = plan.gram_workspace_bytes(self.num_local)
+        if ws is None or ws.numel() < need:
+            ws = t.empty((need,), dtype=t.uint8, device="cuda")
+            dev['gram_ws'] = ws
+        plan.gram(T, self.num_local, out=A, workspace=ws)
+        plan.phi_t_vec(T, self.num_local, self._y_dev, out=r)
+        s.copy_(self._device_mod.sumsq(self._y_dev))
+        if self._dist is not None:
+            self._dist.all_reduce(buf)
+        dev['tables'] = T
+        dev['stats'] = dict(A=A, r=r, s=s, buf=buf)
+        return dev['stats']
+
+    def _cov_setup(self, want_grad=False, want_G2=False):
+        dev = self._dev
+        have = dev.get('solve')
+        if have is not None and (have['Pinv'] is not None or not (want_grad or want_G2)) and \
+                (have['G2'] is not None or not want_G2):
+            return have
+        self._w = self.kern.w
+        st = self._stats()
+        w_dev = self._torch.as_tensor(np.ascontiguousarray(self._w, dtype=np.float64)).cuda()
+        out = self._solver.solve(st['A'], st['r'], st['s'], w_dev, float(self.noise_var), self.num_data,
+                                 want_grad=want_grad or want_G2, want_G2=want_G2)
+        dev['solve'] = out
+        for k in ('_P', '_Pchol', '_alpha', '_alpha_p'):
+            self._host.pop(k, None)
+        return out
+
+    # ------------------------------------------------------------------ likelihood and gradients
+    def _compute_log_likelihood(self, parameters):
+        """log N(y | 0, Phi W Phi^T + noise_var I), returned as a (1, 1) array like the reference (:203-214)."""
+        self.parameters = parameters
+        out = self._cov_setup()
+        return np.array([[out['lml']]])
+
+    def _adjoint_gradient(self, parameters):
+        """(log likelihood, gradient); NaN in the slots of fixed parameters (reference :156-200)."""
+        assert isinstance(parameters, np.ndarray)
+        self.parameters = parameters
+        free = np.logical_not(self._fixed_indicies)
+        gradient = np.zeros(parameters.shape) + np.nan
+        n_base = parameters.size - 1 - self.kern.n_eigs
+        theta_free = np.nonzero(free[1:1 + n_base])[0]
+        need_theta = self.kern.opt_kernel_params and theta_free.size > 0
+        out = self._cov_setup(want_grad=True, want_G2=need_theta)
+        log_like = np.array([[out['lml']]])
+        if self.kern.reweight_eig_funs:
+            gradient[-self.kern.n_eigs:] = out['grad_w'].cpu().numpy()
+        if self.noise_var_constraint != 'fixed':
+            gradient[0] = out['grad_noise']
+        if need_theta:
+            if self.kern.has_aliased_kernels():
+                raise NotImplementedError("analytic kernel-parameter gradient needs distinct kernel objects per dimension; "
+                                          "use grad_method='finite_difference'")
+            pmap = self.kern.base_parameter_map()
+            active = [pmap[i] for i in theta_free]
+            gradient[1 + theta_free] = self._theta_gradient(active, out)
+        assert not np.any(np.isnan(gradient[free])), "gradient missed!"
+        return log_like, gradient
+
+    def _theta_gradient(self, active, solve_out):
+        """d LML / d theta for the active base-kernel parameters [(dim, kind)] (pass 2 on the device)."""
+        t = self._torch
+        plan = self.kern.device_plan()
+        dqs = self.kern.scaled_eigvec_derivatives(active)
+        plan.grad_setup([a[0] for a in active], [0 if a[1] == 'variance' else 1 for a in active], dqs)
+        g = plan.grad_theta(self._dev['tables'], self._X_dev, self._y_dev, self.num_local, solve_out['G2'],
+                            solve_out['b'], float(self.noise_var))
+        if self._dist is not None:
+            self._dist.all_reduce(g)
+        return g.cpu().numpy()
+
+    # ------------------------------------------------------------------ prediction
+    def predict_precompute(self, Xnew):
+        logger.debug('Predicting model at new points.')
+        assert Xnew.ndim == 2
+        assert Xnew.shape[1] == self.input_dim
+        self.parameters
+        self._cov_setup()
+
+    def predict(self, Xnew, compute_var='full'):
+        """Posterior mean (M, 1) and covariance at Xnew (reference :99-125).
+
+        compute_var: 'full' -> (M, M) covariance as the reference returns (small M only);
+                     'diag' -> (M, 1) marginal variances, computed without the M x M matrix; None -> mean only.
+        """
+        self.predict_precompute(Xnew)
+        t = self._torch
+        plan = self.kern.device_plan()
+        out = self._cov_setup(want_grad=compute_var is not None)
+        M = Xnew.shape[0]
+        Xd = t.as_tensor(np.ascontiguousarray(Xnew, dtype=np.float64)).cuda()
+        Tn = plan.build_tables(Xd)
+        Yhat = plan.phi_vec(Tn, M, out['b']).cpu().numpy().reshape((-1, 1))       # alpha_p == b
+        if compute_var is None:
+            return Yhat
+        nv = float(self.noise_var)
+        if compute_var == 'diag':
+            q = plan.quadform_rows(Tn, M, out['Pinv'])
+            return Yhat, (nv * (q + 1.0)).cpu().numpy().reshape((-1, 1))
+        Phi_new = plan.phi_rows(Tn, M)
+        Yhatvar = nv * (Phi_new @ (out['Pinv'] @ Phi_new.T)) + nv * t.eye(M, dtype=t.float64, device="cuda")
+        return Yhat, Yhatvar.cpu().numpy()
+
+    def d_Yhat_d_x(self, Xnew, dim):
+        """d Yhat / d x[:, dim] (reference :127-134)."""
+        self.predict_precompute(Xnew)
+        dPhi = self.kern.cov_grad(Xnew, dim)
+        return dPhi.dot(self._alpha_p)
+
+    # ------------------------------------------------------------------ covariance operators (inspection-sized n)
+    def _mv_cov(self, x):
+        """(Phi W Phi^T + noise_var I) x."""
+        assert x.shape[0] == self.num_local
+        Phi = self._Phi
+        assert Phi is not None, "cov has not been setup"
+        return Phi.dot(Phi.T.dot(x) * self._w.reshape((-1, 1))) + x * self.noise_var
+
+    def _mv_cov_inv(self, x):
+        """(Phi W Phi^T + noise_var I)^-1 x through the matrix inversion lemma."""
+        from scipy.linalg import cho_solve
+        assert x.shape[0] == self.num_local
+        assert self._Pchol is not None, "cov has not been setup"
+        Phi = self._Phi
+        return (x - Phi.dot(cho_solve(self._Pchol, Phi.T.dot(x)))) / self.noise_var
+
+    def _cov_log_det(self):
+        assert self._dev.get('solve') is not None, "cov has not been setup"
+        return self._dev['solve']['logdet']

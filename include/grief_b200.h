@@ -149,6 +149,36 @@ int grief_solve_lml(grief_ctx* ctx, int p, const double* A_dev, int64_t lda, con
                     double* b_dev, double* Pinv_dev, double* grad_w_dev, double* G2_dev, double* scalars_host,
                     int* info_host, void* stream);
 
+/*
+ * Analytic hyper-parameter gradient (pass 2).  The reference has no counterpart: for kernel
+ * hyper-parameters it falls back to forward finite differences (models/gp_grief_model.py:71-74,
+ * :194-196; models/basemodel.py:328-361), i.e. (#free + 1) complete evaluations.
+ *
+ * grief_grad_setup: declare the parameters to differentiate.
+ *   dims[a], kinds[a]   input dimension and kind (0 = variance, 1 = lengthscale) of active parameter a
+ *   dqs_concat          per active parameter an (m_i, u_i) row-major matrix d(qs_i)/d(theta_a): derivative of
+ *                       the scaled eigenvectors passed to grief_plan_create (host-side eigen-perturbation)
+ * grief_grad_theta: grad_dev[a] = d LML / d theta_a for the rows given (a row shard when multi-GPU: sum over
+ *   ranks), holding the selected eigen-index set fixed (as finite differences implicitly do).
+ *   T_dev          tables of the n rows (grief_build_tables)
+ *   G2_dev, ldg    -(P^-1 + b b^T/noise_var) from grief_solve_lml, symmetric, ldg even
+ *   b_dev          P^-1 r from grief_solve_lml
+ */
+int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat);
+size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n);
+int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev,
+                     int64_t n, const double* G2_dev, int64_t ldg, const double* b_dev, double noise_var,
+                     double* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * q[n] = phi(x_n)^T B phi(x_n) for a symmetric (p,p) matrix B, phi built on the fly.
+ * With B = P^-1 this is the diagonal of Phi* P^-1 Phi*^T of models/gp_grief_model.py:122-124
+ * (predictive variance = noise_var * (q + 1)).
+ */
+size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n);
+int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb,
+                        double* q_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,18 +115,35 @@ def run_model_case(name, x, y, xg, kernel_name, variances, lengthscales, n_eigs,
     if type2:
         ll, g = m._finite_diff_gradient(params.copy())
         out["grad_fd"] = g
-        # central differences with Richardson extrapolation (oracle-quality theta gradient)
+        # central differences with Richardson extrapolation of the REFERENCE's LML.  The LML jumps wherever the
+        # selected eigen-index set changes, so the step is shrunk until all four evaluation points keep the
+        # base point's selection (then the difference quotient is taken on one smooth branch).
         free = np.nonzero(np.logical_not(m._fixed_indicies))[0]
+        base_sel = [np.sort(np.ravel_multi_index(np.array([s_.indicies for s_ in kern._Sp]),
+                                                 [int(s_.shape[1]) for s_ in kern._Sp]))]
         gc = np.zeros(params.shape)
+        steps = np.zeros(params.shape)
         for idx in free:
-            def f(h):
-                p1 = params.copy(); p1[idx] += h
-                p2 = params.copy(); p2[idx] -= h
-                return (float(np.asarray(m._compute_log_likelihood(p1)).squeeze()) -
-                        float(np.asarray(m._compute_log_likelihood(p2)).squeeze())) / (2 * h)
-            h = 1e-3 * max(1.0, abs(params[idx]))
-            d1, d2 = f(h), f(h / 2)
+            def f(hh):
+                vals = []
+                for sgn in (+1, -1):
+                    pp = params.copy(); pp[idx] += sgn * hh
+                    vals.append(float(np.asarray(m._compute_log_likelihood(pp)).squeeze()))
+                    sel = np.sort(np.ravel_multi_index(np.array([s_.indicies for s_ in kern._Sp]),
+                                                       [int(s_.shape[1]) for s_ in kern._Sp]))
+                    if not np.array_equal(sel, base_sel[0]):
+                        return None
+                return (vals[0] - vals[1]) / (2 * hh)
+            h = 2e-4 * max(1.0, abs(params[idx]))
+            while True:
+                d1, d2 = f(h), f(h / 2)
+                if d1 is not None and d2 is not None:
+                    break
+                h /= 4
+                assert h > 1e-9
             gc[idx] = (4 * d2 - d1) / 3
+            steps[idx] = h
+        out["grad_central_step"] = steps
         out["grad_central"] = gc
         out["free"] = free
         m.parameters = params
