@@ -24,6 +24,9 @@ SIGNATURES = {
     "grief_last_error": (ctypes.c_char_p, []),
     "grief_launch_count": (c_int, []),
     "grief_launch_count_reset": (None, []),
+    "grief_profile_enable": (None, [c_int]),
+    "grief_profile_slots": (c_int, []),
+    "grief_profile_read": (None, [c_void, c_void]),
     "grief_ctx_create": (c_int, [_P(c_void)]),
     "grief_ctx_destroy": (None, [c_void]),
     "grief_topk_kron": (c_int, [c_int, c_void, c_void, c_void, c_int, c_void, c_void, _P(c_int), c_void]),
@@ -94,6 +97,22 @@ def check(rc):
     if rc == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise RuntimeError("libgrief_b200 error %d: %s" % (rc, msg))
+
+
+PROFILE_SLOTS = ("k_gram", "k_zgemm", "k_tables", "k_contract", "k_topk", "solve", "phi_t_y", "k_dtables")
+
+
+def profile_enable(on=True):
+    lib().grief_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{slot name: (milliseconds, launches)} accumulated since the last read."""
+    n = lib().grief_profile_slots()
+    ms = np.zeros(n, dtype=np.float64)
+    cnt = np.zeros(n, dtype=np.int32)
+    lib().grief_profile_read(host_ptr(ms), host_ptr(cnt))
+    return {PROFILE_SLOTS[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def host_ptr(a):

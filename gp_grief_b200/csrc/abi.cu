@@ -3,6 +3,8 @@
 
 namespace grief {
 const char* last_error_cstr();
+void prof_enable(bool on);
+void prof_read(double* ms, int* count);
 struct SolveCtx;
 int solve_ctx_create(SolveCtx** out);
 void solve_ctx_destroy(SolveCtx* c);
@@ -66,6 +68,10 @@ int grief_version(void) { return 100; }
 const char* grief_last_error(void) { return last_error_cstr(); }
 int grief_launch_count(void) { return g_launches; }
 void grief_launch_count_reset(void) { g_launches = 0; }
+
+void grief_profile_enable(int on) { prof_enable(on != 0); }
+int grief_profile_slots(void) { return PROF_COUNT; }
+void grief_profile_read(double* ms_out, int* count_out) { prof_read(ms_out, count_out); }
 
 int grief_ctx_create(grief_ctx** ctx) {
   GRIEF_REQUIRE(ctx != nullptr, "grief_ctx_create: null");

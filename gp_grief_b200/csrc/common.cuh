@@ -30,6 +30,11 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return ::grief::fail(GRIEF_ERR_BAD_ARG, __VA_ARGS__); \
   } while (0)
 
+// ---- optional per-kernel timing (CUDA events on the launch stream; off by default) --------------------
+enum ProfSlot : int { PROF_GRAM = 0, PROF_ZGEMM, PROF_TABLES, PROF_CONTRACT, PROF_TOPK, PROF_SOLVE, PROF_PHITY, PROF_DTABLES, PROF_COUNT };
+void prof_begin(int slot, cudaStream_t stream);
+void prof_end(int slot, cudaStream_t stream);
+
 // ---- shape constants shared by host and device ------------------------------------------------
 constexpr int kMaxDims = 64;       // input dimensions
 constexpr int kMaxGrid = 64;       // grid points per dimension

@@ -360,7 +360,9 @@ int launch_dtables(const Plan* pl, const GradDesc* gd, const double* X, int64_t 
   const size_t smem = per_row * RB;
   GRIEF_CUDA(cudaFuncSetAttribute(k_dtables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (rows_total + RB - 1) / RB;
+  prof_begin(PROF_DTABLES, stream);
   k_dtables<<<(unsigned)blocks, 256, smem, stream>>>(P, rows_total);
+  prof_end(PROF_DTABLES, stream);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
@@ -386,17 +388,21 @@ int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t
   const size_t smem = ((size_t)nw * (pl->stride + gd->dt_width) + (size_t)nw * gd->n_active) * sizeof(double);
   if (smem > 200 * 1024) return fail(GRIEF_ERR_UNSUPPORTED, "contract: %zu bytes of shared memory per block", smem);
   const int blocks = contract_blocks(sms);
+  int rc;
+  prof_begin(PROF_CONTRACT, stream);
   switch (pl->n_groups) {
-    case 1: return launch_contract_g<1>(P, blocks, smem, stream);
-    case 2: return launch_contract_g<2>(P, blocks, smem, stream);
-    case 3: return launch_contract_g<3>(P, blocks, smem, stream);
-    case 4: return launch_contract_g<4>(P, blocks, smem, stream);
-    case 5: return launch_contract_g<5>(P, blocks, smem, stream);
-    case 6: return launch_contract_g<6>(P, blocks, smem, stream);
-    case 7: return launch_contract_g<7>(P, blocks, smem, stream);
-    case 8: return launch_contract_g<8>(P, blocks, smem, stream);
+    case 1: rc = launch_contract_g<1>(P, blocks, smem, stream); break;
+    case 2: rc = launch_contract_g<2>(P, blocks, smem, stream); break;
+    case 3: rc = launch_contract_g<3>(P, blocks, smem, stream); break;
+    case 4: rc = launch_contract_g<4>(P, blocks, smem, stream); break;
+    case 5: rc = launch_contract_g<5>(P, blocks, smem, stream); break;
+    case 6: rc = launch_contract_g<6>(P, blocks, smem, stream); break;
+    case 7: rc = launch_contract_g<7>(P, blocks, smem, stream); break;
+    case 8: rc = launch_contract_g<8>(P, blocks, smem, stream); break;
     default: return fail(GRIEF_ERR_UNSUPPORTED, "contract: %d groups", pl->n_groups);
   }
+  prof_end(PROF_CONTRACT, stream);
+  return rc;
 }
 
 int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream) {

@@ -330,6 +330,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   const int grid = std::min(sms, s.n_items);
   int rc = GRIEF_OK;
   if (s.n_chunks > 0) {
+    prof_begin(PROF_GRAM, stream);
     switch (G) {
       case 1: rc = launch_gram_g<1>(pl, prm, grid, smem, stream); break;
       case 2: rc = launch_gram_g<2>(pl, prm, grid, smem, stream); break;
@@ -341,6 +342,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
       case 8: rc = launch_gram_g<8>(pl, prm, grid, smem, stream); break;
       default: return fail(GRIEF_ERR_UNSUPPORTED, "gram: %d groups", G);
     }
+    prof_end(PROF_GRAM, stream);
     if (rc != GRIEF_OK) return rc;
   } else {
     GRIEF_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)s.n_items * kTileN * kTileN * sizeof(double), stream));

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <numeric>
+#include <vector>
 
 namespace grief {
 
@@ -21,6 +22,41 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   g_last_error = buf;
   return code;
+}
+
+// ---- per-kernel timing ----
+struct ProfRec { int slot; cudaEvent_t e0, e1; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof_recs;
+static thread_local std::vector<cudaEvent_t> g_prof_open(PROF_COUNT, nullptr);
+
+void prof_enable(bool on) { g_prof_on = on; }
+void prof_begin(int slot, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  g_prof_open[slot] = e;
+}
+void prof_end(int slot, cudaStream_t stream) {
+  if (!g_prof_on || !g_prof_open[slot]) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  g_prof_recs.push_back({slot, g_prof_open[slot], e});
+  g_prof_open[slot] = nullptr;
+}
+// sums (ms) and launch counts per slot since the last read; synchronises on the recorded events
+void prof_read(double* ms, int* count) {
+  for (int i = 0; i < PROF_COUNT; ++i) { ms[i] = 0.0; count[i] = 0; }
+  for (auto& r : g_prof_recs) {
+    cudaEventSynchronize(r.e1);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms[r.slot] += t; count[r.slot] += 1; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.clear();
 }
 
 Plan::~Plan() {

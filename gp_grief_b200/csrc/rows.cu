@@ -107,9 +107,11 @@ int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64
   GRIEF_CUDA(cudaFuncSetAttribute(k_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (n_pad + RB - 1) / RB;
   if (blocks == 0) return GRIEF_OK;
+  prof_begin(PROF_TABLES, stream);
   k_tables<<<(unsigned)blocks, 256, smem, stream>>>(pl->d_dims, pl->d_grid, pl->d_qs, pl->d_slot_k, pl->d_slot_group,
                                                     pl->d_group_begin, pl->d, pl->sum_m, pl->sum_u, pl->width,
                                                     pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB);
+  prof_end(PROF_TABLES, stream);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
@@ -202,9 +204,11 @@ int launch_phi_t_vec(const Plan* pl, const double* T, int64_t n, const double* v
   rpb = (rpb + 31) / 32 * 32;
   const size_t smem = ((size_t)32 * pl->stride + 32) * sizeof(double);
   GRIEF_CUDA(cudaFuncSetAttribute(k_phi_t_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(PROF_PHITY, stream);
   k_phi_t_vec<<<nblk, 256, smem, stream>>>(T, pl->stride, pl->d_col_slot, pl->n_groups, pl->p, n, rpb, v, ws);
   GRIEF_CUDA(cudaGetLastError());
   k_reduce_rows<<<(pl->p + 255) / 256, 256, 0, stream>>>(ws, nblk, pl->p, out);
+  prof_end(PROF_PHITY, stream);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }

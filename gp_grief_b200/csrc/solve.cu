@@ -163,6 +163,7 @@ int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* 
     ctx->lwork = lwork;
   }
   const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)p * p + 255) / 256, 148 * 8);
+  prof_begin(PROF_SOLVE, stream);
   k_form_P<<<eb, 256, 0, stream>>>(A, lda, w, noise, p, L);
   GRIEF_CUDA(cudaGetLastError());
   if (cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, p, L, p, ctx->work, ctx->lwork, ctx->d_info) != CUSOLVER_STATUS_SUCCESS)
@@ -188,6 +189,7 @@ int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* 
     k_form_G2<<<eb, 256, 0, stream>>>(Pinv, b, noise, p, G2);
     GRIEF_CUDA(cudaGetLastError());
   }
+  prof_end(PROF_SOLVE, stream);
   GRIEF_CUDA(cudaMemcpyAsync(scalars_host, ctx->d_scalars, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
   GRIEF_CUDA(cudaStreamSynchronize(stream));
   if (launches) *launches += 2 + (Pinv ? 1 : 0) + (G2 ? 1 : 0);

@@ -256,7 +256,9 @@ int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const dou
   const size_t smem = (size_t)N * (sizeof(double) + sizeof(int));
   cudaError_t e3 = cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e3 == cudaSuccess) {
+    prof_begin(PROF_TOPK, stream);
     k_topk<<<1, kTopkThreads, smem, stream>>>(P);
+    prof_end(PROF_TOPK, stream);
     e3 = cudaGetLastError();
   }
   int n_out = 0;

@@ -238,6 +238,7 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   const size_t smem = fixed + (size_t)nb * kZBStageBytes;
   const int grid = std::min(sms, prm.n_row_blocks);
   int rc;
+  prof_begin(PROF_ZGEMM, stream);
   switch (pl->n_groups) {
     case 1: rc = launch_zgemm_g<1>(map, prm, grid, smem, stream); break;
     case 2: rc = launch_zgemm_g<2>(map, prm, grid, smem, stream); break;
@@ -249,6 +250,7 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
     case 8: rc = launch_zgemm_g<8>(map, prm, grid, smem, stream); break;
     default: return fail(GRIEF_ERR_UNSUPPORTED, "zgemm: %d groups", pl->n_groups);
   }
+  prof_end(PROF_ZGEMM, stream);
   if (rc == GRIEF_OK && launches) *launches += 1;
   return rc;
 }

@@ -164,10 +164,12 @@ class GPGriefModel(BaseModel):
         plan = self.kern.device_plan()
         p = plan.p
         T = plan.build_tables(self._X_dev)
-        buf = t.zeros((p * p + p + 1,), dtype=t.float64, device="cuda")
-        A = buf[:p * p].view(p, p)
-        r = buf[p * p:p * p + p]
-        s = buf[p * p + p:]
+        from ..sharding import stats_layout
+        lay = stats_layout(p)
+        buf = t.zeros((lay["size"],), dtype=t.float64, device="cuda")
+        A = buf[lay["A"][0]:lay["A"][1]].view(p, p)
+        r = buf[lay["r"][0]:lay["r"][1]]
+        s = buf[lay["s"][0]:lay["s"][1]]
         ws = dev.get('gram_ws')
         need = plan.gram_workspace_bytes(self.num_local)
         if ws is None or ws.numel() < need:

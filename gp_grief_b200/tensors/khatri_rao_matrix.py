@@ -17,7 +17,7 @@ from .selection_matrix import SelectionMatrix, SelectionMatrixSparse
 class KhatriRaoMatrix(BlockMatrix):
     def __init__(self, A, partition=None):
         """A: list of equal-height (partition=0) or equal-width (partition=1) matrices, or a 2-D array of KronMatrix."""
-        if np.ndim(A) == 2 and isinstance(A[0, 0], KronMatrix):
+        if isinstance(A, np.ndarray) and A.ndim == 2 and isinstance(A[0, 0], KronMatrix):   # (np.ndim of a ragged list raises)
             super(KhatriRaoMatrix, self).__init__(A)
             return
         assert partition in range(2)

@@ -59,6 +59,16 @@ const char* grief_last_error(void);
 int grief_launch_count(void);
 void grief_launch_count_reset(void);
 
+/*
+ * Optional per-kernel timing for benchmarks: CUDA events are recorded on the launch stream around the kernels
+ * of each slot.  Slots: 0 fused Gram (k_gram), 1 fused Phi*B GEMM (k_zgemm), 2 table prepass, 3 gradient
+ * contraction, 4 top-p select, 5 p x p stage, 6 Phi^T y, 7 derivative tables.  grief_profile_read synchronises,
+ * writes the accumulated milliseconds and launch counts of every slot (arrays of grief_profile_slots()) and resets.
+ */
+void grief_profile_enable(int on);
+int grief_profile_slots(void);
+void grief_profile_read(double* ms_out, int* count_out);
+
 int grief_ctx_create(grief_ctx** ctx);
 void grief_ctx_destroy(grief_ctx* ctx);
 

@@ -1,0 +1,172 @@
+"""CPU-only tests: host logic of the package, the C-ABI export surface, and the no-fallback guarantee."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from conftest import load_golden, case_inputs, ROOT
+from oracle import grief_oracle as orc
+
+import gp_grief_b200 as gp
+from gp_grief_b200 import _native
+
+
+def test_library_exports_every_symbol_of_the_header():
+    """The shared library loads without a GPU and exports exactly what include/grief_b200.h declares."""
+    assert os.path.exists(_native.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "grief_b200.h")).read()
+    declared = set(re.findall(r"\b(grief_[a-z0-9_]+)\s*\(", header))
+    declared -= {"grief_plan", "grief_ctx"}
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
+    assert declared == set(_native.SIGNATURES), (declared ^ set(_native.SIGNATURES))
+    assert lib.grief_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g = load_golden("syn_t1_n2000_d4_m8_p64")
+    d = 4
+    grid = gp.grid.InducingGrid(xg=[g["xg_%d" % i].reshape(-1, 1) for i in range(d)])
+    kern = gp.kern.GriefKernel([gp.kern.RBF(1, lengthscale=0.3 + 0.05 * i) for i in range(d)], grid, n_eigs=64)
+    with pytest.raises(RuntimeError):
+        gp.models.GPGriefModel(g["x"], g["y"], kern, noise_var=0.1)
+    with pytest.raises(RuntimeError):
+        kern.cov(g["x"][:5])
+    assert not any("oracle" in m for m in __import__("sys").modules if m.startswith("gp_grief_b200"))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gp_grief_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("name", ["RBF", "Exponential", "Matern32", "Matern52"])
+def test_kernels_match_oracle_and_derivatives(name):
+    rng = np.random.default_rng(0)
+    x, z = rng.random((7, 1)), rng.random((5, 1))
+    k = getattr(gp.kern, name)(1, variance=1.3, lengthscale=0.45)
+    assert_array_equal(k.cov(x, z), orc.kernel_cov(name, x[:, 0], z[:, 0], 1.3, 0.45))
+    h = 1e-6
+    kp = getattr(gp.kern, name)(1, variance=1.3, lengthscale=0.45 + h)
+    km = getattr(gp.kern, name)(1, variance=1.3, lengthscale=0.45 - h)
+    assert_allclose(k.grad_lengthscale(x, z), (kp.cov(x, z) - km.cov(x, z)) / (2 * h), rtol=1e-6, atol=1e-8)
+    assert_allclose(k.grad_variance(x, z), k.cov(x, z) / 1.3, rtol=1e-14)
+    assert_allclose(k.grad_x(x, z), (k.cov(x + h, z) - k.cov(x - h, z)) / (2 * h), rtol=1e-5, atol=1e-7)
+    assert_array_equal(k.parameters, [1.3, 0.45])
+    assert list(k.constraints) == ['+ve', '+ve']
+
+
+def test_grid_kernel_factors_bit_identical_to_reference():
+    """cov_grid + schur reproduce the reference's Schur vectors bit for bit (inputs of the top-p selection)."""
+    g = load_golden("syn_t1_ragged_n700_d5_p40")
+    c = case_inputs(g)
+    d = c["d"]
+    grid = gp.grid.InducingGrid(xg=[x.reshape(-1, 1) for x in c["xg"]])
+    assert_array_equal(grid.grid_shape, [7, 1, 2, 12, 5])
+    gk = gp.kern.GridKernel([gp.kern.RBF(1, variance=c["variances"][i], lengthscale=c["lengthscales"][i]) for i in range(d)])
+    Kuu = gk.cov_grid(grid.xg, dim_noise_var=1e-12)
+    Q, T = Kuu.schur()
+    for k in range(d):
+        assert_array_equal(Q.K[k], g["Q_%d" % k])
+    assert list(gk.constraints) == ['+ve', '+ve'] + ['fixed', '+ve'] * (d - 1)
+
+
+def test_inducing_grid_from_data():
+    np.random.seed(0)
+    x = np.random.rand(100, 3)
+    x[:, 2] = np.round(x[:, 2] * 3) / 3
+    grid = gp.grid.InducingGrid(x)
+    assert_array_equal(grid.grid_shape, [10, 10, 4])
+    assert grid.num_data == 400.0 and grid.input_dim == 3
+    assert_allclose(grid.xg[0][:, 0], np.linspace(x[:, 0].min(), x[:, 0].max(), 10))
+    assert_array_equal(grid.xg[2][:, 0], np.unique(x[:, 2]))
+    g2 = gp.grid.InducingGrid(x, mbar=5, beyond_domain=0.1)
+    assert_array_equal(g2.grid_shape, [5, 5, 4])
+    assert g2.xg[0][0, 0] < x[:, 0].min() and g2.xg[0][-1, 0] > x[:, 0].max()
+    assert gp.grid.grid2mat(np.arange(2), np.arange(3)).shape == (6, 2)
+
+
+def test_tensor_types_host():
+    """tests/test_tensors/* of the reference, restated: KR mat-vecs, logged expansion with zeros, selections."""
+    np.random.seed(0)
+    T = gp.tensors
+    A = [np.random.rand(5, 3), np.random.rand(5, 2), np.random.rand(5, 4)]
+    KR = T.KhatriRaoMatrix(A, partition=0)
+    dense = np.vstack([np.kron(np.kron(A[0][i], A[1][i]), A[2][i]) for i in range(5)])
+    assert_allclose(KR.expand(), dense)
+    x = np.random.rand(dense.shape[1], 1)
+    assert_allclose(KR * x, dense.dot(x))
+    assert_allclose(KR.T * np.ones((5, 1)), dense.T.dot(np.ones((5, 1))))
+    R = [np.random.rand(6, 3) for _ in range(2)]
+    K = [np.random.rand(3, 3) for _ in range(2)]
+    C = [np.random.rand(3, 4) for _ in range(2)]
+    R[0][1, :] = 0.
+    rkc = T.RowColKhatriRaoMatrix(R, K, C)
+    full = (R[0].dot(K[0]).dot(C[0])) * (R[1].dot(K[1]).dot(C[1]))
+    assert_allclose(rkc.expand(), full)
+    lg, sg = rkc.expand(logged=True)
+    assert_allclose(sg * np.exp(lg), full, atol=1e-15)
+    v = np.random.rand(4, 1)
+    assert_allclose(rkc * v, full.dot(v))
+    assert_allclose(rkc.T * np.ones((6, 1)), full.T.dot(np.ones((6, 1))))
+    idx = np.array([2, 0, 2, 1])
+    S = T.SelectionMatrixSparse((idx, 3))
+    M = np.random.rand(3, 5)
+    assert_array_equal(S.mul(M), M[idx])
+    assert_array_equal(S.mul_unique(M)[S.unique_inverse], M[idx])
+    assert_array_equal(T.SelectionMatrix((idx, 3)).mul(M), M[idx])
+    lp, sn = T.expand_SKC([S], [M.T[:3, :3]], [np.random.rand(3, 6)])
+    assert lp.shape == (4, 6)
+    assert_allclose(gp.linalg.log_kron(np.array([1., 2.]), np.array([3., 4., 5.])), np.log(np.kron([1., 2.], [3., 4., 5.])))
+
+
+def test_grief_kernel_parameter_plumbing():
+    g = load_golden("syn_t2_n2000_d4_m8_p64")
+    d = 4
+    grid = gp.grid.InducingGrid(xg=[g["xg_%d" % i].reshape(-1, 1) for i in range(d)])
+    kl = [gp.kern.RBF(1, lengthscale=0.3 + 0.05 * i) for i in range(d)]
+    kern = gp.kern.GriefKernel(kl, grid, n_eigs=64, reweight_eig_funs=False, opt_kernel_params=True)
+    assert_array_equal(kern.parameters, g["parameters"][1:])
+    assert list(kern.constraints) == [str(c) for c in g["constraints"][1:]]
+    p2 = kern.parameters
+    p2[1] = 0.77
+    kern.parameters = p2
+    assert kl[0].lengthscale == 0.77
+    assert kern.base_parameter_map()[:3] == [(0, 'variance'), (0, 'lengthscale'), (1, 'variance')]
+    assert not kern.has_aliased_kernels()
+    k1 = gp.kern.GriefKernel([gp.kern.RBF(1), ] * 3, gp.grid.InducingGrid(xg=[np.linspace(0, 1, 4).reshape(-1, 1)] * 3), n_eigs=1000)
+    assert k1.n_eigs == 64 and k1.has_aliased_kernels()
+    assert list(k1.constraints[:6]) == ['fixed'] * 6 and list(k1.constraints[6:8]) == ['+ve'] * 2
+
+
+def test_logexp_transform_roundtrip():
+    t = gp.linalg.LogexpTransformation()
+    f = np.array([1e-3, 0.5, 3.0, 40.0])
+    assert_allclose(t.inverse_transform(t.transform(f)), f, rtol=1e-12)
+    h = 1e-6
+    assert_allclose(t.transform_grad(f, np.ones(4)), (t.inverse_transform(t.transform(f) + h) - f) / h, rtol=1e-4)
+
+
+def test_sharding_and_layout():
+    from gp_grief_b200.sharding import row_shard, stats_layout
+    for n, w in [(10, 3), (7, 8), (10_000_000, 8), (5, 1)]:
+        cover = []
+        for r in range(w):
+            a, b = row_shard(n, w, r)
+            assert 0 <= a <= b <= n
+            cover += list(range(a, b)) if n < 100 else []
+        if n < 100:
+            assert cover == list(range(n))
+    lay = stats_layout(4)
+    assert lay["A"] == (0, 16) and lay["r"] == (16, 20) and lay["s"] == (20, 21) and lay["size"] == 21
