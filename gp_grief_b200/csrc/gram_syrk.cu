@@ -50,38 +50,45 @@ __device__ __forceinline__ void load_slots(const uint16_t* __restrict__ ip, int 
   for (int g = 0; g < G; ++g) s[g] = (g & 1) ? (int)(w[g >> 1] >> 16) : (int)(w[g >> 1] & 0xffffu);
 }
 
-// Phi elements are built in batches of NB: gather() issues every shared-memory load of the batch,
-// finish() multiplies and stores.  The MMA block of the current chunk is issued between the two, so the
-// gather latency and the dependent DMUL chain hide behind tensor work of the same warp.
+// Tile builder.  The columns of a tile are consecutive columns of the plan's SORTED order (smallest group = major
+// key), so neighbouring columns share their leading slots: sLvl[c] is the first key position where column c differs
+// from c-1 (0 at the start of every run).  A lane walks a run of columns keeping the product P of the first G-1
+// factors in a register; P is rebuilt only when one of those factors changes (sLvl[c] < G-1, rare), and every
+// element costs one gather of the last factor and one DMUL.  C3: ~1.5 gathers and ~1.3 DMULs per element instead
+// of 4 and 3 -- the build phase is bound by shared-memory gather traffic (profiles/r01_gram_design_notes.md).
 template <int G, int NB>
-struct PhiBatch {
-  double v[NB][G];
-  __device__ __forceinline__ void gather(const double* __restrict__ trow, const uint16_t* __restrict__ sIdx, int c_first) {
-    constexpr int GP = SlotPack<G>::GP;
-    int slots[NB][G];
+__device__ __forceinline__ void build_run(double& P, const double* __restrict__ trow, const uint16_t* __restrict__ sIdx,
+                                          const uint8_t* __restrict__ sLvl, double* __restrict__ dst, int c0) {
+  constexpr int GP = SlotPack<G>::GP;
+  double last[NB];
+  int lv[NB];
 #pragma unroll
-    for (int e = 0; e < NB; ++e) load_slots<G>(sIdx + (c_first + 2 * e) * GP, slots[e]);
-#pragma unroll
-    for (int e = 0; e < NB; ++e)
-#pragma unroll
-      for (int g = 0; g < G; ++g) v[e][g] = trow[slots[e][g]];
+  for (int e = 0; e < NB; ++e) {                      // all last-factor gathers are issued up front
+    lv[e] = sLvl[c0 + e];
+    last[e] = trow[sIdx[(c0 + e) * GP + (G - 1)]];
   }
-  __device__ __forceinline__ void finish(double* __restrict__ dst, int c_first) {
-    // pairwise tree: ceil(log2 G) dependent DMUL steps, NB independent chains per step
 #pragma unroll
-    for (int st = 1; st < G; st *= 2)
+  for (int e = 0; e < NB; ++e) {
+    if constexpr (G > 1) {
+      if (lv[e] < G - 1) {                            // some leading factor changed: rebuild the prefix product
+        int sl[G];
+        load_slots<G>(sIdx + (c0 + e) * GP, sl);
+        double q = trow[sl[0]];
 #pragma unroll
-      for (int g = 0; g + st < G; g += 2 * st)
-#pragma unroll
-        for (int e = 0; e < NB; ++e) v[e][g] *= v[e][g + st];
-#pragma unroll
-    for (int e = 0; e < NB; ++e) dst[(c_first + 2 * e) * kPhiLd] = v[e][0];
+        for (int g = 1; g < G - 1; ++g) q *= trow[sl[g]];
+        P = q;
+      }
+      last[e] *= P;
+    }
   }
-};
+#pragma unroll
+  for (int e = 0; e < NB; ++e) dst[(c0 + e) * kPhiLd] = last[e];
+}
 
 struct GramParams {
   const double* T;            // group table, n_pad rows x stride
-  const uint16_t* col_slot;   // p_pad x G
+  const uint16_t* sorted_slot;   // p_pad x G, sorted column order
+  const uint8_t* sorted_level;   // p_pad
   const int2* tiles;          // n_tiles (bi, bj)
   double* ws;                 // n_items x 128 x 128 partial tiles
   int stride;
@@ -98,11 +105,12 @@ struct GramParams {
 template <int G>
 __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) {
   constexpr int GP = SlotPack<G>::GP;
-  constexpr int NB = (G <= 4) ? 8 : 4;      // Phi elements in flight per lane during the build phase
+  constexpr int NB = 8;                     // columns in flight per lane during the build phase
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* t_full = reinterpret_cast<uint64_t*>(smem_raw);                      // kTStages barriers (64 B reserved)
   uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem_raw + 64);                   // 256 x GP
-  double* sT = reinterpret_cast<double*>(smem_raw + 64 + 256 * GP * sizeof(uint16_t));
+  uint8_t* sLvl = smem_raw + 64 + 256 * GP * sizeof(uint16_t);                   // 256
+  double* sT = reinterpret_cast<double*>(smem_raw + 64 + 256 * GP * sizeof(uint16_t) + 256);
   const int stage_doubles = kChunk * prm.stride;
   double* sPhi = sT + (size_t)kTStages * stage_doubles;                          // 2 x 256 x kPhiLd
 
@@ -132,11 +140,16 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
     const int boff = diag ? 0 : kTileN;
     const int cpw = ncols >> 3;                 // columns per warp per chunk (32, or 16 on diagonal tiles)
 
+    const int run = cpw >> 1;                   // columns per half-warp per chunk: one contiguous run of sorted columns
     __syncthreads();
     for (int e = tid; e < ncols * G; e += kGramThreads) {
       const int c = e / G, g = e - c * G;
       const int col = (c < kTileN ? ij.x * kTileN + c : ij.y * kTileN + (c - kTileN));
-      sIdx[c * GP + g] = prm.col_slot[(size_t)col * G + g];
+      sIdx[c * GP + g] = prm.sorted_slot[(size_t)col * G + g];
+    }
+    for (int c = tid; c < ncols; c += kGramThreads) {
+      const int col = (c < kTileN ? ij.x * kTileN + c : ij.y * kTileN + (c - kTileN));
+      sLvl[c] = (c % run == 0) ? (uint8_t)0 : prm.sorted_level[col];
     }
     __syncthreads();
 
@@ -165,11 +178,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
         mbar_wait(&t_full[st], (uint32_t)((gq / kTStages) & 1));
         const double* trow = sT + (size_t)st * stage_doubles + (size_t)krow * prm.stride;
         double* dst = sPhi + krow;
-        for (int it = 0; it < cpw; it += 2 * NB) {
-          PhiBatch<G, NB> pb;
-          pb.gather(trow, sIdx, warp * cpw + it + khalf);
-          pb.finish(dst, warp * cpw + it + khalf);
-        }
+        double P = 1.0;
+        for (int it = 0; it < run; it += NB) build_run<G, NB>(P, trow, sIdx, sLvl, dst, warp * cpw + khalf * run + it);
       }
       __syncthreads();
       for (int lc = 0; lc < nc; ++lc) {
@@ -186,11 +196,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
         // ---- build phase (chunk lc+1): FP64 DMULs of all warps are issued together, not mixed with DMMAs:
         //      a DMUL that has to enter a DMMA-busy FP64 pipe stalls ~60 cycles (profiles/r01 notes) ----
         if (more) {
-          for (int it = 0; it < cpw; it += 2 * NB) {
-            PhiBatch<G, NB> pb;
-            pb.gather(trow, sIdx, warp * cpw + it + khalf);
-            pb.finish(dst, warp * cpw + it + khalf);
-          }
+          double P = 1.0;
+          for (int it = 0; it < run; it += NB) build_run<G, NB>(P, trow, sIdx, sLvl, dst, warp * cpw + khalf * run + it);
         }
         // ---- MMA phase (chunk lc).  K order inside the chunk is permuted (lane t supplies rows 4t..4t+3):
         //      one LDS.128 yields two K steps; K steps are outermost so consecutive DMMAs are independent ----
@@ -234,25 +241,23 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
   }
 }
 
-// A[bi*128+m][bj*128+n] = sum_s ws[s][tile][m][n], mirrored across the diagonal.
+// A[perm[bi*128+m]][perm[bj*128+n]] = sum_s ws[s][tile][m][n] (fixed split order), mirrored across the diagonal.
+// `perm` maps the sorted column order the tiles were computed in back to the caller's column order.
 __global__ void __launch_bounds__(256)
-k_gram_reduce(const double* __restrict__ ws, const int2* __restrict__ tiles, int n_tiles, int n_splits, int p,
-              int64_t lda, double* __restrict__ A) {
+k_gram_reduce(const double* __restrict__ ws, const int2* __restrict__ tiles, const int* __restrict__ perm, int n_tiles,
+              int n_splits, int p, int64_t lda, double* __restrict__ A) {
   const int tile = blockIdx.x;
   const int2 ij = tiles[tile];
   for (int e = threadIdx.x; e < kTileN * kTileN; e += blockDim.x) {
     const int m = e / kTileN, n = e - m * kTileN;
-    const int row = ij.x * kTileN + m, col = ij.y * kTileN + n;
-    if (row >= p || col >= p) continue;
+    const int srow = ij.x * kTileN + m, scol = ij.y * kTileN + n;
+    if (ij.x == ij.y && scol > srow) continue;       // diagonal tile: lower triangle only, mirrored below
+    const int row = perm[srow], col = perm[scol];
+    if (row < 0 || col < 0) continue;                // padding columns
     double s = 0.0;
     for (int sp = 0; sp < n_splits; ++sp) s += ws[((size_t)sp * n_tiles + tile) * (kTileN * kTileN) + e];
-    if (ij.x != ij.y) {
-      A[(size_t)row * lda + col] = s;
-      A[(size_t)col * lda + row] = s;
-    } else if (col <= row) {        // diagonal tile: keep the lower triangle, mirror it (bit-symmetric result)
-      A[(size_t)row * lda + col] = s;
-      A[(size_t)col * lda + row] = s;
-    }
+    A[(size_t)row * lda + col] = s;
+    A[(size_t)col * lda + row] = s;
   }
 }
 
@@ -315,7 +320,8 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
 
   GramParams prm;
   prm.T = T;
-  prm.col_slot = pl->d_col_slot;
+  prm.sorted_slot = pl->d_sorted_slot;
+  prm.sorted_level = pl->d_sorted_level;
   prm.tiles = d_tiles;
   prm.ws = d_ws;
   prm.stride = pl->stride;
@@ -325,7 +331,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   prm.chunks_per_split = s.chunks_per_split;
   const int G = pl->n_groups;
   const int GP = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
-  const size_t smem = 64 + 256 * GP * sizeof(uint16_t) + (size_t)kTStages * kChunk * pl->stride * sizeof(double) +
+  const size_t smem = 64 + 256 * GP * sizeof(uint16_t) + 256 + (size_t)kTStages * kChunk * pl->stride * sizeof(double) +
                       (size_t)2 * kPhiStageDoubles * sizeof(double);
   const int grid = std::min(sms, s.n_items);
   int rc = GRIEF_OK;
@@ -347,7 +353,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   } else {
     GRIEF_CUDA(cudaMemsetAsync(d_ws, 0, (size_t)s.n_items * kTileN * kTileN * sizeof(double), stream));
   }
-  k_gram_reduce<<<s.n_tiles, 256, 0, stream>>>(d_ws, d_tiles, s.n_tiles, s.n_splits, pl->p, lda, A);
+  k_gram_reduce<<<s.n_tiles, 256, 0, stream>>>(d_ws, d_tiles, pl->d_perm, s.n_tiles, s.n_splits, pl->p, lda, A);
   GRIEF_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   return GRIEF_OK;

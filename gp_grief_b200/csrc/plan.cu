@@ -68,6 +68,9 @@ Plan::~Plan() {
   cudaFree(d_slot_group);
   cudaFree(d_group_begin);
   cudaFree(d_col_slot);
+  cudaFree(d_sorted_slot);
+  cudaFree(d_sorted_level);
+  cudaFree(d_perm);
 }
 
 static inline uint64_t mix64(uint64_t h, uint64_t v) {
@@ -229,6 +232,36 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   for (int s = 0; s < pl->width; ++s)
     std::memcpy(&slot_k[(size_t)s * pl->max_group_dims], slot_rows[s].data(), pl->max_group_dims);
 
+  // ---- sorted column order for the tile builders ----
+  std::vector<uint16_t> sorted_slot((size_t)pl->p_pad * G, 0);
+  std::vector<uint8_t> sorted_level(pl->p_pad, 0);
+  pl->perm_h.assign(pl->p_pad, -1);
+  {
+    std::vector<int> key_order(G);                       // key position -> group (fewest distinct sub-tuples first)
+    std::iota(key_order.begin(), key_order.end(), 0);
+    std::stable_sort(key_order.begin(), key_order.end(), [&](int a, int b) { return pl->group_size[a] < pl->group_size[b]; });
+    std::vector<int> cols(p);
+    std::iota(cols.begin(), cols.end(), 0);
+    auto key = [&](int j, int kpos) { return pl->col_slot_h[(size_t)j * G + key_order[kpos]]; };
+    std::stable_sort(cols.begin(), cols.end(), [&](int x, int y) {
+      for (int k = 0; k < G; ++k)
+        if (key(x, k) != key(y, k)) return key(x, k) < key(y, k);
+      return false;
+    });
+    for (int c = 0; c < pl->p_pad; ++c) {
+      const int j = c < p ? cols[c] : c;                 // padding columns keep their (all-constant) slots
+      if (c < p) pl->perm_h[c] = j;
+      for (int k = 0; k < G; ++k) sorted_slot[(size_t)c * G + k] = pl->col_slot_h[(size_t)j * G + key_order[k]];
+      int lv = 0;
+      if (c > 0) {
+        lv = G;
+        for (int k = 0; k < G; ++k)
+          if (sorted_slot[(size_t)c * G + k] != sorted_slot[(size_t)(c - 1) * G + k]) { lv = k; break; }
+      }
+      sorted_level[c] = (uint8_t)lv;
+    }
+  }
+
   // ---- upload ----
   std::vector<double> grid(grid_concat, grid_concat + pl->sum_m);
   std::vector<double> qs(qs_concat, qs_concat + qoff);
@@ -239,6 +272,9 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   if (rc == GRIEF_OK) rc = upload(&pl->d_slot_group, slot_group);
   if (rc == GRIEF_OK) rc = upload(&pl->d_group_begin, pl->group_begin);
   if (rc == GRIEF_OK) rc = upload(&pl->d_col_slot, pl->col_slot_h);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_slot, sorted_slot);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_level, sorted_level);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_perm, pl->perm_h);
   if (rc != GRIEF_OK) {
     delete pl;
     return rc;

@@ -52,7 +52,13 @@ struct Plan {
   uint8_t* d_slot_k = nullptr;          // width x max_group_dims: unique-index of every dim of the slot's group
   int* d_slot_group = nullptr;          // width: group of the slot (-1 for the constant slots)
   int* d_group_begin = nullptr;         // G+1
-  uint16_t* d_col_slot = nullptr;       // p_pad x G
+  uint16_t* d_col_slot = nullptr;       // p_pad x G, external column order (row kernels)
+  // Tile builders (k_gram, k_zgemm) walk the columns in LEXICOGRAPHIC slot order (smallest group = major key):
+  // consecutive columns then share their leading slots and only the factors from `level` on are re-gathered.
+  uint16_t* d_sorted_slot = nullptr;    // p_pad x G: slots of sorted column c, listed in key order
+  uint8_t* d_sorted_level = nullptr;    // p_pad: first key position where sorted column c differs from c-1 (G: identical)
+  int* d_perm = nullptr;                // p_pad: external column of sorted column c (-1 for padding columns)
+  std::vector<int> perm_h;
   int device = 0;
   GradDesc* grad = nullptr;             // set by grief_grad_setup
   ~Plan();
