@@ -41,7 +41,7 @@ constexpr int kMaxGrid = 64;       // grid points per dimension
 constexpr int kMaxGroups = 8;      // table groups gathered per basis column
 constexpr int kTileN = 128;        // Gram / GEMM tile edge (columns of Phi per block)
 constexpr int kChunk = 16;         // rows of Phi per pipeline stage (= one m16n8k16 K step)
-constexpr int kTableCap = 136;     // max table row width (doubles) that the pass-2 kernel keeps resident
+constexpr int kTableCap = 116;     // max table row width (doubles): 3 x 32-row ring stages + two 32-row Phi tile buffers fit 227 KB
 
 #ifdef __CUDACC__
 // ---- PTX: mbarrier + bulk async copy ----------------------------------------------------------

@@ -16,9 +16,10 @@
 
 namespace grief {
 
-constexpr int kGramThreads = 256;                 // 8 warps, 2 x 4, warp tile 64 (M) x 32 (N)
-constexpr int kTStages = 4;                       // table-chunk ring (bulk async copies)
-constexpr int kPhiLd = 18;                        // doubles per Phi-tile column in smem (16 rows + 2 pad: conflict-free LDS.128)
+constexpr int kGramThreads = 512;                 // 16 warps, 4 x 4, warp tile 32 (M) x 32 (N); 4 warps per SM sub-partition
+constexpr int kGramRows = 32;                     // data rows per pipeline chunk (two m16n8k16-equivalent K steps)
+constexpr int kTStages = 3;                       // table-chunk ring (bulk async copies)
+constexpr int kPhiLd = 34;                        // doubles per Phi-tile column in smem (32 rows + 2 pad: conflict-free LDS.128)
 constexpr int kPhiStageDoubles = 2 * kTileN * kPhiLd;
 
 template <int G> struct SlotPack;   // G u16 slot indices of one column, padded to a power of two
@@ -31,31 +32,12 @@ template <> struct SlotPack<6> { static constexpr int GP = 8; };
 template <> struct SlotPack<7> { static constexpr int GP = 8; };
 template <> struct SlotPack<8> { static constexpr int GP = 8; };
 
-template <int G>
-__device__ __forceinline__ void load_slots(const uint16_t* __restrict__ ip, int (&s)[G]) {
-  constexpr int GP = SlotPack<G>::GP;
-  uint32_t w[4];
-  if constexpr (GP == 1) {
-    w[0] = ip[0];
-  } else if constexpr (GP == 2) {
-    w[0] = *reinterpret_cast<const uint32_t*>(ip);
-  } else if constexpr (GP == 4) {
-    const uint2 v = *reinterpret_cast<const uint2*>(ip);
-    w[0] = v.x; w[1] = v.y;
-  } else {
-    const uint4 v = *reinterpret_cast<const uint4*>(ip);
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  }
-#pragma unroll
-  for (int g = 0; g < G; ++g) s[g] = (g & 1) ? (int)(w[g >> 1] >> 16) : (int)(w[g >> 1] & 0xffffu);
-}
-
-// Tile builder.  The columns of a tile are consecutive columns of the plan's SORTED order (smallest group = major
-// key), so neighbouring columns share their leading slots: sLvl[c] is the first key position where column c differs
-// from c-1 (0 at the start of every run).  A lane walks a run of columns keeping the product P of the first G-1
-// factors in a register; P is rebuilt only when one of those factors changes (sLvl[c] < G-1, rare), and every
-// element costs one gather of the last factor and one DMUL.  C3: ~1.5 gathers and ~1.3 DMULs per element instead
-// of 4 and 3 -- the build phase is bound by shared-memory gather traffic (profiles/r01_gram_design_notes.md).
+// Tile builder.  Lane = data row of the 32-row chunk, the warp walks a run of consecutive columns of the plan's
+// SORTED order (smallest group = major key), so neighbouring columns share their leading slots: sLvl[c] is the
+// first key position where column c differs from c-1 (0 at the start of a run).  The product P of the first G-1
+// factors lives in a register and is rebuilt only when one of them changes (warp-uniform branch, rare); every
+// element then costs one gather of the last factor and one DMUL.  C3: ~1.5 gathers / 1.3 DMULs per element
+// instead of 4 / 3 -- the build phase is bound by shared-memory traffic (profiles/r01_gram_design_notes.md).
 template <int G, int NB>
 __device__ __forceinline__ void build_run(double& P, const double* __restrict__ trow, const uint16_t* __restrict__ sIdx,
                                           const uint8_t* __restrict__ sLvl, double* __restrict__ dst, int c0) {
@@ -70,12 +52,10 @@ __device__ __forceinline__ void build_run(double& P, const double* __restrict__ 
 #pragma unroll
   for (int e = 0; e < NB; ++e) {
     if constexpr (G > 1) {
-      if (lv[e] < G - 1) {                            // some leading factor changed: rebuild the prefix product
-        int sl[G];
-        load_slots<G>(sIdx + (c0 + e) * GP, sl);
-        double q = trow[sl[0]];
+      if (lv[e] < G - 1) {                            // a leading factor changed: rebuild the prefix product
+        double q = trow[sIdx[(c0 + e) * GP]];
 #pragma unroll
-        for (int g = 1; g < G - 1; ++g) q *= trow[sl[g]];
+        for (int g = 1; g < G - 1; ++g) q *= trow[sIdx[(c0 + e) * GP + g]];
         P = q;
       }
       last[e] *= P;
@@ -86,22 +66,21 @@ __device__ __forceinline__ void build_run(double& P, const double* __restrict__ 
 }
 
 struct GramParams {
-  const double* T;            // group table, n_pad rows x stride
+  const double* T;               // group table, n_pad rows x stride
   const uint16_t* sorted_slot;   // p_pad x G, sorted column order
   const uint8_t* sorted_level;   // p_pad
-  const int2* tiles;          // n_tiles (bi, bj)
-  double* ws;                 // n_items x 128 x 128 partial tiles
+  const int2* tiles;             // n_tiles (bi, bj)
+  double* ws;                    // n_items x 128 x 128 partial tiles
   int stride;
   int n_tiles;
   int n_items;
-  int64_t n_chunks;           // total 16-row chunks
+  int64_t n_chunks;              // total 32-row chunks
   int64_t chunks_per_split;
 };
 
-// Every warp does both jobs in two phases per chunk: build its share of the Phi tiles of chunk lc+1 (all
-// warps together, 8 elements in flight per lane), then the DMMAs of chunk lc.  Measured alternatives
-// (profiles/r01_gram_design_notes.md): dedicated builder warps and DMULs interleaved between DMMAs are both
-// slower, because every DMMA->DMUL switch of the shared FP64 pipe costs tens of idle cycles.
+// Every warp does both jobs in two phases per 32-row chunk: build its share of the Phi tiles of chunk lc+1, then the
+// DMMAs of chunk lc.  Measured alternatives (profiles/r01_gram_design_notes.md): dedicated builder warps and DMULs
+// interleaved between DMMAs are both slower, because a DMUL entering the DMMA-busy FP64 pipe stalls for tens of cycles.
 template <int G>
 __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) {
   constexpr int GP = SlotPack<G>::GP;
@@ -111,13 +90,16 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
   uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem_raw + 64);                   // 256 x GP
   uint8_t* sLvl = smem_raw + 64 + 256 * GP * sizeof(uint16_t);                   // 256
   double* sT = reinterpret_cast<double*>(smem_raw + 64 + 256 * GP * sizeof(uint16_t) + 256);
-  const int stage_doubles = kChunk * prm.stride;
+  const int stage_doubles = kGramRows * prm.stride;
   double* sPhi = sT + (size_t)kTStages * stage_doubles;                          // 2 x 256 x kPhiLd
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g4 = lane >> 2, t4 = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
-  const int krow = lane & 15, khalf = lane >> 4;    // builder: lane <-> chunk row, half-warp <-> column
+  // Warps 0-3 and 8-11 build first and multiply second, warps 4-7 and 12-15 the other way round: every SM
+  // sub-partition (warp % 4) always has two warps with DMMAs in flight while the other two sit in the
+  // latency-bound tile build.
+  const bool build_first = ((warp >> 2) & 1) == 0;
 
   if (tid == 0) {
     for (int s = 0; s < kTStages; ++s) mbar_init(&t_full[s], 1);
@@ -138,9 +120,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
     const int nc = (int)max((int64_t)0, c1 - c0);
     const int ncols = diag ? kTileN : 2 * kTileN;
     const int boff = diag ? 0 : kTileN;
-    const int cpw = ncols >> 3;                 // columns per warp per chunk (32, or 16 on diagonal tiles)
+    const int cpw = ncols >> 4;                 // columns per warp per chunk: one run of sorted columns (16, or 8 on diagonal tiles)
 
-    const int run = cpw >> 1;                   // columns per half-warp per chunk: one contiguous run of sorted columns
     __syncthreads();
     for (int e = tid; e < ncols * G; e += kGramThreads) {
       const int c = e / G, g = e - c * G;
@@ -149,13 +130,13 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
     }
     for (int c = tid; c < ncols; c += kGramThreads) {
       const int col = (c < kTileN ? ij.x * kTileN + c : ij.y * kTileN + (c - kTileN));
-      sLvl[c] = (c % run == 0) ? (uint8_t)0 : prm.sorted_level[col];
+      sLvl[c] = (c % cpw == 0) ? (uint8_t)0 : prm.sorted_level[col];
     }
     __syncthreads();
 
-    double acc[4][4][4];
+    double acc[2][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -168,58 +149,50 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
       mbar_arrive_expect_tx(&t_full[st], stage_bytes);
       bulk_g2s(sT + (size_t)st * stage_doubles, prm.T + (size_t)(c0 + lc) * stage_doubles, stage_bytes, &t_full[st]);
     };
+    auto build = [&](int lc) {   // chunk lc: table ring slot -> Phi tile buffer lc & 1
+      const uint64_t q = gq + lc;
+      const int st = (int)(q % kTStages);
+      mbar_wait(&t_full[st], (uint32_t)((q / kTStages) & 1));
+      const double* trow = sT + (size_t)st * stage_doubles + (size_t)lane * prm.stride;
+      double* dst = sPhi + (size_t)(lc & 1) * kPhiStageDoubles + lane;
+      double P = 1.0;
+      for (int it = 0; it < cpw; it += NB) build_run<G, NB>(P, trow, sIdx, sLvl, dst, warp * cpw + it);
+    };
 
     if (nc > 0) {
       if (tid == 0)
         for (int s = 0; s < kTStages - 1 && s < nc; ++s) issue(s);
-      // chunk 0 has no MMA to hide behind: plain build
-      {
-        const int st = (int)(gq % kTStages);
-        mbar_wait(&t_full[st], (uint32_t)((gq / kTStages) & 1));
-        const double* trow = sT + (size_t)st * stage_doubles + (size_t)krow * prm.stride;
-        double* dst = sPhi + krow;
-        double P = 1.0;
-        for (int it = 0; it < run; it += NB) build_run<G, NB>(P, trow, sIdx, sLvl, dst, warp * cpw + khalf * run + it);
-      }
+      build(0);
       __syncthreads();
       for (int lc = 0; lc < nc; ++lc) {
         if (tid == 0 && lc + kTStages - 1 < nc) issue(lc + kTStages - 1);   // slot of chunk lc-1: free since last sync
-        const bool more = (lc + 1 < nc);
-        const uint64_t qn = gq + lc + 1;
-        const int stn = (int)(qn % kTStages);
-        if (more) mbar_wait(&t_full[stn], (uint32_t)((qn / kTStages) & 1));
-        const double* trow = sT + (size_t)stn * stage_doubles + (size_t)krow * prm.stride;
-        double* dst = sPhi + (size_t)((lc + 1) & 1) * kPhiStageDoubles + krow;
-        const double* base = sPhi + (size_t)(lc & 1) * kPhiStageDoubles;
-        const double* pa = base + (size_t)(wm * 64 + g4) * kPhiLd + 4 * t4;
-        const double* pbp = base + (size_t)(boff + wn * 32 + g4) * kPhiLd + 4 * t4;
-        // ---- build phase (chunk lc+1): FP64 DMULs of all warps are issued together, not mixed with DMMAs:
-        //      a DMUL that has to enter a DMMA-busy FP64 pipe stalls ~60 cycles (profiles/r01 notes) ----
-        if (more) {
-          double P = 1.0;
-          for (int it = 0; it < run; it += NB) build_run<G, NB>(P, trow, sIdx, sLvl, dst, warp * cpw + khalf * run + it);
-        }
-        // ---- MMA phase (chunk lc).  K order inside the chunk is permuted (lane t supplies rows 4t..4t+3):
+        if (build_first && lc + 1 < nc) build(lc + 1);
+        // ---- MMA phase (chunk lc).  K order inside each 16-row half is permuted (lane t supplies rows 4t..4t+3):
         //      one LDS.128 yields two K steps; K steps are outermost so consecutive DMMAs are independent ----
+        const double* base = sPhi + (size_t)(lc & 1) * kPhiStageDoubles;
+        const double* pa = base + (size_t)(wm * 32 + g4) * kPhiLd + 4 * t4;
+        const double* pbp = base + (size_t)(boff + wn * 32 + g4) * kPhiLd + 4 * t4;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          double2 av[4][2], bv[4];
+        for (int q4 = 0; q4 < 4; ++q4) {                   // (16-row half, 8-row quarter pair) = offset 16*(q4>>1) + 2*(q4&1)
+          const int off = 16 * (q4 >> 1) + 2 * (q4 & 1);
+          double2 av[2][2], bv[4];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) bv[nt] = *reinterpret_cast<const double2*>(pbp + nt * 8 * kPhiLd + 2 * hf);
+          for (int nt = 0; nt < 4; ++nt) bv[nt] = *reinterpret_cast<const double2*>(pbp + nt * 8 * kPhiLd + off);
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-              av[mt][h] = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * kPhiLd + 2 * hf);
+              av[mt][h] = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * kPhiLd + off);
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].x, av[mt][1].x, bv[nt].x);
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].y, av[mt][1].y, bv[nt].y);
         }
+        if (!build_first && lc + 1 < nc) build(lc + 1);
         __syncthreads();
       }
       gq += nc;
@@ -228,12 +201,12 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
     // partial tile -> workspace (row-major 128 x 128: [m][n], m indexes block bi, n block bj)
     double* out = prm.ws + (size_t)item * (kTileN * kTileN);
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int mrow = wm * 64 + mt * 16 + g4 + 8 * hh;
+          const int mrow = wm * 32 + mt * 16 + g4 + 8 * hh;
           const int ncol = wn * 32 + nt * 8 + 2 * t4;
           *reinterpret_cast<double2*>(out + (size_t)mrow * kTileN + ncol) =
               make_double2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
@@ -270,9 +243,9 @@ GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
   GramSchedule s;
   s.nb = p_pad / kTileN;
   s.n_tiles = s.nb * (s.nb + 1) / 2;
-  s.n_chunks = n_pad / kChunk;
-  // choose the number of row splits: fill whole waves of `sms` CTAs, keep >= 64 chunks per split
-  int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.n_chunks / 64, 4096 / std::max(1, s.n_tiles) + 1));
+  s.n_chunks = n_pad / kGramRows;
+  // choose the number of row splits: fill whole waves of `sms` CTAs, keep >= 32 chunks (1024 rows) per split
+  int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.n_chunks / 32, 4096 / std::max(1, s.n_tiles) + 1));
   int best = 1;
   double best_eff = -1.0;
   for (int64_t S = 1; S <= max_splits; ++S) {
@@ -304,7 +277,7 @@ static int launch_gram_g(const Plan* pl, const GramParams& prm, int grid, size_t
 
 int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, void* workspace,
                 size_t ws_bytes, int sms, cudaStream_t stream, int* launches) {
-  GRIEF_REQUIRE(n_pad % kChunk == 0, "gram: n_pad=%lld must be a multiple of %d", (long long)n_pad, kChunk);
+  GRIEF_REQUIRE(n_pad % kGramRows == 0, "gram: n_pad=%lld must be a multiple of %d", (long long)n_pad, kGramRows);
   GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
   GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
   // workspace layout: [tiles (int2 x n_tiles) padded to 256 B][partials]
@@ -331,7 +304,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   prm.chunks_per_split = s.chunks_per_split;
   const int G = pl->n_groups;
   const int GP = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
-  const size_t smem = 64 + 256 * GP * sizeof(uint16_t) + 256 + (size_t)kTStages * kChunk * pl->stride * sizeof(double) +
+  const size_t smem = 64 + 256 * GP * sizeof(uint16_t) + 256 + (size_t)kTStages * kGramRows * pl->stride * sizeof(double) +
                       (size_t)2 * kPhiStageDoubles * sizeof(double);
   const int grid = std::min(sms, s.n_items);
   int rc = GRIEF_OK;
