@@ -15,7 +15,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -52,37 +51,33 @@ def step_lengthscales(d, step):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """One long-running `nvidia-smi -lms 500` process (the recipe's clocks line) sampled over the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
-        self._stop = threading.Event()
-        self._th = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
-                parts = [s.strip() for s in r.stdout.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
 
     def start(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
-        self._th.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "500"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        if self._th:
-            self._th.join(timeout=10)
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=10)
+                rows = [[t.strip() for t in ln.split(",")] for ln in out.splitlines() if ln.count(",") >= 5]
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for p in self.rows:
+        for p in rows:
             try:
                 sm.append(float(p[0])); mx.append(float(p[1]))
             except ValueError:
@@ -306,12 +301,14 @@ def run_ours(args):
     p_pad = (p + 127) // 128 * 128
     rows128 = (n_local + 127) // 128 * 128
     kern_rows = []
-    for name, flops_per_step in (("k_zgemm", 2.0 * rows128 * p_pad * p_pad), ("k_gram", float(rows128) * p_pad * (p_pad + 128))):
+    flops = {"k_zgemm": 2.0 * rows128 * p_pad * p_pad, "k_gram": float(rows128) * p_pad * (p_pad + 128)}
+    for name in ("k_zgemm", "k_gram", "k_contract", "solve", "k_dtables", "k_tables", "phi_t_y", "k_topk"):
         t_ms, cnt = prof.get(name, (0.0, 0))
         if cnt:
-            kern_rows.append({"kernel": name, "launches": cnt, "ms_total": t_ms,
-                              "algorithmic_tflops": flops_per_step * args.steps / (t_ms * 1e-3) * 1e-12,
-                              "share_of_step": t_ms / ms_total})
+            row = {"kernel": name, "launches": cnt, "ms_total": t_ms, "share_of_step": t_ms / ms_total}
+            if name in flops:
+                row["algorithmic_tflops"] = flops[name] * args.steps / (t_ms * 1e-3) * 1e-12
+            kern_rows.append(row)
     dom = kern_rows[0] if kern_rows else None
     roofline = None
     if dom:

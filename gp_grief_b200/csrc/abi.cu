@@ -32,7 +32,8 @@ int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t
                     const double* gvec, int64_t rows, double* partial, int sms, cudaStream_t stream);
 int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream);
 int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream);
-int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* B, int64_t ldb, double* Z, int64_t ldz, int sms,
+int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream);
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Z, int64_t ldz, int sms,
                  cudaStream_t stream, int* launches);
 int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
 
@@ -194,7 +195,8 @@ size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
-         align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p * sizeof(double));
+         align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p * sizeof(double)) +
+         align256((size_t)pl->p * pl->p_pad * sizeof(double));
 }
 
 int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev, int64_t n,
@@ -213,17 +215,20 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   double* Z = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
   double* DT = reinterpret_cast<double*>(q); q += align256((size_t)slab * std::max(1, dtw) * sizeof(double));
   double* partial = reinterpret_cast<double*>(q); q += align256((size_t)contract_blocks(sms) * std::max(1, na) * sizeof(double));
-  double* gvec = reinterpret_cast<double*>(q);
+  double* gvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p * sizeof(double));
+  double* Bperm = reinterpret_cast<double*>(q);
   if (na == 0) return GRIEF_OK;
   GRIEF_CUDA(cudaMemsetAsync(partial, 0, (size_t)contract_blocks(sms) * na * sizeof(double), stream));
   int rc = launch_scale_vec(b_dev, 1.0 / noise_var, pl->p, gvec, stream);
   if (rc != GRIEF_OK) return rc;
-  g_launches += 1;
+  rc = launch_permute_b(pl, G2_dev, ldg, Bperm, stream);
+  if (rc != GRIEF_OK) return rc;
+  g_launches += 2;
   const int64_t n128 = grief_table_rows(n);
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, G2_dev, ldg, Z, pl->p_pad, sms, stream, &g_launches);
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, Z, pl->p_pad, sms, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_dtables(pl, gd, X_dev + (size_t)r0 * ldx, ldx, rows_valid, rows_valid, DT, stream);
     if (rc != GRIEF_OK) return rc;
@@ -238,7 +243,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
 
 size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
-  return align256((size_t)slab_rows_for(n, sm_count()) * pl->p_pad * sizeof(double));
+  return align256((size_t)slab_rows_for(n, sm_count()) * pl->p_pad * sizeof(double)) + align256((size_t)pl->p * pl->p_pad * sizeof(double));
 }
 
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb, double* q_dev,
@@ -250,11 +255,17 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   double* Z = reinterpret_cast<double*>(workspace_dev);
+  double* Bperm = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace_dev) + align256((size_t)slab * pl->p_pad * sizeof(double)));
+  {
+    int rc0 = launch_permute_b(pl, B_dev, ldb, Bperm, stream);
+    if (rc0 != GRIEF_OK) return rc0;
+    g_launches += 1;
+  }
   const int64_t n128 = grief_table_rows(n);
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, B_dev, ldb, Z, pl->p_pad, sms, stream, &g_launches);
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, Z, pl->p_pad, sms, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_rowdot(pl, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, rows_valid, q_dev + r0, stream);
     if (rc != GRIEF_OK) return rc;

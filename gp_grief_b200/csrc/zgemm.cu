@@ -14,22 +14,24 @@
 
 namespace grief {
 
-constexpr int kZThreads = 256;
+constexpr int kZThreads = 512;              // 16 warps, 4 x 4, warp tile 32 (rows) x 32 (cols); two anti-phase groups
 constexpr int kZRows = 128;                 // data rows per CTA
 constexpr int kZPhiLd = 18;                 // doubles per Phi-operand row in smem (16 + 2 pad)
 constexpr int kZPhiStage = kZRows * kZPhiLd;
 constexpr int kZBStageBytes = kTileN * kChunk * 8;   // 16 KB: 128 rows of B x 16 doubles, swizzled
+constexpr int kZE = 4;                      // Phi elements per thread per K chunk (128 rows x 16 columns / 512 threads)
 
 struct ZgemmParams {
-  const double* T;             // table rows of the slab (row 0 = first slab row), stride doubles per row
-  const uint16_t* col_slot;    // p_pad x G
-  double* Z;                   // out: slab_rows x ldz
+  const double* T;               // table rows of the slab (row 0 = first slab row), stride doubles per row
+  const uint16_t* sorted_slot;   // p_pad x G: K columns are walked in the plan's sorted order
+  const uint8_t* sorted_level;   // p_pad
+  double* Z;                     // out: slab_rows x ldz
   int64_t ldz;
   int stride;
-  int n_row_blocks;            // slab_rows / 128
-  int n_col_blocks;            // p_pad / 128
-  int n_k_chunks;              // p_pad / 16
-  int nb_stages;               // B ring depth (2..4)
+  int n_row_blocks;              // slab_rows / 128
+  int n_col_blocks;              // p_pad / 128
+  int n_k_chunks;                // p_pad / 16
+  int nb_stages;                 // B ring depth (2..4)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -40,9 +42,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+// B'[c][k] = B[c][perm[k]] (0 for padding columns): the K dimension of Z = Phi * B is walked in sorted column order.
+__global__ void __launch_bounds__(256)
+k_permute_cols(const double* __restrict__ B, int64_t ldb, const int* __restrict__ perm, int p, int p_pad, double* __restrict__ out) {
+  const int64_t total = (int64_t)p * p_pad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e / p_pad), k = (int)(e - (int64_t)c * p_pad);
+    const int src = perm[k];
+    out[e] = src >= 0 ? B[(size_t)c * ldb + src] : 0.0;
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ CUtensorMap mapB, const ZgemmParams prm) {
-  constexpr int NBE = 8;   // Phi elements per thread per chunk
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem);          // nb_stages barriers
@@ -54,7 +66,8 @@ __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g4 = lane >> 2, t4 = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
-  const int brow = tid & (kZRows - 1), bhalf = tid >> 7;         // builder: thread <-> data row, 8 of the 16 chunk columns
+  const int brow = tid & (kZRows - 1), bq4 = tid >> 7;           // builder: thread <-> data row, 4 of the 16 chunk columns
+  const bool build_first = ((warp >> 2) & 1) == 0;               // anti-phase groups, two warps of each per SM sub-partition
 
   if (tid == 0) {
     for (int s = 0; s < prm.nb_stages; ++s) mbar_init(&b_full[s], 1);
@@ -91,32 +104,37 @@ __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ 
     t_parity ^= 1;
 
     const double* trow = sT + (size_t)brow * prm.stride;
+    // Phi operand of K chunk f: thread = (row, 4 consecutive sorted columns).  The product of the first G-1 factors
+    // is rebuilt only where a leading slot changes (warp-uniform: all lanes of a warp share the columns).
     auto build = [&](int f) {
       const int kc = f % prm.n_k_chunks;
-      const uint16_t* cs = prm.col_slot + ((size_t)kc * kChunk + bhalf * NBE) * G;   // warp-uniform
-      double* dst = sPhi + (size_t)(f & 1) * kZPhiStage + (size_t)brow * kZPhiLd + bhalf * NBE;
-      constexpr int SB = (G <= 2) ? 8 : ((G <= 4) ? 4 : 2);   // elements in flight (register budget)
+      const int col0 = kc * kChunk + bq4 * kZE;
+      const uint16_t* cs = prm.sorted_slot + (size_t)col0 * G;
+      double v[kZE];
 #pragma unroll
-      for (int e0 = 0; e0 < NBE; e0 += SB) {
-        double v[SB][G];
+      for (int e = 0; e < kZE; ++e) v[e] = trow[__ldg(cs + e * G + (G - 1))];
+      if constexpr (G > 1) {
+        double P = 1.0;
 #pragma unroll
-        for (int e = 0; e < SB; ++e)
+        for (int e = 0; e < kZE; ++e) {
+          const int lv = (e == 0) ? 0 : (int)__ldg(prm.sorted_level + col0 + e);
+          if (lv < G - 1) {
+            double q = trow[__ldg(cs + e * G)];
 #pragma unroll
-          for (int g = 0; g < G; ++g) v[e][g] = trow[__ldg(cs + (e0 + e) * G + g)];
-#pragma unroll
-        for (int st = 1; st < G; st *= 2)
-#pragma unroll
-          for (int g = 0; g + st < G; g += 2 * st)
-#pragma unroll
-            for (int e = 0; e < SB; ++e) v[e][g] *= v[e][g + st];
-#pragma unroll
-        for (int e = 0; e < SB; e += 2) *reinterpret_cast<double2*>(dst + e0 + e) = make_double2(v[e][0], v[e + 1][0]);
+            for (int g = 1; g < G - 1; ++g) q *= trow[__ldg(cs + e * G + g)];
+            P = q;
+          }
+          v[e] *= P;
+        }
       }
+      double* dst = sPhi + (size_t)(f & 1) * kZPhiStage + (size_t)brow * kZPhiLd + bq4 * kZE;
+      *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
     };
 
-    double acc[4][4][4];
+    double acc[2][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -125,29 +143,29 @@ __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ 
     build(0);
     __syncthreads();
     for (int f = 0; f < F; ++f) {
-      if (f + 1 < F) build(f + 1);
+      if (build_first && f + 1 < F) build(f + 1);
       const uint64_t q = bq + f;
       const int st = (int)(q % prm.nb_stages);
       mbar_wait(&b_full[st], (uint32_t)((q / prm.nb_stages) & 1));
-      const double* pa = sPhi + (size_t)(f & 1) * kZPhiStage + (size_t)(wm * 64 + g4) * kZPhiLd + 4 * t4;
+      const double* pa = sPhi + (size_t)(f & 1) * kZPhiStage + (size_t)(wm * 32 + g4) * kZPhiLd + 4 * t4;
       const unsigned char* pb = sB + (size_t)st * kZBStageBytes + (size_t)(wn * 32 + g4) * 128;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        double2 av[4][2], bv[4];
+        double2 av[2][2], bv[4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)     // row n = wn*32 + nt*8 + g4 (n & 7 == g4); 16-B unit (2*t4 + hf) ^ (n & 7)
           bv[nt] = *reinterpret_cast<const double2*>(pb + nt * 8 * 128 + (((2 * t4 + hf) ^ g4) << 4));
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int h = 0; h < 2; ++h)
             av[mt][h] = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * kZPhiLd + 2 * hf);
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].x, av[mt][1].x, bv[nt].x);
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].y, av[mt][1].y, bv[nt].y);
       }
@@ -155,12 +173,12 @@ __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ 
       if (kc == prm.n_k_chunks - 1) {       // column block finished: write the Z tile, restart the accumulators
         double* out = prm.Z + ((size_t)rb * kZRows) * prm.ldz + (size_t)cb * kTileN;
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              const int mrow = wm * 64 + mt * 16 + g4 + 8 * hh;
+              const int mrow = wm * 32 + mt * 16 + g4 + 8 * hh;
               const int ncol = wn * 32 + nt * 8 + 2 * t4;
               *reinterpret_cast<double2*>(out + (size_t)mrow * prm.ldz + ncol) =
                   make_double2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
@@ -168,6 +186,7 @@ __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ 
               acc[mt][nt][2 * hh + 1] = 0.0;
             }
       }
+      if (!build_first && f + 1 < F) build(f + 1);
       __syncthreads();
       if (tid == 0 && f + prm.nb_stages < F) issue_b(f + prm.nb_stages);
     }
@@ -201,8 +220,19 @@ static int launch_zgemm_g(const CUtensorMap& map, const ZgemmParams& prm, int gr
 
 // Z (slab_rows x ldz) = Phi(slab rows) * B.   B: (p x p) symmetric, leading dimension ldb (even).
 // slab_rows must be a multiple of 128 and T must hold that many (zero padded) rows.
-int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* B, int64_t ldb, double* Z,
+// Bperm (p x p_pad doubles) must hold permute_b(B): call launch_permute_b once per B, then launch_zgemm per slab.
+int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream) {
+  GRIEF_REQUIRE(ldb >= pl->p, "permute_b: ldb=%lld < p", (long long)ldb);
+  const unsigned blocks = (unsigned)std::min<int64_t>(((int64_t)pl->p * pl->p_pad + 255) / 256, 148 * 8);
+  k_permute_cols<<<blocks, 256, 0, stream>>>(B, ldb, pl->d_perm, pl->p, pl->p_pad, Bperm);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Z,
                  int64_t ldz, int sms, cudaStream_t stream, int* launches) {
+  const double* B = Bperm;
+  const int64_t ldb = pl->p_pad;
   GRIEF_REQUIRE(slab_rows % kZRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kZRows);
   GRIEF_REQUIRE(ldb % 2 == 0 && ldb >= pl->p, "zgemm: ldb=%lld must be even and >= p", (long long)ldb);
   GRIEF_REQUIRE(ldz >= pl->p_pad && ldz % 2 == 0, "zgemm: ldz=%lld must be even and >= p_pad=%d", (long long)ldz, pl->p_pad);
@@ -211,7 +241,7 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(GRIEF_ERR_CUDA, "zgemm: cuTensorMapEncodeTiled is not available from the driver");
   alignas(64) CUtensorMap map;
-  const cuuint64_t gdim[2] = {(cuuint64_t)pl->p, (cuuint64_t)pl->p};        // inner = columns (k), outer = rows (n)
+  const cuuint64_t gdim[2] = {(cuuint64_t)pl->p_pad, (cuuint64_t)pl->p};    // inner = sorted K columns, outer = rows (n)
   const cuuint64_t gstr[1] = {(cuuint64_t)ldb * sizeof(double)};
   const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)kTileN};       // 16 doubles (128 B) x 128 rows
   const cuuint32_t estr[2] = {1, 1};
@@ -222,7 +252,8 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
 
   ZgemmParams prm;
   prm.T = T_slab;
-  prm.col_slot = pl->d_col_slot;
+  prm.sorted_slot = pl->d_sorted_slot;
+  prm.sorted_level = pl->d_sorted_level;
   prm.Z = Z;
   prm.ldz = ldz;
   prm.stride = pl->stride;
