@@ -311,11 +311,19 @@ def run_ours(args):
             kern_rows.append(row)
     dom = kern_rows[0] if kern_rows else None
     roofline = None
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["k_zgemm"]
+        if tr["config"] == args.config:
+            traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "rows_per_launch": tr["rows_per_launch"],
+                       "source": tr["source"]}
+    except Exception:
+        traffic = None
     if dom:
         algo = 2.0 * n_local * p * p * args.steps / (dom["ms_total"] * 1e-3) * 1e-12      # algorithmic: 2 n p^2 per evaluation
         roofline = {"bound": "tensor", "kernel": "k_zgemm (fused Phi-tile build + FP64 DMMA GEMM Phi*G2, pass 2)",
                     "achieved": algo, "peak": peak_sust, "unit": "TFLOP/s", "frac": algo / peak_sust,
-                    "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained %.1f / burst %.1f TFLOP/s; "
+                    "traffic": traffic, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained %.1f / burst %.1f TFLOP/s; "
                     "MEASURED_PEAKS.json has no FP64 row; FP64 DMMA issue-rate peak 37.2 TFLOP/s (profiles/r01_fp64_pipes_microbench.txt)"
                     % (peak_sust, peak_burst),
                     "avg_launch_ms": dom["ms_total"] / dom["launches"], "kernels": kern_rows,

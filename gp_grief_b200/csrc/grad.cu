@@ -252,10 +252,11 @@ struct ContractParams {
   const int* ga; int n_active;
 };
 
-constexpr int kContractK = 8;   // parameters of one group handled per sweep over the columns
+constexpr int kContractK = 4;   // parameters per group accumulated in registers per sweep over the columns
 
-// One warp per data row.  For every group g: sweep the columns, L = Zt * prod_{g' != g} H_g', accumulate
-// L * DT[g][t_g(j)][kk] for the group's parameters kk, warp-reduce, add to the block's partial sums.
+// One warp per data row, ONE sweep over the columns for all groups (a second sweep only if a group has more than
+// kContractK active parameters): per column the leave-one-group-out products L_g = Zt * prod_{g' != g} H_g' come from
+// prefix / suffix products, and L_g * DT[g][t_g(j)][kk] is accumulated per (group, parameter) in registers.
 template <int G>
 __global__ void __launch_bounds__(256) k_contract(const ContractParams P) {
   extern __shared__ double sm[];
@@ -263,6 +264,9 @@ __global__ void __launch_bounds__(256) k_contract(const ContractParams P) {
   double* sRow = sm + (size_t)warp * (P.stride + P.dt_width);          // [stride] table row, [dt_width] DT row
   double* sAcc = sm + (size_t)nw * (P.stride + P.dt_width) + (size_t)warp * P.n_active;
   for (int a = lane; a < P.n_active; a += 32) sAcc[a] = 0.0;
+  int np[G], slot0[G], dtoff[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { np[g] = P.g_np[g]; slot0[g] = P.g_slot0[g]; dtoff[g] = P.g_dtoff[g]; }
   for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < P.rows; row += (int64_t)gridDim.x * nw) {
     __syncwarp();
     for (int e = lane; e < P.stride; e += 32) sRow[e] = P.T[row * P.stride + e];
@@ -270,39 +274,42 @@ __global__ void __launch_bounds__(256) k_contract(const ContractParams P) {
     __syncwarp();
     const double yr = P.y[row];
     const double* zrow = P.Z + row * P.ldz;
-    for (int g = 0; g < G; ++g) {
-      const int np = P.g_np[g];
-      if (np == 0) continue;
-      const double* dtg = sRow + P.stride + P.g_dtoff[g];
-      const int slot0 = P.g_slot0[g];
-      for (int k0 = 0; k0 < np; k0 += kContractK) {
-        double acc[kContractK];
+    const double* sDT = sRow + P.stride;
+    for (int k0 = 0; k0 < P.max_np; k0 += kContractK) {
+      double acc[G][kContractK];
 #pragma unroll
-        for (int kk = 0; kk < kContractK; ++kk) acc[kk] = 0.0;
-        for (int j = lane; j < P.p; j += 32) {
-          const double zt = fma(yr, P.gvec[j], zrow[j]);
-          const uint16_t* cs = P.col_slot + (size_t)j * G;
-          double L = zt;
-          int tl = 0;
+      for (int g = 0; g < G; ++g)
 #pragma unroll
-          for (int gg = 0; gg < G; ++gg) {
-            const int s = cs[gg];
-            if (gg != g) L *= sRow[s];
-            else tl = s - slot0;
-          }
-          const double* dt = dtg + (size_t)tl * np + k0;
+        for (int kk = 0; kk < kContractK; ++kk) acc[g][kk] = 0.0;
+      for (int j = lane; j < P.p; j += 32) {
+        const double zt = fma(yr, P.gvec[j], zrow[j]);
+        const uint16_t* cs = P.col_slot + (size_t)j * G;
+        int sl[G];
+        double h[G], L[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { sl[g] = cs[g]; h[g] = sRow[sl[g]]; }
+        double run = zt;                       // prefix pass: L[g] = zt * prod_{g' < g} h
+#pragma unroll
+        for (int g = 0; g < G; ++g) { L[g] = run; run *= h[g]; }
+        run = 1.0;                             // suffix pass: L[g] *= prod_{g' > g} h
+#pragma unroll
+        for (int g = G - 1; g >= 0; --g) { L[g] *= run; run *= h[g]; }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const double* dt = sDT + dtoff[g] + (size_t)(sl[g] - slot0[g]) * np[g] + k0;
 #pragma unroll
           for (int kk = 0; kk < kContractK; ++kk)
-            if (k0 + kk < np) acc[kk] = fma(L, dt[kk], acc[kk]);
-        }
-#pragma unroll
-        for (int kk = 0; kk < kContractK; ++kk) {
-          if (k0 + kk < np) {
-            const double v = warp_sum(acc[kk]);
-            if (lane == 0) sAcc[P.ga[(size_t)g * P.max_np + k0 + kk]] += v;
-          }
+            if (k0 + kk < np[g]) acc[g][kk] = fma(L[g], dt[kk], acc[g][kk]);
         }
       }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int kk = 0; kk < kContractK; ++kk)
+          if (k0 + kk < np[g]) {               // warp-uniform
+            const double v = warp_sum(acc[g][kk]);
+            if (lane == 0) sAcc[P.ga[(size_t)g * P.max_np + k0 + kk]] += v;
+          }
     }
   }
   __syncthreads();

@@ -200,6 +200,15 @@ class GPGriefModel(BaseModel):
             self._host.pop(k, None)
         return out
 
+    def to_web_model(self):
+        """GPwebModel sharing this model's device-resident statistics (Type-I inner loop / MCMC: O(p^3) per evaluation)."""
+        from .gp_web_model import GPwebModel
+        self.parameters
+        st = self._stats()
+        web = GPwebModel.from_statistics(st['A'], st['r'], st['s'], self.num_data, noise_var=self.noise_var)
+        web.kern.parameters = np.array(self.kern.w, dtype=float)
+        return web
+
     # ------------------------------------------------------------------ likelihood and gradients
     def _compute_log_likelihood(self, parameters):
         """log N(y | 0, Phi W Phi^T + noise_var I), returned as a (1, 1) array like the reference (:203-214)."""

@@ -193,3 +193,33 @@ def test_kron_matrix_host_methods():
         loc, vals, gl = eigs.find_extremum_eigs(5, mode=mode, log_expand=False, sort=True, compute_global_loc=True)
         ref = np.sort(all_eigs)[-5:] if mode == 'largest' else np.sort(all_eigs)[:5]
         assert_array_almost_equal(np.sort(vals), ref, decimal=15)
+
+
+def test_gpweb_reference_test():
+    """tests/test_models/test_gp_web_model.py:13-34 of the reference + its outputs on the same inputs (golden)."""
+    gp = _pkg()
+    g = load_golden("gpweb_n100_p4")
+    m = gp.models.GPwebModel(Phi=g["Phi"], y=g["y"])
+    m.parameters = g["parameters"].copy()
+    ll = m.log_likelihood()
+    w = m.kern.parameters.reshape((1, -1))
+    K = g["Phi"].dot(np.diag(w.squeeze()).dot(g["Phi"].T)) + m.noise_var * np.identity(g["Phi"].shape[0])
+    assert_array_almost_equal(ll, mvn.logpdf(g["y"].squeeze(), mean=np.zeros(g["Phi"].shape[0]), cov=K))
+    assert_allclose(float(ll), float(g["lml"]), rtol=1e-9)
+    assert m.checkgrad()
+    _, grad = m.log_likelihood(return_gradient=True)
+    assert_allclose(grad, g["grad"], rtol=1e-9)
+    yhat, yvar = m.predict(g["Phi_new"])
+    assert_allclose(yhat.squeeze(), g["yhat"], rtol=1e-9)
+    assert_allclose(yvar, g["yvar"], rtol=1e-9)
+
+
+def test_grief_to_web_model_shares_statistics():
+    g = load_golden("syn_t1_n3000_d6_m10_p256_w")
+    m = build_model(g)
+    web = m.to_web_model()
+    assert_allclose(float(web.log_likelihood()), float(g["lml"]), rtol=1e-9)
+    _, gw = web.log_likelihood(return_gradient=True)
+    ref = g["grad_adjoint"]
+    assert_allclose(gw[0], ref[0], rtol=1e-9)
+    assert_allclose(gw[1:], ref[-256:], rtol=1e-9, atol=1e-9 * np.abs(ref[-256:]).max())
