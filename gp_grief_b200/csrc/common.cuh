@@ -107,6 +107,16 @@ __device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1
       : "d"(a0), "d"(a1), "d"(b));
 }
 
+// A short not-ready window for the calling warp (two dependent clock reads).  Issued by the MMA warps once per
+// 32 DMMAs: without it the warps that build Phi tiles wait several hundred cycles for a slot in the FP64 pipe
+// (ncu: builder DMULs in stall_math); measured +1..4 % on k_gram (profiles/r01_gram_design_notes.md).
+__device__ __forceinline__ void pipe_window() {
+  unsigned c1, c2;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c1));
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c2));
+  if (c1 - c2 == 0x7fffffffu) asm volatile("trap;");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

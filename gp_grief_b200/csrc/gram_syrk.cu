@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram(const GramParams prm) 
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].y, av[mt][1].y, bv[nt].y);
+          pipe_window();
         }
         if (!build_first && lc + 1 < nc) build(lc + 1);
         __syncthreads();

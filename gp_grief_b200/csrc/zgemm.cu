@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kZThreads, 1) k_zgemm(const __grid_constant__ 
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].y, av[mt][1].y, bv[nt].y);
+        pipe_window();
       }
       const int cb = f / prm.n_k_chunks, kc = f - cb * prm.n_k_chunks;
       if (kc == prm.n_k_chunks - 1) {       // column block finished: write the Z tile, restart the accumulators
