@@ -10,23 +10,31 @@
 //   Y^T alpha   = (s - r^T b)/sigma^2        alpha^T alpha = (s - 2 r^T b + b^T A b)/sigma^4
 //   b^T A b     = b^T r - sum_j D_j b_j^2    tr(P^-1 A) = p - sum_j D_j (P^-1)_jj
 //   diag(A) - colsum(A o P^-1 A) = D_j (1 - D_j (P^-1)_jj)
-// Round-1 note: the dense factorisation itself (potrf / potrs) is delegated to cuSOLVER;
-// it is < 0.5 % of an evaluation at the benchmark shapes.  Everything else here is our kernels.
-#include <cusolverDn.h>
-
+// The dense factorisation, the triangular solves and the inverse are hand-written too (dense.cu: blocked right-looking
+// Cholesky on a TMA-fed FP64 DMMA GEMM, block forward substitution for L^-1, P^-1 = L^-T L^-1); no cuSOLVER / cuBLAS.
 #include "plan.h"
 
 namespace grief {
 
+struct DenseWork;
+DenseWork* dense_work_new();
+void dense_work_delete(DenseWork* wk);
+int dense_work_reserve(DenseWork* wk, int q);
+double* dense_work_factor(DenseWork* wk);
+double* dense_work_inverse(DenseWork* wk);
+double* dense_work_tmp(DenseWork* wk);
+int dense_potrf(DenseWork* wk, int q, int* d_info, cudaStream_t stream, int* launches);
+int dense_inverse_from_factor(DenseWork* wk, int q, cudaStream_t stream, int* launches);
+int dense_trsv_pair(DenseWork* wk, int q, const double* r, int p, double* b, double* tmp, cudaStream_t stream, int* launches);
+int launch_form_P_padded(const double* A, int64_t lda, const double* w, double noise, int p, int q, double* P, cudaStream_t stream);
+int launch_copy_block(const double* in, int q, int p, bool transpose, bool upper_only, double* out, int64_t ldo, cudaStream_t stream);
+
 struct SolveCtx {
-  cusolverDnHandle_t solver = nullptr;
-  double* work = nullptr;
-  int lwork = 0;
+  DenseWork* work = nullptr;
   int* d_info = nullptr;
-  double* d_scalars = nullptr;   // kNumScalars doubles
+  double* d_scalars = nullptr;   // SC_COUNT doubles
   ~SolveCtx() {
-    if (solver) cusolverDnDestroy(solver);
-    cudaFree(work);
+    if (work) dense_work_delete(work);
     cudaFree(d_info);
     cudaFree(d_scalars);
   }
@@ -36,10 +44,7 @@ enum { SC_LML = 0, SC_YT_ALPHA, SC_LOGDET, SC_GRAD_NOISE, SC_RTB, SC_ALPHA_SQ, S
 
 int solve_ctx_create(SolveCtx** out) {
   SolveCtx* c = new SolveCtx();
-  if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS) {
-    delete c;
-    return fail(GRIEF_ERR_LIBRARY, "cusolverDnCreate failed");
-  }
+  c->work = dense_work_new();
   if (cudaMalloc(&c->d_info, sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_scalars, SC_COUNT * sizeof(double)) != cudaSuccess) {
     delete c;
     return fail(GRIEF_ERR_CUDA, "solve_ctx_create: cudaMalloc failed");
@@ -48,47 +53,6 @@ int solve_ctx_create(SolveCtx** out) {
   return GRIEF_OK;
 }
 void solve_ctx_destroy(SolveCtx* c) { delete c; }
-
-// L <- A + diag(noise/w)   (full copy; only one triangle is referenced by cuSOLVER)
-__global__ void k_form_P(const double* __restrict__ A, int64_t lda, const double* __restrict__ w, double noise, int p,
-                         double* __restrict__ L) {
-  const int64_t total = (int64_t)p * p;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(e / p), j = (int)(e - (int64_t)i * p);
-    double v = A[(size_t)i * lda + j];
-    if (i == j) v += noise / w[i];
-    L[e] = v;
-  }
-}
-
-// cuSOLVER (column-major, LOWER) leaves the other triangle untouched: mirror so M is fully symmetric.
-// In our row-major view the valid triangle is j >= i  (element (i,j) row-major == (j,i) column-major).
-__global__ void k_symmetrize_from_colmajor_lower(double* __restrict__ M, int p) {
-  const int64_t total = (int64_t)p * p;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(e / p), j = (int)(e - (int64_t)i * p);
-    if (j < i) M[e] = M[(size_t)j * p + i];
-  }
-}
-
-__global__ void k_set_identity(double* __restrict__ M, int p) {
-  const int64_t total = (int64_t)p * p;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    M[e] = (e / p == e % p) ? 1.0 : 0.0;
-}
-
-// M <- (M + M^T)/2, computed pairwise so both halves hold bit-identical values
-__global__ void k_symmetrize_mean(double* __restrict__ M, int p) {
-  const int64_t total = (int64_t)p * p;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(e / p), j = (int)(e - (int64_t)i * p);
-    if (j > i) {
-      const double v = 0.5 * (M[e] + M[(size_t)j * p + i]);
-      M[e] = v;
-      M[(size_t)j * p + i] = v;
-    }
-  }
-}
 
 // G2 = -(Pinv + b b^T / noise)
 __global__ void k_form_G2(const double* __restrict__ Pinv, const double* __restrict__ b, double noise, int p,
@@ -162,6 +126,7 @@ k_assemble(const double* __restrict__ L, const double* __restrict__ Pinv /* may 
 }
 
 // Returns GRIEF_ERR_NOT_PD with the failing leading-minor order in *info_out when P is not PD.
+// L_out receives the factor in scipy's cho_factor convention for a row-major array: upper U with P = U^T U (lower part 0).
 int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* r, const double* yty,
               const double* w, double noise, int64_t n_rows, double* L /* p*p */, double* b /* p */,
               double* Pinv /* p*p or null */, double* grad_w /* p or null */, double* G2 /* p*p or null */,
@@ -169,41 +134,27 @@ int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* 
   GRIEF_REQUIRE(p >= 1, "solve_lml: p=%d", p);
   GRIEF_REQUIRE(noise > 0.0, "solve_lml: noise_var=%g must be positive", noise);
   GRIEF_REQUIRE(G2 == nullptr || Pinv != nullptr, "solve_lml: G2 needs Pinv");
-  if (cusolverDnSetStream(ctx->solver, stream) != CUSOLVER_STATUS_SUCCESS) return fail(GRIEF_ERR_LIBRARY, "cusolverDnSetStream");
-  int lw1 = 0, lw2 = 0;
-  if (cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, p, L, p, &lw1) != CUSOLVER_STATUS_SUCCESS)
-    return fail(GRIEF_ERR_LIBRARY, "cusolver bufferSize failed");
-  const int lwork = std::max(lw1, lw2);
-  if (lwork > ctx->lwork) {
-    cudaFree(ctx->work);
-    ctx->work = nullptr;
-    GRIEF_CUDA(cudaMalloc(&ctx->work, (size_t)lwork * sizeof(double)));
-    ctx->lwork = lwork;
-  }
+  const int q = (p + 127) / 128 * 128;               // P is padded with an identity block to a multiple of the tile
+  int rc = dense_work_reserve(ctx->work, q);
+  if (rc != GRIEF_OK) return rc;
   const unsigned eb = (unsigned)std::min<int64_t>(((int64_t)p * p + 255) / 256, 148 * 8);
   prof_begin(PROF_SOLVE, stream);
-  k_form_P<<<eb, 256, 0, stream>>>(A, lda, w, noise, p, L);
-  GRIEF_CUDA(cudaGetLastError());
-  if (cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, p, L, p, ctx->work, ctx->lwork, ctx->d_info) != CUSOLVER_STATUS_SUCCESS)
-    return fail(GRIEF_ERR_LIBRARY, "cusolverDnDpotrf failed");
+  GRIEF_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), stream));
+  rc = launch_form_P_padded(A, lda, w, noise, p, q, dense_work_factor(ctx->work), stream);
+  if (rc == GRIEF_OK) rc = dense_potrf(ctx->work, q, ctx->d_info, stream, launches);
+  if (rc != GRIEF_OK) return rc;
   int info = 0;
   GRIEF_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, stream));
   GRIEF_CUDA(cudaStreamSynchronize(stream));
   if (info_out) *info_out = info;
   if (info != 0) return fail(GRIEF_ERR_NOT_PD, "Cholesky failed: leading minor of order %d of P = A + diag(noise_var/w) is not positive definite", info);
-  GRIEF_CUDA(cudaMemcpyAsync(b, r, (size_t)p * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-  if (cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, p, 1, L, p, b, p, ctx->d_info) != CUSOLVER_STATUS_SUCCESS)
-    return fail(GRIEF_ERR_LIBRARY, "cusolverDnDpotrs failed");
+  rc = launch_copy_block(dense_work_factor(ctx->work), q, p, true, true, L, p, stream);
+  if (rc == GRIEF_OK) rc = dense_trsv_pair(ctx->work, q, r, p, b, dense_work_tmp(ctx->work), stream, launches);
+  if (rc != GRIEF_OK) return rc;
   if (Pinv) {
-    // P^-1 = solve(P, I): two triangular solves with p right-hand sides (measured ~10x faster than cusolverDnDpotri
-    // at p = 4096, profiles/r01_launch_list_summary.txt).  The result is symmetric up to rounding; the symmetric
-    // part is taken so that P^-1 and G2 are exactly symmetric (k_zgemm reads B[n][k] for b[k][n]).
-    k_set_identity<<<eb, 256, 0, stream>>>(Pinv, p);
-    GRIEF_CUDA(cudaGetLastError());
-    if (cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, p, p, L, p, Pinv, p, ctx->d_info) != CUSOLVER_STATUS_SUCCESS)
-      return fail(GRIEF_ERR_LIBRARY, "cusolverDnDpotrs (inverse) failed");
-    k_symmetrize_mean<<<eb, 256, 0, stream>>>(Pinv, p);
-    GRIEF_CUDA(cudaGetLastError());
+    rc = dense_inverse_from_factor(ctx->work, q, stream, launches);
+    if (rc == GRIEF_OK) rc = launch_copy_block(dense_work_inverse(ctx->work), q, p, false, false, Pinv, p, stream);
+    if (rc != GRIEF_OK) return rc;
   }
   k_assemble<<<1, 1024, 0, stream>>>(L, Pinv, r, b, w, yty, noise, (double)n_rows, p, grad_w, ctx->d_scalars);
   GRIEF_CUDA(cudaGetLastError());
@@ -214,7 +165,7 @@ int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* 
   prof_end(PROF_SOLVE, stream);
   GRIEF_CUDA(cudaMemcpyAsync(scalars_host, ctx->d_scalars, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
   GRIEF_CUDA(cudaStreamSynchronize(stream));
-  if (launches) *launches += 2 + (Pinv ? 1 : 0) + (G2 ? 1 : 0);
+  if (launches) *launches += 4 + (Pinv ? 1 : 0) + (G2 ? 1 : 0);
   return GRIEF_OK;
 }
 

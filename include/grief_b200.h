@@ -33,7 +33,7 @@ extern "C" {
 #define GRIEF_ERR_CUDA 2         /* -> RuntimeError                                             */
 #define GRIEF_ERR_NOT_PD 3       /* -> numpy.linalg.LinAlgError (what scipy cho_factor raises)   */
 #define GRIEF_ERR_UNSUPPORTED 4  /* -> NotImplementedError                                      */
-#define GRIEF_ERR_LIBRARY 5      /* -> RuntimeError (cuSOLVER)                                  */
+#define GRIEF_ERR_LIBRARY 5      /* -> RuntimeError (driver entry point missing)                */
 
 #define GRIEF_KERN_RBF 0         /* kern/stationary.py:108-134 */
 #define GRIEF_KERN_EXPONENTIAL 1 /* kern/stationary.py:161-175 */
@@ -51,7 +51,7 @@ extern "C" {
 #define GRIEF_SC_COUNT 7
 
 typedef struct grief_plan grief_plan; /* one basis (one value of the kernel hyper-parameters) */
-typedef struct grief_ctx grief_ctx;   /* per-model scratch: cuSOLVER handle and workspaces     */
+typedef struct grief_ctx grief_ctx;   /* per-model scratch: dense-stage workspaces             */
 
 int grief_version(void);
 const char* grief_last_error(void);
@@ -146,7 +146,8 @@ int grief_sumsq(const double* y_dev, int64_t n, double* out_dev, void* ws_dev, v
  * The p x p stage (models/gp_grief_model.py:152-153 cho_factor, :234 cho_solve, :243-245 log-det,
  * :212-213 LML, :171-180 d/dw, :185-191 d/d noise_var), from the reduced statistics A, r, y^T y.
  *   n_rows          total number of data rows (over all GPUs)
- *   L_dev           out (p,p): Cholesky factor of P = A + diag(noise_var/w) (cuSOLVER lower, column-major)
+ *   L_dev           out (p,p): upper Cholesky factor U of P = A + diag(noise_var/w), P = U^T U, row-major,
+ *                   strictly lower part zero (what scipy.linalg.cho_factor + np.triu give)
  *   b_dev           out (p): P^-1 r  (== alpha_p of models/gp_grief_model.py:97)
  *   Pinv_dev        out (p,p) or NULL: P^-1 (needed for the gradients)
  *   grad_w_dev      out (p) or NULL

@@ -168,3 +168,48 @@ def test_gram_larger_random_shape_vs_materialised_phi():
     assert_allclose(A.cpu().numpy(), A_ref.cpu().numpy(), rtol=0, atol=1e-12 * float(A_ref.abs().max()))
     Phi_o = orc.grief_phi(basis, names, var, ls, xg, X[:2000].cpu().numpy())
     assert_allclose(Phi[:2000].cpu().numpy(), Phi_o, rtol=1e-11, atol=1e-13 * np.abs(Phi_o).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p", [1, 5, 127, 128, 129, 300, 640, 1000])
+def test_dense_stage_against_scipy(p):
+    """The hand-written Cholesky / solve / inverse (dense.cu) against scipy (reference gp_grief_model.py:152-153,171-191)."""
+    import scipy.linalg as sl
+    import torch
+    rng = np.random.RandomState(100 + p)
+    n = 4 * p + 7
+    Phi = rng.randn(n, p) / np.sqrt(n)
+    y = rng.randn(n)
+    w = rng.rand(p) + 0.5
+    noise = 0.3
+    A = Phi.T.dot(Phi)
+    r = Phi.T.dot(y)
+    P = A + np.diag(noise / w)
+    U = sl.cho_factor(P)[0]
+    b_ref = sl.cho_solve((np.triu(U), False), r)
+    Pinv_ref = np.linalg.inv(P)
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = _dev().DeviceSolver().solve(dv(A), dv(r), dv(np.array([y.dot(y)])), dv(w), noise, n, want_grad=True, want_G2=True)
+    L = out["L"].cpu().numpy()
+    assert np.all(np.tril(L, -1) == 0.0)
+    np.testing.assert_allclose(L, np.triu(U), rtol=1e-10, atol=1e-12 * np.abs(U).max())
+    np.testing.assert_allclose(out["b"].cpu().numpy(), b_ref, rtol=1e-9, atol=1e-11 * np.abs(b_ref).max())
+    Pinv = out["Pinv"].cpu().numpy()
+    assert np.array_equal(Pinv, Pinv.T)
+    np.testing.assert_allclose(Pinv, Pinv_ref, rtol=1e-8, atol=1e-10 * np.abs(Pinv_ref).max())
+    logdet = 2.0 * np.log(np.diag(U)).sum()
+    logdet_full = logdet + np.log(w).sum() + (n - p) * np.log(noise)       # log|Phi W Phi^T + noise I|
+    assert abs(out["logdet"] - logdet_full) <= 1e-10 * max(1.0, abs(logdet_full))
+    G2_ref = -(Pinv_ref + np.outer(b_ref, b_ref) / noise)
+    np.testing.assert_allclose(out["G2"].cpu().numpy(), G2_ref, rtol=1e-8, atol=1e-10 * np.abs(G2_ref).max())
+
+
+@pytest.mark.gpu
+def test_dense_stage_not_pd_reports_minor():
+    import torch
+    p = 200
+    A = np.eye(p)
+    A[150, 150] = -5.0
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    with pytest.raises(np.linalg.LinAlgError, match="151"):
+        _dev().DeviceSolver().solve(dv(A), dv(np.ones(p)), dv(np.array([1.0])), dv(np.full(p, 1e30)), 0.5, 100)
