@@ -49,6 +49,7 @@ SIGNATURES = {
                                  c_void, c_size, c_void]),
     "grief_quadform_workspace_bytes": (c_size, [c_void, c_i64]),
     "grief_quadform_rows": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_void, c_size, c_void]),
+    "grief_gemm_nt": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
     "grief_solve_lml": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void, c_void, c_dbl, c_i64, c_void, c_void,
                                 c_void, c_void, c_void, c_void, _P(c_int), c_void]),
 }
@@ -99,7 +100,8 @@ def check(rc):
     raise RuntimeError("libgrief_b200 error %d: %s" % (rc, msg))
 
 
-PROFILE_SLOTS = ("k_gram", "k_zgemm", "k_tables", "k_contract", "k_topk", "solve", "phi_t_y", "k_dtables")
+PROFILE_SLOTS = ("k_gram", "k_zgemm", "k_tables", "k_contract", "k_topk", "solve", "phi_t_y", "k_dtables", "k_build_phi_t",
+                 "k_build_phi")
 
 
 def profile_enable(on=True):

@@ -33,7 +33,7 @@ int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t
 int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream);
 int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream);
 int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream);
-int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Z, int64_t ldz, int sms,
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Phi_slab, double* Z, int64_t ldz,
                  cudaStream_t stream, int* launches);
 int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
 
@@ -62,6 +62,11 @@ using namespace grief;
 
 struct grief_plan { Plan* impl; };
 struct grief_ctx { SolveCtx* solve; };
+
+namespace grief {
+int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K,
+            double alpha, double beta, bool lower_only, bool store_t, cudaStream_t stream, int* launches, bool tri_k);
+}
 
 extern "C" {
 
@@ -194,7 +199,7 @@ size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   if (!pl->grad) return 0;
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
-  return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
+  return 2 * align256((size_t)slab * pl->p_pad * sizeof(double)) + align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
          align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p * sizeof(double)) +
          align256((size_t)pl->p * pl->p_pad * sizeof(double));
 }
@@ -213,6 +218,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   const int64_t slab = slab_rows_for(n, sms);
   char* q = reinterpret_cast<char*>(workspace_dev);
   double* Z = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
+  double* PhiS = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
   double* DT = reinterpret_cast<double*>(q); q += align256((size_t)slab * std::max(1, dtw) * sizeof(double));
   double* partial = reinterpret_cast<double*>(q); q += align256((size_t)contract_blocks(sms) * std::max(1, na) * sizeof(double));
   double* gvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p * sizeof(double));
@@ -228,7 +234,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, Z, pl->p_pad, sms, stream, &g_launches);
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, PhiS, Z, pl->p_pad, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_dtables(pl, gd, X_dev + (size_t)r0 * ldx, ldx, rows_valid, rows_valid, DT, stream);
     if (rc != GRIEF_OK) return rc;
@@ -243,7 +249,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
 
 size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
-  return align256((size_t)slab_rows_for(n, sm_count()) * pl->p_pad * sizeof(double)) + align256((size_t)pl->p * pl->p_pad * sizeof(double));
+  return 2 * align256((size_t)slab_rows_for(n, sm_count()) * pl->p_pad * sizeof(double)) + align256((size_t)pl->p * pl->p_pad * sizeof(double));
 }
 
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb, double* q_dev,
@@ -255,7 +261,8 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   double* Z = reinterpret_cast<double*>(workspace_dev);
-  double* Bperm = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace_dev) + align256((size_t)slab * pl->p_pad * sizeof(double)));
+  double* PhiS = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace_dev) + align256((size_t)slab * pl->p_pad * sizeof(double)));
+  double* Bperm = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace_dev) + 2 * align256((size_t)slab * pl->p_pad * sizeof(double)));
   {
     int rc0 = launch_permute_b(pl, B_dev, ldb, Bperm, stream);
     if (rc0 != GRIEF_OK) return rc0;
@@ -265,13 +272,21 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, Z, pl->p_pad, sms, stream, &g_launches);
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, PhiS, Z, pl->p_pad, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_rowdot(pl, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, rows_valid, q_dev + r0, stream);
     if (rc != GRIEF_OK) return rc;
     g_launches += 1;
   }
   return GRIEF_OK;
+}
+
+int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M, int N, int K,
+                  double alpha, double beta, void* stream_) {
+  GRIEF_REQUIRE(A_dev && B_dev && C_dev, "grief_gemm_nt: null pointer");
+  GRIEF_REQUIRE(M % 128 == 0 && N % 128 == 0 && K % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0,
+                "grief_gemm_nt: M=%d N=%d must be multiples of 128 and K=%d, lda, ldb even", M, N, K);
+  return gemm_nt(A_dev, lda, B_dev, ldb, C_dev, ldc, M, N, K, alpha, beta, false, false, (cudaStream_t)stream_, &g_launches, false);
 }
 
 }  // extern "C"

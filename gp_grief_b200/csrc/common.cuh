@@ -31,7 +31,7 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 // ---- optional per-kernel timing (CUDA events on the launch stream; off by default) --------------------
-enum ProfSlot : int { PROF_GRAM = 0, PROF_ZGEMM, PROF_TABLES, PROF_CONTRACT, PROF_TOPK, PROF_SOLVE, PROF_PHITY, PROF_DTABLES, PROF_COUNT };
+enum ProfSlot : int { PROF_GRAM = 0, PROF_ZGEMM, PROF_TABLES, PROF_CONTRACT, PROF_TOPK, PROF_SOLVE, PROF_PHITY, PROF_DTABLES, PROF_BUILD_T, PROF_BUILD, PROF_COUNT };
 void prof_begin(int slot, cudaStream_t stream);
 void prof_end(int slot, cudaStream_t stream);
 

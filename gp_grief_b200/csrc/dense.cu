@@ -16,6 +16,9 @@
 
 namespace grief {
 
+int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K,
+            double alpha, double beta, bool lower_only, bool store_t, cudaStream_t stream, int* launches, bool tri_k = false);
+
 constexpr int kDB = 128;                 // block size of the blocked algorithms = GEMM tile edge
 constexpr int kGemmThreads = 512;
 constexpr int kGemmStages = 4;
@@ -29,6 +32,8 @@ struct GemmParams {
   int lower_only;      // skip tiles strictly above the block diagonal
   int store_t;         // write C^T: element (m, n) goes to C[n * ldc + m]
   int tri_k;           // operands are upper block triangular in K: start the K loop at block bm (needs bm >= bn)
+  int split_chunks;    // > 0: blockIdx.z owns K chunks [z * split_chunks, (z + 1) * split_chunks) and the C copy z
+  int64_t c_split_stride;
 };
 
 __device__ __forceinline__ void tma_tile_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -56,8 +61,10 @@ k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     fence_barrier_init();
   }
   __syncthreads();
-  const int c_first = prm.tri_k ? bm * (kDB / kChunk) : 0;
-  const int nk = (prm.K + kChunk - 1) / kChunk - c_first;
+  const int c_first = prm.tri_k ? bm * (kDB / kChunk) : (int)blockIdx.z * prm.split_chunks;
+  int nk = (prm.K + kChunk - 1) / kChunk - c_first;
+  if (prm.split_chunks > 0 && nk > prm.split_chunks) nk = prm.split_chunks;
+  double* const Cz = prm.C + (size_t)blockIdx.z * prm.c_split_stride;
   auto issue = [&](int c) {
     const int st = c % kGemmStages;
     unsigned char* dst = ring + (size_t)st * kGemmStageBytes;
@@ -110,7 +117,7 @@ k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       for (int i = 0; i < 4; ++i) {
         const int m = bm * kDB + wm * 32 + mt * 16 + g4 + 8 * (i >> 1);
         const int n = bn * kDB + wn * 32 + nt * 8 + 2 * t4 + (i & 1);
-        double* dst = prm.store_t ? prm.C + (size_t)n * prm.ldc + m : prm.C + (size_t)m * prm.ldc + n;
+        double* dst = prm.store_t ? Cz + (size_t)n * prm.ldc + m : Cz + (size_t)m * prm.ldc + n;
         double v = prm.alpha * acc[mt][nt][i];
         if (prm.beta != 0.0) v += prm.beta * (*dst);
         *dst = v;
@@ -147,28 +154,44 @@ static int make_map(CUtensorMap* map, const double* base, int rows, int cols, in
 }
 
 // C (M x N, ldc) = beta*C + alpha * A (M x K, lda) * B (N x K, ldb)^T.   M, N multiples of 128; lda, ldb even.
-int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K,
-            double alpha, double beta, bool lower_only, bool store_t, cudaStream_t stream, int* launches, bool tri_k = false) {
+// rows_a / rows_b: rows of A / B that exist in memory (the rest of the M / N range reads as zeros through the TMA
+// out-of-bounds fill); splits > 1: split K over blockIdx.z, split z accumulating into C + z * c_split_stride.
+int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K, double alpha,
+               double beta, const GemmOpts& o, cudaStream_t stream, int* launches) {
   if (M <= 0 || N <= 0) return GRIEF_OK;
-  GRIEF_REQUIRE(M % kDB == 0 && N % kDB == 0 && K > 0, "gemm_nt: M=%d N=%d K=%d", M, N, K);
+  GRIEF_REQUIRE(M % kDB == 0 && N % kDB == 0 && K >= 0, "gemm_nt: M=%d N=%d K=%d", M, N, K);
+  GRIEF_REQUIRE(!(o.tri_k && o.splits > 1), "gemm_nt: tri_k and split K do not combine");
   alignas(64) CUtensorMap mA, mB;
-  int rc = make_map(&mA, A, M, K, lda);
-  if (rc == GRIEF_OK) rc = make_map(&mB, B, N, K, ldb);
+  const int Kmap = std::max(K, 2);
+  int rc = make_map(&mA, A, o.rows_a > 0 ? o.rows_a : M, Kmap, lda);
+  if (rc == GRIEF_OK) rc = make_map(&mB, B, o.rows_b > 0 ? o.rows_b : N, Kmap, ldb);
   if (rc != GRIEF_OK) return rc;
   GemmParams prm;
   prm.C = C; prm.ldc = ldc; prm.K = K; prm.alpha = alpha; prm.beta = beta;
-  prm.lower_only = lower_only ? 1 : 0; prm.store_t = store_t ? 1 : 0; prm.tri_k = tri_k ? 1 : 0;
+  prm.lower_only = o.lower_only ? 1 : 0; prm.store_t = o.store_t ? 1 : 0; prm.tri_k = o.tri_k ? 1 : 0;
+  const int splits = std::max(1, o.splits);
+  const int chunks = (K + kChunk - 1) / kChunk;
+  prm.split_chunks = splits > 1 ? (chunks + splits - 1) / splits : 0;
+  prm.c_split_stride = o.c_split_stride;
   const size_t smem = 1024 + 1024 + (size_t)kGemmStages * kGemmStageBytes;
   static bool attr_set = false;
   if (!attr_set) {
     GRIEF_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(N / kDB, M / kDB);
+  dim3 grid(N / kDB, M / kDB, splits);
   k_gemm_nt<<<grid, kGemmThreads, smem, stream>>>(mA, mB, prm);
   GRIEF_CUDA(cudaGetLastError());
   if (launches) *launches += 1;
   return GRIEF_OK;
+}
+
+int gemm_nt(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K,
+            double alpha, double beta, bool lower_only, bool store_t, cudaStream_t stream, int* launches, bool tri_k) {
+  GemmOpts o;
+  o.lower_only = lower_only; o.store_t = store_t; o.tri_k = tri_k;
+  GRIEF_REQUIRE(K > 0, "gemm_nt: K=%d", K);
+  return gemm_nt_ex(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, o, stream, launches);
 }
 
 // sum over k = k_begin, k_begin + 4, ... < k_end of a[k] * b[k], with four independent chains so that the shared-memory

@@ -4,7 +4,7 @@
 //   dLML/dtheta = sum_n sum_j Zt[n,j] * dPhi[n,j]/dtheta,    Zt = Phi * G2 + y g^T,
 //   G2 = -(P^-1 + b b^T/sigma^2),  g = b/sigma^2                                
 //
-// Z = Phi*G2 comes from k_zgemm (zgemm.cu), one slab of rows at a time.  For a parameter theta of
+// Z = Phi*G2 comes from launch_zgemm (phi_stage.cu: Phi slab builder + k_gemm_nt), one slab of rows at a time.  For a parameter theta of
 // input dimension i (group g of the table layout) only the factor of dimension i changes:
 //   dPhi[n,j]/dtheta = DT_theta[n, t_g(j)] * prod_{g' != g} H_g'[n, t_g'(j)]
 //   DT_theta[n,t]    = dF_i[n,k_i(t)]/dtheta * prod_{i' in g, i' != i} F_i'[n,k_i'(t)]

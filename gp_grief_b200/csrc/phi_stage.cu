@@ -1,0 +1,272 @@
+// The two O(n p^2) products of an evaluation, staged:  the basis matrix Phi of a slab of data rows is built by a
+// bandwidth-bound kernel into HBM, then a plain TMA-fed FP64 DMMA GEMM (dense.cu, k_gemm_nt) consumes it.
+//
+//   pass 1 (models/gp_grief_model.py:148-149)   A = Phi^T Phi :  Phi^T slab (p_pad x R, data rows contiguous)
+//                                               -> SYRK on the lower tiles, K = data rows split over gridDim.z
+//   pass 2 / predictive var.    Z = Phi B     :  Phi slab (R x p_pad, sorted columns contiguous)
+//                                               -> GEMM against the column-permuted symmetric B
+//
+// Why staged and not fused (round-1 measurements, profiles/r01_gram_design_notes.md): DMUL, DFMA and DMMA share ONE FP64
+// pipe per SM sub-partition.  With the Phi tiles built inside the GEMM CTAs the builder's DMULs queue behind the DMMAs
+// (32 % of warp samples in stall_math) and the kernels stop at 25-28 TFLOP/s; the same DMMA loop fed by TMA alone runs at
+// 33 TFLOP/s.  The slab costs 8 B written + 8 B read per element of Phi, 1-2 % of the GEMM time at HBM speed, and
+// HBM is otherwise idle during these passes.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "plan.h"
+
+namespace grief {
+
+constexpr int kBuildRows = 128;       // table rows per builder CTA
+constexpr int kBuildThreads = 512;
+
+// table rows [rb*128, rb*128+128) -> shared memory (bulk async copy in 16-row pieces), one barrier
+__device__ __forceinline__ void stage_table_rows(double* sT, uint64_t* bar, const double* T, int stride, int64_t rb) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    const uint32_t piece = (uint32_t)(16 * stride * sizeof(double));
+    fence_proxy_async();
+    mbar_arrive_expect_tx(bar, piece * (kBuildRows / 16));
+    for (int i = 0; i < kBuildRows / 16; ++i)
+      bulk_g2s(sT + (size_t)i * 16 * stride, T + ((size_t)rb * kBuildRows + i * 16) * stride, piece, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+// Phi^T slab: out[c * ld + row], c = sorted column.  Lane = data row; a warp walks a run of consecutive sorted columns,
+// which share their leading slots: the product P of the first G-1 factors stays in a register and is rebuilt only where
+// sorted_level says a leading factor changed (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
+template <int G>
+__global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __restrict__ T, int stride,
+                                                               const uint16_t* __restrict__ sorted_slot,
+                                                               const uint8_t* __restrict__ sorted_level, int p_pad,
+                                                               double* __restrict__ out, int64_t ld) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* sT = reinterpret_cast<double*>(smem_raw + 128);
+  stage_table_rows(sT, bar, T, stride, blockIdx.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = (warp & 3) * 32 + lane;
+  const double* trow = sT + (size_t)row * stride;
+  const int cpq = p_pad / 4;                           // four warps share a row group, a quarter of the columns each
+  const int c_begin = (warp >> 2) * cpq;
+  double* dst = out + (size_t)blockIdx.x * kBuildRows + row;
+  constexpr int NB = 8;
+  double P = 1.0;
+  for (int c0 = c_begin; c0 < c_begin + cpq; c0 += NB) {
+    double last[NB];
+    int lv[NB];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) {
+      lv[e] = (c0 + e == c_begin) ? 0 : (int)__ldg(sorted_level + c0 + e);
+      last[e] = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + (G - 1))];
+    }
+#pragma unroll
+    for (int e = 0; e < NB; ++e) {
+      if constexpr (G > 1) {
+        if (lv[e] < G - 1) {
+          double q = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G)];
+#pragma unroll
+          for (int g = 1; g < G - 1; ++g) q *= trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + g)];
+          P = q;
+        }
+        last[e] *= P;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NB; ++e) dst[(size_t)(c0 + e) * ld] = last[e];
+  }
+}
+
+// Phi slab, row-major: out[row * ldo + c].  Lane = sorted column (coalesced stores); the G slots of a column are loaded
+// once and reused for the warp's eight rows.
+template <int G>
+__global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __restrict__ T, int stride,
+                                                             const uint16_t* __restrict__ sorted_slot, int p_pad,
+                                                             double* __restrict__ out, int64_t ldo) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* sT = reinterpret_cast<double*>(smem_raw + 128);
+  stage_table_rows(sT, bar, T, stride, blockIdx.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int RW = kBuildRows / (kBuildThreads / 32);   // 8 rows per warp
+  const double* tbase = sT + (size_t)warp * RW * stride;
+  double* obase = out + ((size_t)blockIdx.x * kBuildRows + warp * RW) * ldo;
+  for (int c = lane; c < p_pad; c += 32) {
+    int sl[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) sl[g] = __ldg(sorted_slot + (size_t)c * G + g);
+    double v[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) v[r] = tbase[r * stride + sl[0]];
+#pragma unroll
+    for (int g = 1; g < G; ++g)
+#pragma unroll
+      for (int r = 0; r < RW; ++r) v[r] *= tbase[r * stride + sl[g]];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) obase[(size_t)r * ldo + c] = v[r];
+  }
+}
+
+template <int G>
+static int launch_build_g(const Plan* pl, const double* T, int64_t rows, bool transposed, double* out, int64_t ld, cudaStream_t stream) {
+  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
+  const unsigned grid = (unsigned)(rows / kBuildRows);
+  if (transposed) {
+    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_build_phi_t<G><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad, out, ld);
+  } else {
+    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_build_phi<G><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, out, ld);
+  }
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+// rows: multiple of 128.  transposed: out is p_pad x ld (ld >= rows); otherwise rows x ld (ld >= p_pad).
+static int launch_build(const Plan* pl, const double* T, int64_t rows, bool transposed, double* out, int64_t ld, cudaStream_t stream) {
+  if (rows == 0) return GRIEF_OK;
+  GRIEF_REQUIRE(rows % kBuildRows == 0, "build_phi: rows=%lld is not a multiple of %d", (long long)rows, kBuildRows);
+  switch (pl->n_groups) {
+    case 1: return launch_build_g<1>(pl, T, rows, transposed, out, ld, stream);
+    case 2: return launch_build_g<2>(pl, T, rows, transposed, out, ld, stream);
+    case 3: return launch_build_g<3>(pl, T, rows, transposed, out, ld, stream);
+    case 4: return launch_build_g<4>(pl, T, rows, transposed, out, ld, stream);
+    case 5: return launch_build_g<5>(pl, T, rows, transposed, out, ld, stream);
+    case 6: return launch_build_g<6>(pl, T, rows, transposed, out, ld, stream);
+    case 7: return launch_build_g<7>(pl, T, rows, transposed, out, ld, stream);
+    case 8: return launch_build_g<8>(pl, T, rows, transposed, out, ld, stream);
+    default: return fail(GRIEF_ERR_UNSUPPORTED, "build_phi: %d groups", pl->n_groups);
+  }
+}
+
+// ---- pass 1: A = Phi^T Phi ----
+struct GramSchedule {
+  int nb, n_tiles, splits;
+  int64_t slab_rows;
+};
+
+GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
+  GramSchedule s;
+  s.nb = p_pad / kTileN;
+  s.n_tiles = s.nb * (s.nb + 1) / 2;
+  const int64_t budget_rows = ((int64_t)4 << 30) / ((int64_t)p_pad * 8) / kBuildRows * kBuildRows;   // 4 GiB of Phi^T
+  s.slab_rows = std::max<int64_t>(kBuildRows, std::min<int64_t>(n_pad, std::max<int64_t>(kBuildRows, budget_rows)));
+  // K splits: fill whole waves of `sms` CTAs, keep >= 256 data rows per split
+  const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.slab_rows / 256, 64));
+  int best = 1;
+  double best_eff = -1.0;
+  for (int64_t S = 1; S <= max_splits; ++S) {
+    const int64_t items = S * s.n_tiles;
+    const int64_t waves = (items + sms - 1) / sms;
+    const double eff = (double)items / (double)(waves * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)S; }
+    if (eff >= 0.97) { best = (int)S; break; }
+  }
+  s.splits = best;
+  return s;
+}
+
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms) {
+  const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
+  return align256((size_t)pl->p_pad * s.slab_rows * sizeof(double)) + (size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double);
+}
+
+// A[perm[i]][perm[j]] = sum_s part[s][i][j] over the lower tiles (fixed split order), mirrored bit-identically.
+__global__ void __launch_bounds__(256)
+k_gram_reduce(const double* __restrict__ part, const int* __restrict__ perm, int p_pad, int splits, int64_t lda, double* __restrict__ A) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const size_t pp = (size_t)p_pad * p_pad;
+  for (int e = threadIdx.x; e < kTileN * kTileN; e += blockDim.x) {
+    const int m = e / kTileN, n = e - m * kTileN;
+    const int srow = bi * kTileN + m, scol = bj * kTileN + n;
+    if (bi == bj && scol > srow) continue;
+    const int row = perm[srow], col = perm[scol];
+    if (row < 0 || col < 0) continue;                // padding columns
+    double s = 0.0;
+    for (int sp = 0; sp < splits; ++sp) s += part[sp * pp + (size_t)srow * p_pad + scol];
+    A[(size_t)row * lda + col] = s;
+    A[(size_t)col * lda + row] = s;
+  }
+}
+
+int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, void* workspace, size_t ws_bytes,
+                int sms, cudaStream_t stream, int* launches) {
+  GRIEF_REQUIRE(n_pad % kBuildRows == 0, "gram: n_pad=%lld must be a multiple of %d", (long long)n_pad, kBuildRows);
+  GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
+  const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
+  const int pp = pl->p_pad;
+  double* PhiT = reinterpret_cast<double*>(workspace);
+  double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + align256((size_t)pp * s.slab_rows * sizeof(double)));
+  const size_t part_doubles = (size_t)s.splits * pp * pp;
+  if (n_pad == 0) GRIEF_CUDA(cudaMemsetAsync(part, 0, part_doubles * sizeof(double), stream));
+  GemmOpts o;
+  o.lower_only = true;
+  o.splits = s.splits;
+  o.c_split_stride = (int64_t)pp * pp;
+  for (int64_t r0 = 0; r0 < n_pad; r0 += s.slab_rows) {
+    const int64_t R = std::min(s.slab_rows, n_pad - r0);
+    prof_begin(PROF_BUILD_T, stream);
+    int rc = launch_build(pl, T + (size_t)r0 * pl->stride, R, true, PhiT, s.slab_rows, stream);
+    prof_end(PROF_BUILD_T, stream);
+    if (rc != GRIEF_OK) return rc;
+    prof_begin(PROF_GRAM, stream);
+    rc = gemm_nt_ex(PhiT, s.slab_rows, PhiT, s.slab_rows, part, pp, pp, pp, (int)R, 1.0, r0 > 0 ? 1.0 : 0.0, o, stream, launches);
+    prof_end(PROF_GRAM, stream);
+    if (rc != GRIEF_OK) return rc;
+    if (launches) *launches += 1;
+  }
+  k_gram_reduce<<<dim3(s.nb, s.nb), 256, 0, stream>>>(part, pl->d_perm, pp, s.splits, lda, A);
+  GRIEF_CUDA(cudaGetLastError());
+  if (launches) *launches += 1;
+  return GRIEF_OK;
+}
+
+// ---- pass 2 / predictive variance: Z = Phi B ----
+// B'[c][k] = B[c][perm[k]] (0 for padding columns): the K dimension of Z = Phi * B is walked in sorted column order.
+__global__ void __launch_bounds__(256)
+k_permute_cols(const double* __restrict__ B, int64_t ldb, const int* __restrict__ perm, int p, int p_pad, double* __restrict__ out) {
+  const int64_t total = (int64_t)p * p_pad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e / p_pad), k = (int)(e - (int64_t)c * p_pad);
+    const int src = perm[k];
+    out[e] = src >= 0 ? B[(size_t)c * ldb + src] : 0.0;
+  }
+}
+
+int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream) {
+  const int64_t total = (int64_t)pl->p * pl->p_pad;
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  k_permute_cols<<<blocks, 256, 0, stream>>>(B, ldb, pl->d_perm, pl->p, pl->p_pad, Bperm);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+// Z (slab_rows x ldz; columns >= p are zero) = Phi(slab) * B, B symmetric given as Bperm (p x p_pad, launch_permute_b).
+// Phi_slab: scratch of slab_rows x p_pad doubles.
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Phi_slab, double* Z, int64_t ldz,
+                 cudaStream_t stream, int* launches) {
+  GRIEF_REQUIRE(slab_rows % kBuildRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kBuildRows);
+  GRIEF_REQUIRE(ldz >= pl->p_pad, "zgemm: ldz=%lld must be >= p_pad=%d", (long long)ldz, pl->p_pad);
+  if (slab_rows == 0) return GRIEF_OK;
+  prof_begin(PROF_BUILD, stream);
+  int rc = launch_build(pl, T_slab, slab_rows, false, Phi_slab, pl->p_pad, stream);
+  prof_end(PROF_BUILD, stream);
+  if (rc != GRIEF_OK) return rc;
+  GemmOpts o;
+  o.rows_b = pl->p;                                   // rows p..p_pad of B' do not exist: TMA fills zeros
+  prof_begin(PROF_ZGEMM, stream);
+  rc = gemm_nt_ex(Phi_slab, pl->p_pad, Bperm, pl->p_pad, Z, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);
+  prof_end(PROF_ZGEMM, stream);
+  if (rc == GRIEF_OK && launches) *launches += 1;
+  return rc;
+}
+
+}  // namespace grief

@@ -70,4 +70,16 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
                 const double* lengthscale, const double* grid_concat, const int32_t* u,
                 const double* qs_concat, int p, const int32_t* uinv, int width_cap);
 
+// TMA-fed FP64 DMMA GEMM (dense.cu):  C = beta*C + alpha * A * B^T,  A (M x K) and B (N x K) row-major, K contiguous.
+struct GemmOpts {
+  bool lower_only = false;   // skip tiles strictly above the block diagonal
+  bool store_t = false;      // write C^T
+  bool tri_k = false;        // K loop starts at the block row (operands upper block triangular in K)
+  int splits = 1;            // split K over gridDim.z; split z accumulates into C + z * c_split_stride
+  int64_t c_split_stride = 0;
+  int rows_a = 0, rows_b = 0;   // rows of A / B present in memory (0: all M / N); the rest reads as zeros
+};
+int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K, double alpha,
+               double beta, const GemmOpts& opts, cudaStream_t stream, int* launches);
+
 }  // namespace grief

@@ -1,10 +1,10 @@
 """GP-GRIEF regression model on the B200 (reference: gp_grief/models/gp_grief_model.py).
 
 Same class, constructor and methods as the reference.  Data rows live on the GPU; one evaluation is
-    prepass tables  ->  fused Gram A = Phi^T Phi, r = Phi^T y, s = y^T y   (csrc/rows.cu, csrc/gram_syrk.cu)
+    prepass tables  ->  Gram A = Phi^T Phi, r = Phi^T y, s = y^T y   (csrc/rows.cu, csrc/phi_stage.cu, csrc/dense.cu)
     [all-reduce of (A | r | s) when the rows are sharded over ranks]
     Cholesky / solve / LML / d/dw / d/dnoise_var                           (csrc/solve.cu)
-    analytic d/d(kernel hyper-parameters)                                  (csrc/zgemm.cu, csrc/grad.cu)
+    analytic d/d(kernel hyper-parameters)                                  (csrc/phi_stage.cu, csrc/dense.cu, csrc/grad.cu)
 and Phi (n x p) is never formed.  Differences from the reference that a caller can observe:
   * `_Phi`, `_alpha` are computed on demand (they are n-sized); `_A`, `_P`, `_Pchol` are host copies.
   * with `opt_kernel_params=True` and distinct in-house kernels the default `grad_method` is the analytic

@@ -3,7 +3,7 @@
 `KhatriRaoMatrix` is the row/column-partitioned block-Kronecker container GridKernel.cov_kr returns;
 `RowColKhatriRaoMatrix` is the R*K*C product with memory-bounded row chunking.  Both are host NumPy
 containers: the GRIEF hot path never goes through them (the device builds Phi tiles directly from the
-per-dimension factors, csrc/gram_syrk.cu) -- exactly as in the reference, whose GriefKernel imports
+per-dimension factors, csrc/phi_stage.cu) -- exactly as in the reference, whose GriefKernel imports
 RowColKhatriRaoMatrix but calls expand_SKC instead.
 """
 import numpy as np

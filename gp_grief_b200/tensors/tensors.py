@@ -71,7 +71,7 @@ def expand_SKC(S, K, C, logged=True):
 
     Same contract as the reference (tensors/tensors.py:97-128): returns `prod` (p, n), or with
     logged=True the pair (log|prod|, sign).  The GP-GRIEF model does NOT call this: its Phi is produced
-    tile by tile on the GPU (csrc/rows.cu + csrc/gram_syrk.cu) from the same three ingredients.
+    tile by tile on the GPU (csrc/rows.cu + csrc/phi_stage.cu) from the same three ingredients.
     """
     assert isinstance(S, (list, np.ndarray))
     assert isinstance(S[0], SelectionMatrixSparse)

@@ -190,6 +190,14 @@ size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n);
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb,
                         double* q_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/*
+ * C (M x N, ldc) = beta * C + alpha * A (M x K, lda) * B (N x K, ldb)^T, all row-major on the device; the TMA-fed FP64 DMMA
+ * GEMM the dense stage is built on.  M, N multiples of 128; K, lda, ldb even.  Stands in for the numpy `dot` calls on
+ * p x p and M x p operands (models/gp_grief_model.py:122-124 full predictive covariance).
+ */
+int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M,
+                  int N, int K, double alpha, double beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
