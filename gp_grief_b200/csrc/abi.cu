@@ -18,6 +18,7 @@ int launch_phi_t_vec(const Plan* pl, const double* T, int64_t n, const double* v
 int launch_phi_vec(const Plan* pl, const double* T, int64_t n, const double* v, double* out, cudaStream_t stream);
 int launch_sumsq(const double* y, int64_t n, double* out, double* ws, cudaStream_t stream);
 size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms);
+void set_slab_budget(size_t bytes);
 int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, void* workspace, size_t ws_bytes,
                 int sms, cudaStream_t stream, int* launches);
 int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const double* logeig_host, int p, int32_t* idx_dev,
@@ -144,6 +145,8 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
   if (rc == GRIEF_OK && n > 0) g_launches += 1;
   return rc;
 }
+
+void grief_set_slab_budget(size_t bytes) { set_slab_budget(bytes); }
 
 size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n) {
   return gram_workspace_bytes(plan->impl, grief_table_rows(n), sm_count());

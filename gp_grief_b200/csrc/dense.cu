@@ -34,30 +34,44 @@ struct GemmParams {
   int tri_k;           // operands are upper block triangular in K: start the K loop at block bm (needs bm >= bn)
   int split_chunks;    // > 0: blockIdx.z owns K chunks [z * split_chunks, (z + 1) * split_chunks) and the C copy z
   int64_t c_split_stride;
+  int tiles_m, tiles_n;
+  int group_n;         // rasterisation: CTAs walk all M tiles of a group of group_n N tiles before the next group, so the
+                       // group's B panels stay in L2 and A is streamed tiles_n / group_n times
 };
 
-__device__ __forceinline__ void tma_tile_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
 }
 
-// grid = (tiles along N, tiles along M); A is M x K and B is N x K, both row-major with K contiguous.
+// grid = (tiles along N, tiles along M, K splits); A is M x K and B is N x K, both row-major with K contiguous.
+// Stage ring: full[s] is completed by the two TMA tile loads of a chunk, empty[s] by one arrival per warp once its
+// fragment loads of that chunk are done.  No CTA-wide barrier in the main loop: warps drift by up to a stage, so the
+// fragment-load latency of one warp hides behind the DMMAs of the others.  Thread 0 refills, at iteration c, the stage
+// that was consumed at iteration c-1 (every warp has normally released it by then).
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams prm) {
-  const int bn = blockIdx.x, bm = blockIdx.y;
+  int bn, bm;
+  {
+    const int per_group = prm.group_n * prm.tiles_m;
+    const int g = (int)blockIdx.x / per_group, rem = (int)blockIdx.x - g * per_group;
+    const int gcols = min(prm.group_n, prm.tiles_n - g * prm.group_n);
+    bm = rem / gcols;
+    bn = g * prm.group_n + (rem - bm * gcols);
+  }
   if (prm.lower_only && bn > bm) return;
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  unsigned char* ring = smem + 1024;
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // 1024-B aligned: SWIZZLE_128B atoms
+  const uint32_t full = base, empty = base + 64, ring = base + 1024;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g4 = lane >> 2, t4 = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
   if (tid == 0) {
-    for (int s = 0; s < kGemmStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kGemmStages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full + 8 * s), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * s), "r"(kGemmThreads / 32));
+    }
     fence_barrier_init();
   }
   __syncthreads();
@@ -67,11 +81,30 @@ k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   double* const Cz = prm.C + (size_t)blockIdx.z * prm.c_split_stride;
   auto issue = [&](int c) {
     const int st = c % kGemmStages;
-    unsigned char* dst = ring + (size_t)st * kGemmStageBytes;
+    const uint32_t dst = ring + (uint32_t)st * kGemmStageBytes;
+    const uint32_t bar = full + 8 * st;
     fence_proxy_async();
-    mbar_arrive_expect_tx(&full[st], kGemmStageBytes);
-    tma_tile_2d(dst, &mapA, (c_first + c) * kChunk, bm * kDB, &full[st]);
-    tma_tile_2d(dst + kGemmStageBytes / 2, &mapB, (c_first + c) * kChunk, bn * kDB, &full[st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kGemmStageBytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(&mapA), "r"((c_first + c) * kChunk), "r"(bm * kDB), "r"(bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     dst + kGemmStageBytes / 2),
+                 "l"(&mapB), "r"((c_first + c) * kChunk), "r"(bn * kDB), "r"(bar)
+                 : "memory");
+  };
+  auto wait = [&](uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
   };
   if (tid == 0)
     for (int c = 0; c < kGemmStages && c < nk; ++c) issue(c);
@@ -82,21 +115,30 @@ k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
+  const uint32_t offA = (uint32_t)(wm * 32 + g4) * 128u, offB = (uint32_t)(kGemmStageBytes / 2) + (uint32_t)(wn * 32 + g4) * 128u;
   for (int c = 0; c < nk; ++c) {
     const int st = c % kGemmStages;
-    mbar_wait(&full[st], (uint32_t)((c / kGemmStages) & 1));
-    const unsigned char* pa = ring + (size_t)st * kGemmStageBytes + (size_t)(wm * 32 + g4) * 128;
-    const unsigned char* pb = ring + (size_t)st * kGemmStageBytes + kGemmStageBytes / 2 + (size_t)(wn * 32 + g4) * 128;
+    if (tid == 0 && c >= 1 && c - 1 + kGemmStages < nk) {
+      wait(empty + 8 * ((c - 1) % kGemmStages), (uint32_t)(((c - 1) / kGemmStages) & 1));
+      issue(c - 1 + kGemmStages);
+    }
+    wait(full + 8 * st, (uint32_t)((c / kGemmStages) & 1));
+    const uint32_t pa = ring + (uint32_t)st * kGemmStageBytes + offA;
+    const uint32_t pb = ring + (uint32_t)st * kGemmStageBytes + offB;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const int unit = ((2 * t4 + hf) ^ g4) << 4;      // SWIZZLE_128B: 16-byte unit index XOR (row & 7)
+      const uint32_t unit = (uint32_t)(((2 * t4 + hf) ^ g4) << 4);      // SWIZZLE_128B: 16-byte unit index XOR (row & 7)
       double2 av[2][2], bv[4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bv[nt] = *reinterpret_cast<const double2*>(pb + nt * 8 * 128 + unit);
+      for (int nt = 0; nt < 4; ++nt) bv[nt] = lds128(pb + nt * 8 * 128 + unit);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) av[mt][h] = *reinterpret_cast<const double2*>(pa + (mt * 16 + 8 * h) * 128 + unit);
+        for (int h = 0; h < 2; ++h) av[mt][h] = lds128(pa + (mt * 16 + 8 * h) * 128 + unit);
+      if (hf == 1) {                                                     // this warp is done reading the stage
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty + 8 * st) : "memory");
+      }
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -106,21 +148,34 @@ k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma_16x8x4(acc[mt][nt], av[mt][0].y, av[mt][1].y, bv[nt].y);
     }
-    __syncthreads();
-    if (tid == 0 && c + kGemmStages < nk) issue(c + kGemmStages);
   }
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = bm * kDB + wm * 32 + mt * 16 + g4 + 8 * (i >> 1);
-        const int n = bn * kDB + wn * 32 + nt * 8 + 2 * t4 + (i & 1);
-        double* dst = prm.store_t ? Cz + (size_t)n * prm.ldc + m : Cz + (size_t)m * prm.ldc + n;
-        double v = prm.alpha * acc[mt][nt][i];
-        if (prm.beta != 0.0) v += prm.beta * (*dst);
-        *dst = v;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = bm * kDB + wm * 32 + mt * 16 + g4 + 8 * hh;
+        const int n = bn * kDB + wn * 32 + nt * 8 + 2 * t4;
+        double v0 = prm.alpha * acc[mt][nt][2 * hh], v1 = prm.alpha * acc[mt][nt][2 * hh + 1];
+        if (prm.store_t) {
+          double* d0 = Cz + (size_t)n * prm.ldc + m;
+          double* d1 = d0 + prm.ldc;
+          if (prm.beta != 0.0) { v0 += prm.beta * (*d0); v1 += prm.beta * (*d1); }
+          *d0 = v0;
+          *d1 = v1;
+        } else {
+          double* d0 = Cz + (size_t)m * prm.ldc + n;
+          if ((prm.ldc & 1) == 0) {                                      // 16-byte aligned pairs
+            double2* d2 = reinterpret_cast<double2*>(d0);
+            if (prm.beta != 0.0) { const double2 o = *d2; v0 += prm.beta * o.x; v1 += prm.beta * o.y; }
+            *d2 = make_double2(v0, v1);
+          } else {
+            if (prm.beta != 0.0) { v0 += prm.beta * d0[0]; v1 += prm.beta * d0[1]; }
+            d0[0] = v0;
+            d0[1] = v1;
+          }
+        }
       }
 }
 
@@ -179,7 +234,14 @@ int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, doubl
     GRIEF_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(N / kDB, M / kDB, splits);
+  prm.tiles_m = M / kDB;
+  prm.tiles_n = N / kDB;
+  // B panels of one group (group_n x 128 rows x the K range of a CTA) are sized to ~40 % of the 126 MB L2
+  const int64_t k_cta = splits > 1 ? (int64_t)prm.split_chunks * kChunk : (int64_t)K;
+  const int64_t panel_bytes = std::max<int64_t>(1, k_cta * kDB * 8);
+  prm.group_n = (int)std::max<int64_t>(1, std::min<int64_t>(prm.tiles_n, ((int64_t)50 << 20) / panel_bytes));
+  if (o.lower_only) prm.group_n = prm.tiles_n;       // triangle: plain row-major tile order
+  dim3 grid((unsigned)(prm.tiles_m * prm.tiles_n), 1, splits);
   k_gemm_nt<<<grid, kGemmThreads, smem, stream>>>(mA, mB, prm);
   GRIEF_CUDA(cudaGetLastError());
   if (launches) *launches += 1;

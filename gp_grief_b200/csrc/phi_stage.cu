@@ -150,11 +150,14 @@ struct GramSchedule {
   int64_t slab_rows;
 };
 
+static size_t g_slab_budget_bytes = (size_t)4 << 30;      // bytes of Phi^T staged per pass-1 slab
+void set_slab_budget(size_t bytes) { g_slab_budget_bytes = bytes ? bytes : ((size_t)4 << 30); }
+
 GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
   GramSchedule s;
   s.nb = p_pad / kTileN;
   s.n_tiles = s.nb * (s.nb + 1) / 2;
-  const int64_t budget_rows = ((int64_t)4 << 30) / ((int64_t)p_pad * 8) / kBuildRows * kBuildRows;   // 4 GiB of Phi^T
+  const int64_t budget_rows = (int64_t)(g_slab_budget_bytes / ((size_t)p_pad * 8)) / kBuildRows * kBuildRows;
   s.slab_rows = std::max<int64_t>(kBuildRows, std::min<int64_t>(n_pad, std::max<int64_t>(kBuildRows, budget_rows)));
   // K splits: fill whole waves of `sms` CTAs, keep >= 256 data rows per split
   const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.slab_rows / 256, 64));

@@ -125,6 +125,13 @@ int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx,
 int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, double* Phi_dev, void* stream);
 
 /*
+ * HBM budget (bytes) for the Phi^T slab that pass 1 stages per GEMM launch (default 4 GiB; 0 restores the default).
+ * Smaller budgets mean more, shorter launches; results are identical up to the order of the fixed-order accumulation.
+ * Query grief_gram_workspace_bytes again after changing it.
+ */
+void grief_set_slab_budget(size_t bytes);
+
+/*
  * Fused Gram:  A = Phi^T Phi without materialising Phi (models/gp_grief_model.py:148-149).
  *   A_dev       out, (p, lda) row-major, full symmetric matrix
  *   workspace   device scratch of at least grief_gram_workspace_bytes(plan, n) bytes

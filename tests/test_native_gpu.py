@@ -5,6 +5,7 @@ from numpy.testing import assert_allclose, assert_array_equal
 
 from conftest import load_golden, model_cases, case_inputs
 from oracle import grief_oracle as orc
+from gp_grief_b200 import _native as nat
 
 pytestmark = pytest.mark.gpu
 
@@ -213,3 +214,54 @@ def test_dense_stage_not_pd_reports_minor():
     dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     with pytest.raises(np.linalg.LinAlgError, match="151"):
         _dev().DeviceSolver().solve(dv(A), dv(np.ones(p)), dv(np.array([1.0])), dv(np.full(p, 1e30)), 0.5, 100)
+
+
+@pytest.mark.gpu
+def test_gram_and_quadform_over_several_slabs():
+    """Pass 1 with a tiny Phi^T budget (many slabs accumulated into the split partials) and the Z = Phi B product
+    over more rows than one slab (148 * 256) must match the materialised Phi."""
+    import torch
+    rng = np.random.default_rng(11)
+    d, m, p, n = 4, 5, 200, 40003
+    xg = [np.linspace(0, 1, m) for _ in range(d)]
+    names = ["Matern52"] * d
+    var, ls = [1.0] * d, [0.4 + 0.05 * i for i in range(d)]
+    basis = orc.setup_inducing_cov(names, var, ls, xg, p)
+    plan = _plan_from_basis(dict(d=d, names=names, variances=var, lengthscales=ls, xg=xg), basis)
+    X = torch.from_numpy(rng.random((n, d))).cuda()
+    T = plan.build_tables(X)
+    Phi = plan.phi_rows(T, n)
+    A_ref = (Phi.T @ Phi).cpu().numpy()
+    A_one = plan.gram(T, n).cpu().numpy()
+    try:
+        nat.lib().grief_set_slab_budget(256 * 8 * 3000)          # 3000-row slabs (rounded down to 2944) -> 14 slabs
+        A_many = plan.gram(T, n).cpu().numpy()
+    finally:
+        nat.lib().grief_set_slab_budget(0)
+    tol = 1e-12 * np.abs(A_ref).max()
+    assert_allclose(A_one, A_ref, rtol=0, atol=tol)
+    assert_allclose(A_many, A_ref, rtol=0, atol=tol)
+    assert np.array_equal(A_many, A_many.T)
+    B = rng.standard_normal((p, p))
+    B = torch.from_numpy(B + B.T).cuda()
+    q = plan.quadform_rows(T, n, B).cpu().numpy()
+    q_ref = ((Phi @ B) * Phi).sum(1).cpu().numpy()
+    assert_allclose(q, q_ref, rtol=0, atol=1e-11 * np.abs(q_ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(128, 128, 2), (256, 384, 50), (1280, 256, 1000)])
+def test_gemm_nt_entry(M, N, K):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn((N, K), dtype=torch.float64, device="cuda", generator=g)
+    C0 = torch.randn((M, N), dtype=torch.float64, device="cuda", generator=g)
+    C = C0.clone()
+    nat.check(nat.lib().grief_gemm_nt(nat.dev_ptr(A), K, nat.dev_ptr(B), K, nat.dev_ptr(C), N, M, N, K, -0.5, 2.0,
+                                      nat.stream_ptr()))
+    ref = 2.0 * C0 - 0.5 * (A @ B.T)
+    assert_allclose(C.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=1e-12 * float(ref.abs().max()) * max(1, K) ** 0.5)
+    with pytest.raises(ValueError):
+        nat.check(nat.lib().grief_gemm_nt(nat.dev_ptr(A), K, nat.dev_ptr(B), K, nat.dev_ptr(C), N, M - 1, N, K, 1.0, 0.0,
+                                          nat.stream_ptr()))
