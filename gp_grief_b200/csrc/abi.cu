@@ -287,8 +287,8 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
 int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M, int N, int K,
                   double alpha, double beta, void* stream_) {
   GRIEF_REQUIRE(A_dev && B_dev && C_dev, "grief_gemm_nt: null pointer");
-  GRIEF_REQUIRE(M % 128 == 0 && N % 128 == 0 && K % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0,
-                "grief_gemm_nt: M=%d N=%d must be multiples of 128 and K=%d, lda, ldb even", M, N, K);
+  GRIEF_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "grief_gemm_nt: M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld",
+                M, N, K, (long long)lda, (long long)ldb, (long long)ldc);
   return gemm_nt(A_dev, lda, B_dev, ldb, C_dev, ldc, M, N, K, alpha, beta, false, false, (cudaStream_t)stream_, &g_launches, false);
 }
 

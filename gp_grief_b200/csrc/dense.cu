@@ -35,6 +35,7 @@ struct GemmParams {
   int split_chunks;    // > 0: blockIdx.z owns K chunks [z * split_chunks, (z + 1) * split_chunks) and the C copy z
   int64_t c_split_stride;
   int tiles_m, tiles_n;
+  int m_valid, n_valid;  // C has m_valid x n_valid elements; the rest of the last tiles is not stored
   int group_n;         // rasterisation: CTAs walk all M tiles of a group of group_n N tiles before the next group, so the
                        // group's B panels stay in L2 and A is streamed tiles_n / group_n times
 };
@@ -158,22 +159,24 @@ k_gemm_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int m = bm * kDB + wm * 32 + mt * 16 + g4 + 8 * hh;
         const int n = bn * kDB + wn * 32 + nt * 8 + 2 * t4;
         double v0 = prm.alpha * acc[mt][nt][2 * hh], v1 = prm.alpha * acc[mt][nt][2 * hh + 1];
+        if (m >= prm.m_valid || n >= prm.n_valid) continue;
+        const bool two = n + 1 < prm.n_valid;
         if (prm.store_t) {
           double* d0 = Cz + (size_t)n * prm.ldc + m;
           double* d1 = d0 + prm.ldc;
-          if (prm.beta != 0.0) { v0 += prm.beta * (*d0); v1 += prm.beta * (*d1); }
+          if (prm.beta != 0.0) { v0 += prm.beta * (*d0); if (two) v1 += prm.beta * (*d1); }
           *d0 = v0;
-          *d1 = v1;
+          if (two) *d1 = v1;
         } else {
           double* d0 = Cz + (size_t)m * prm.ldc + n;
-          if ((prm.ldc & 1) == 0) {                                      // 16-byte aligned pairs
+          if (two && ((reinterpret_cast<uintptr_t>(d0) & 15) == 0)) {     // 16-byte aligned pair
             double2* d2 = reinterpret_cast<double2*>(d0);
             if (prm.beta != 0.0) { const double2 o = *d2; v0 += prm.beta * o.x; v1 += prm.beta * o.y; }
             *d2 = make_double2(v0, v1);
           } else {
-            if (prm.beta != 0.0) { v0 += prm.beta * d0[0]; v1 += prm.beta * d0[1]; }
+            if (prm.beta != 0.0) { v0 += prm.beta * d0[0]; if (two) v1 += prm.beta * d0[1]; }
             d0[0] = v0;
-            d0[1] = v1;
+            if (two) d0[1] = v1;
           }
         }
       }
@@ -214,12 +217,17 @@ static int make_map(CUtensorMap* map, const double* base, int rows, int cols, in
 int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K, double alpha,
                double beta, const GemmOpts& o, cudaStream_t stream, int* launches) {
   if (M <= 0 || N <= 0) return GRIEF_OK;
-  GRIEF_REQUIRE(M % kDB == 0 && N % kDB == 0 && K >= 0, "gemm_nt: M=%d N=%d K=%d", M, N, K);
+  GRIEF_REQUIRE(K >= 0, "gemm_nt: K=%d", K);
   GRIEF_REQUIRE(!(o.tri_k && o.splits > 1), "gemm_nt: tri_k and split K do not combine");
+  GRIEF_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                "gemm_nt: operands need 16-byte aligned rows (even leading dimensions)");
+  const int m_valid = M, n_valid = N;
+  M = (M + kDB - 1) / kDB * kDB;                     // partial last tiles: absent rows read as zeros, stores are guarded
+  N = (N + kDB - 1) / kDB * kDB;
   alignas(64) CUtensorMap mA, mB;
   const int Kmap = std::max(K, 2);
-  int rc = make_map(&mA, A, o.rows_a > 0 ? o.rows_a : M, Kmap, lda);
-  if (rc == GRIEF_OK) rc = make_map(&mB, B, o.rows_b > 0 ? o.rows_b : N, Kmap, ldb);
+  int rc = make_map(&mA, A, o.rows_a > 0 ? o.rows_a : m_valid, Kmap, lda);
+  if (rc == GRIEF_OK) rc = make_map(&mB, B, o.rows_b > 0 ? o.rows_b : n_valid, Kmap, ldb);
   if (rc != GRIEF_OK) return rc;
   GemmParams prm;
   prm.C = C; prm.ldc = ldc; prm.K = K; prm.alpha = alpha; prm.beta = beta;
@@ -234,6 +242,8 @@ int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, doubl
     GRIEF_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  prm.m_valid = m_valid;
+  prm.n_valid = n_valid;
   prm.tiles_m = M / kDB;
   prm.tiles_n = N / kDB;
   // B panels of one group (group_n x 128 rows x the K range of a CTA) are sized to ~40 % of the 126 MB L2

@@ -167,14 +167,32 @@ class DevicePlan(object):
         return q
 
 
+def gemm_nt(A, B, alpha=1.0, beta=0.0, out=None):
+    """out = beta * out + alpha * A @ B.T on the library's FP64 DMMA GEMM (A: (M, K), B: (N, K) device tensors)."""
+    torch = _torch()
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[1] == B.shape[1], "gemm_nt: A (M, K) and B (N, K)"
+    A, B = _even_ld(A), _even_ld(B)
+    M, K = A.shape
+    N = B.shape[0]
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    if M and N and K:
+        nat.check(nat.lib().grief_gemm_nt(nat.dev_ptr(A), A.stride(0), nat.dev_ptr(B), B.stride(0), nat.dev_ptr(out), out.stride(0),
+                                          M, N, K, float(alpha), float(beta), nat.stream_ptr()))
+    elif beta == 0.0:
+        out.zero_()
+    return out
+
+
 def _even_ld(B):
-    """TMA needs 16-byte row strides: give an odd-sized symmetric matrix a padded copy (tiny p only)."""
-    if B.stride(0) % 2 == 0:
+    """TMA needs 16-byte aligned rows: unit column stride, even row stride, aligned base -- else a padded copy (small operands)."""
+    if B.stride(1) == 1 and B.stride(0) % 2 == 0 and B.data_ptr() % 16 == 0 and B.stride(0) >= B.shape[1]:
         return B
     import torch
-    pad = torch.zeros((B.shape[0], B.shape[1] + 1), dtype=B.dtype, device=B.device)
+    pad = torch.zeros((B.shape[0], B.shape[1] + (B.shape[1] & 1)), dtype=B.dtype, device=B.device)
     pad[:, :B.shape[1]] = B
-    return pad
+    return pad[:, :B.shape[1]]
 
 
 def sumsq(y_dev):

@@ -281,8 +281,10 @@ class GPGriefModel(BaseModel):
         if compute_var == 'diag':
             q = plan.quadform_rows(Tn, M, out['Pinv'])
             return Yhat, (nv * (q + 1.0)).cpu().numpy().reshape((-1, 1))
+        from ..device import gemm_nt
         Phi_new = plan.phi_rows(Tn, M)
-        Yhatvar = nv * (Phi_new @ (out['Pinv'] @ Phi_new.T)) + nv * t.eye(M, dtype=t.float64, device="cuda")
+        Yhatvar = nv * t.eye(M, dtype=t.float64, device="cuda")
+        gemm_nt(gemm_nt(Phi_new, out['Pinv']), Phi_new, alpha=nv, beta=1.0, out=Yhatvar)     # P^-1 is symmetric
         return Yhat, Yhatvar.cpu().numpy()
 
     def d_Yhat_d_x(self, Xnew, dim):

@@ -25,8 +25,9 @@ class GPwebModel(BaseModel):
         assert Phi.shape[0] == y.shape[0]
         Pd = torch.as_tensor(np.ascontiguousarray(Phi)).cuda()
         yd = torch.as_tensor(np.ascontiguousarray(y[:, 0])).cuda()
-        A = (Pd.T @ Pd).contiguous()                      # one-off library GEMM on a user-supplied matrix
-        r = Pd.T @ yd
+        PdT = Pd.T.contiguous()                           # (p, n): data rows contiguous, the K dimension of both products
+        A = device.gemm_nt(PdT, PdT)                      # Phi^T Phi on the library's FP64 DMMA GEMM
+        r = device.gemm_nt(PdT, yd.reshape(1, -1)).reshape(-1)
         s = (yd * yd).sum().reshape(1)
         self._init_from(A, r, s, y.shape[0], noise_var)
 
@@ -103,6 +104,8 @@ class GPwebModel(BaseModel):
         out = self._run(True)
         Pn = torch.as_tensor(np.ascontiguousarray(Phi_new, dtype=np.float64)).cuda()
         nv = float(self.noise_var)
-        Yhat = (Pn @ out['b']).cpu().numpy().reshape((-1, 1))           # alpha_p == b = P^-1 r
-        Yhatvar = nv * (Pn @ (out['Pinv'] @ Pn.T)) + nv * torch.eye(Pn.shape[0], dtype=torch.float64, device="cuda")
+        from ..device import gemm_nt
+        Yhat = gemm_nt(Pn, out['b'].reshape(1, -1)).cpu().numpy().reshape((-1, 1))   # alpha_p == b = P^-1 r
+        Yhatvar = nv * torch.eye(Pn.shape[0], dtype=torch.float64, device="cuda")
+        gemm_nt(gemm_nt(Pn, out['Pinv']), Pn, alpha=nv, beta=1.0, out=Yhatvar)       # P^-1 is symmetric
         return Yhat, Yhatvar.cpu().numpy()

@@ -199,7 +199,8 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
 
 /*
  * C (M x N, ldc) = beta * C + alpha * A (M x K, lda) * B (N x K, ldb)^T, all row-major on the device; the TMA-fed FP64 DMMA
- * GEMM the dense stage is built on.  M, N multiples of 128; K, lda, ldb even.  Stands in for the numpy `dot` calls on
+ * GEMM both O(n p^2) passes and the dense stage are built on.  Any M, N, K >= 1; A and B need 16-byte aligned rows (even lda,
+ * ldb, aligned base).  Stands in for the numpy `dot` calls on
  * p x p and M x p operands (models/gp_grief_model.py:122-124 full predictive covariance).
  */
 int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M,

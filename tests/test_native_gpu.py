@@ -262,6 +262,21 @@ def test_gemm_nt_entry(M, N, K):
                                       nat.stream_ptr()))
     ref = 2.0 * C0 - 0.5 * (A @ B.T)
     assert_allclose(C.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=1e-12 * float(ref.abs().max()) * max(1, K) ** 0.5)
-    with pytest.raises(ValueError):
-        nat.check(nat.lib().grief_gemm_nt(nat.dev_ptr(A), K, nat.dev_ptr(B), K, nat.dev_ptr(C), N, M - 1, N, K, 1.0, 0.0,
+    with pytest.raises(ValueError):                        # lda < K
+        nat.check(nat.lib().grief_gemm_nt(nat.dev_ptr(A), K - 1, nat.dev_ptr(B), K, nat.dev_ptr(C), N, M, N, K, 1.0, 0.0,
                                           nat.stream_ptr()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 3, 7), (130, 129, 33), (300, 1, 257)])
+def test_gemm_nt_helper_ragged_shapes(M, N, K):
+    """Partial tiles, odd K and odd leading dimensions go through padded operand copies and guarded stores."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(7 * M + N + K)
+    A = torch.randn((M, K), dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn((N, K), dtype=torch.float64, device="cuda", generator=g)
+    C = torch.full((M + 2, N + 3), 7.0, dtype=torch.float64, device="cuda")
+    out = _dev().gemm_nt(A, B, alpha=2.0, beta=1.0, out=C[:M, :N])
+    ref = 7.0 + 2.0 * (A @ B.T)
+    assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=1e-12 * max(1.0, float(ref.abs().max())))
+    assert float(C[M:].min()) == 7.0 and float(C[:, N:].min()) == 7.0 and float(C[M:].max()) == 7.0      # nothing outside written
