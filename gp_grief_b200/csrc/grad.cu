@@ -252,7 +252,7 @@ struct ContractParams {
   const int* ga; int n_active;
 };
 
-constexpr int kContractK = 4;   // parameters per group accumulated in registers per sweep over the columns
+constexpr int kContractK = 6;   // parameters per group accumulated in registers per sweep over the columns (C3: at most 6)
 
 // One warp per data row, ONE sweep over the columns for all groups (a second sweep only if a group has more than
 // kContractK active parameters): per column the leave-one-group-out products L_g = Zt * prod_{g' != g} H_g' come from

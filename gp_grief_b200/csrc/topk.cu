@@ -232,8 +232,18 @@ int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const dou
   const size_t bytes_cho = ((size_t)d * p + 15) / 16 * 16;
   const size_t bytes_eig = ((size_t)(tot + m_host[0]) * sizeof(double) + 15) / 16 * 16;
   const size_t bytes_int = ((size_t)(2 * d + 1) * sizeof(int) + 15) / 16 * 16;
-  char* scratch = nullptr;
-  GRIEF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes_vals + bytes_par + bytes_cho + bytes_eig + bytes_int, stream));
+  // grow-only scratch kept between calls (one evaluation = one call; a stream-ordered alloc/free pair per call showed
+  // erratic 10-800 ms host stalls after long GPU phases)
+  static thread_local char* scratch = nullptr;
+  static thread_local size_t scratch_bytes = 0;
+  const size_t need = bytes_vals + bytes_par + bytes_cho + bytes_eig + bytes_int;
+  if (need > scratch_bytes) {
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr;
+    scratch_bytes = 0;
+    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), need));
+    scratch_bytes = need;
+  }
   char* q = scratch;
   TopkParams P;
   P.vals_a = reinterpret_cast<double*>(q); P.vals_b = P.vals_a + p; q += bytes_vals;
@@ -248,7 +258,7 @@ int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const dou
   for (int i = 0; i < d; ++i) { hint[i] = mm[i]; hint[d + i] = off[i]; }
   cudaError_t e1 = cudaMemcpyAsync(d_eig, heig.data(), heig.size() * sizeof(double), cudaMemcpyHostToDevice, stream);
   cudaError_t e2 = cudaMemcpyAsync(d_int, hint.data(), hint.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
-  if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFreeAsync(scratch, stream); return fail(GRIEF_ERR_CUDA, "topk: upload failed"); }
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(GRIEF_ERR_CUDA, "topk: upload failed");
   P.logeig = d_eig; P.raw0 = d_eig + tot; P.m = d_int; P.off = d_int + d; P.n_out = d_int + 2 * d;
   P.d = d; P.p = p; P.idx_out = idx_dev; P.loglam_out = loglam_dev;
   int N = 1;
@@ -264,7 +274,6 @@ int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const dou
   int n_out = 0;
   if (e3 == cudaSuccess) e3 = cudaMemcpyAsync(&n_out, P.n_out, sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(stream);   // host staging vectors die at return
-  cudaFreeAsync(scratch, stream);
   if (e3 != cudaSuccess) return fail(GRIEF_ERR_CUDA, "topk: %s", cudaGetErrorString(e3));
   if (n_out_host) *n_out_host = n_out;
   if (launches) *launches += 1;
