@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=1 << 13, help="rows per CPU-baseline sample chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm", default="int8", choices=["int8", "fp64"],
+                    help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores (54-bit operands, "
+                         "same parity tests) or the FP64 DMMA GEMM")
     return ap.parse_args()
 
 
@@ -223,6 +226,7 @@ def run_ours(args):
                                    reweight_eig_funs=False, opt_kernel_params=True)
         return gp.models.GPGriefModel(x_pin.numpy(), y_pin.numpy(), kern, noise_var=0.1, distributed=distributed)
 
+    nat.lib().grief_set_gemm_mode(1 if args.gemm == "int8" else 0)
     peak_burst = peak_sust = None
     if rank == 0:
         peak_burst, peak_sust = fp64_peak(torch)
@@ -303,8 +307,10 @@ def run_ours(args):
     kern_rows = []
     # work actually issued by the GEMM launches (padded rows / columns, full diagonal tiles)
     flops = {"k_zgemm": 2.0 * rows128 * p_pad * p_pad, "k_gram": float(rows128) * p_pad * (p_pad + 128)}
-    label = {"k_zgemm": "k_gemm_nt [Z = Phi*G2, pass 2]", "k_gram": "k_gemm_nt [A = Phi^T Phi, lower tiles, split K]",
-             "k_build_phi": "k_build_phi [Phi slab, pass 2]", "k_build_phi_t": "k_build_phi_t [Phi^T slab, pass 1]",
+    gk = "k_ozaki" if args.gemm == "int8" else "k_gemm_nt"
+    sl = " + k_row_exp + k_slice" if args.gemm == "int8" else ""
+    label = {"k_zgemm": gk + " [Z = Phi*G2, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
+             "k_build_phi": "k_build_phi%s [Phi slab, pass 2]" % sl, "k_build_phi_t": "k_build_phi_t%s [Phi^T slab, pass 1]" % sl,
              "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)"}
     for name in ("k_zgemm", "k_gram", "k_contract", "k_build_phi", "k_build_phi_t", "solve", "k_dtables", "k_tables", "phi_t_y", "k_topk"):
         t_ms, cnt = prof.get(name, (0.0, 0))
@@ -325,25 +331,37 @@ def run_ours(args):
         traffic = None
     if dom:
         algo = 2.0 * n_local * p * p * args.steps / (dom["ms_total"] * 1e-3) * 1e-12      # algorithmic: 2 n p^2 per evaluation
-        roofline = {"bound": "tensor", "kernel": "k_gemm_nt (TMA-fed FP64 DMMA GEMM) computing Z = Phi*G2 for pass 2, one launch per slab of "
-                                                 "37888 rows; Phi slab staged in HBM by k_build_phi",
-                    "achieved": algo, "peak": peak_sust, "unit": "TFLOP/s", "frac": algo / peak_sust,
-                    "traffic": traffic, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, sustained %.1f / burst %.1f TFLOP/s; "
-                    "MEASURED_PEAKS.json has no FP64 row; FP64 DMMA issue-rate peak 37.2 TFLOP/s (profiles/r01_fp64_pipes_microbench.txt)"
-                    % (peak_sust, peak_burst),
-                    "frac_of_dmma_issue_peak": algo / 37.2,
-                    "avg_launch_ms": dom["ms_total"] / dom["launches"], "kernels": kern_rows,
-                    "whole_eval_frac_of_peak": 3.0 * n_total * p * p * value / world * 1e-12 / peak_sust}
+        common = {"traffic": traffic, "avg_launch_ms": dom["ms_total"] / dom["launches"], "kernels": kern_rows,
+                  "fp64_equivalent_tflops": algo, "cublas_dgemm_tflops_this_run": peak_sust, "fp64_dmma_issue_peak_tflops": 37.2,
+                  "whole_eval_fp64_equivalent_tflops": 3.0 * n_total * p * p * value / world * 1e-12}
+        if args.gemm == "int8":
+            # 28 exact int8 digit GEMMs per FP64 GEMM; peak = dense INT8 = 2 x the dense bf16 rate measured on this pool
+            tops = 28.0 * flops["k_zgemm"] * args.steps / (dom["ms_total"] * 1e-3) * 1e-12
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                peak_i8, src = 2.0 * float(mp["bf16_tflops_sustained"]), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a long step)"
+            except Exception:
+                peak_i8, src = 4500.0, "nominal dense INT8 4.5 POP/s (MEASURED_PEAKS.json missing)"
+            roofline = dict(common, bound="tensor", kernel="k_ozaki (tcgen05 kind::i8, TMEM accumulators, TMA digit planes): Z = Phi*G2 for pass 2 as 28 "
+                            "exact int8 x int8 -> int32 digit GEMMs per slab of 37888 rows; digits cut by k_slice from the Phi slab of k_build_phi",
+                            achieved=tops, peak=peak_i8, unit="TOP/s (int8)", frac=tops / peak_i8, peak_source=src)
+        else:
+            roofline = dict(common, bound="tensor", kernel="k_gemm_nt (TMA-fed FP64 DMMA GEMM) computing Z = Phi*G2 for pass 2, one launch per slab "
+                            "of 37888 rows; Phi slab staged in HBM by k_build_phi",
+                            achieved=algo, peak=peak_sust, unit="TFLOP/s", frac=algo / peak_sust,
+                            peak_source="cuBLAS DGEMM 8192^3 measured in this run, sustained %.1f / burst %.1f TFLOP/s; MEASURED_PEAKS.json has "
+                            "no FP64 row; FP64 DMMA issue-rate peak 37.2 TFLOP/s (profiles/r01_fp64_pipes_microbench.txt)" % (peak_sust, peak_burst))
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(args.config, n_total, args.cpu_rows)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if args.gemm == "fp64" else "f64 (O(n p^2) products as exact int8 digit GEMMs on the tensor cores, 54-bit operands)",
+            "data": "synthetic",
             "config": {"workload": "%s: Type-II GRIEF LML+gradient, n=%d, d=%d, m=%d grid pts/dim, p=%d, RBF kernels, "
                                    "new lengthscales every step" % (args.config, n_total, d, m, p),
-                       "rows_per_gpu": n_local, "parallelism": "rows sharded over %d rank(s), NCCL all-reduce of (A|r|s) and of the "
+                       "gemm_arithmetic": args.gemm, "rows_per_gpu": n_local, "parallelism": "rows sharded over %d rank(s), NCCL all-reduce of (A|r|s) and of the "
                                                                "theta-gradient" % world,
                        "l2": "inputs (X %.1f GB, tables %.1f GB per GPU) exceed the 126 MB L2" % (n_local * d * 8e-9, rows128 * 105 * 8e-9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

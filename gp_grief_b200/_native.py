@@ -50,6 +50,8 @@ SIGNATURES = {
     "grief_quadform_workspace_bytes": (c_size, [c_void, c_i64]),
     "grief_quadform_rows": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_void, c_size, c_void]),
     "grief_set_slab_budget": (None, [c_size]),
+    "grief_set_gemm_mode": (None, [c_int]),
+    "grief_get_gemm_mode": (c_int, []),
     "grief_gemm_nt": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
     "grief_solve_lml": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void, c_void, c_dbl, c_i64, c_void, c_void,
                                 c_void, c_void, c_void, c_void, _P(c_int), c_void]),

@@ -34,8 +34,10 @@ int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t
 int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream);
 int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream);
 int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream);
-int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Phi_slab, double* Z, int64_t ldz,
-                 cudaStream_t stream, int* launches);
+size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows);
+int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream);
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
+                 int64_t ldz, cudaStream_t stream, int* launches);
 int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
 
 static thread_local int g_launches = 0;
@@ -147,6 +149,8 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
 }
 
 void grief_set_slab_budget(size_t bytes) { set_slab_budget(bytes); }
+void grief_set_gemm_mode(int mode) { set_gemm_mode(mode); }
+int grief_get_gemm_mode(void) { return gemm_mode(); }
 
 size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n) {
   return gram_workspace_bytes(plan->impl, grief_table_rows(n), sm_count());
@@ -155,8 +159,10 @@ int grief_gram(const grief_plan* plan, const double* T_dev, int64_t n, double* A
                size_t workspace_bytes, void* stream) {
   GRIEF_REQUIRE(plan && A_dev && workspace_dev && (T_dev || n == 0), "grief_gram: null pointer");
   GRIEF_REQUIRE(lda >= plan->impl->p, "grief_gram: lda=%lld < p=%d", (long long)lda, plan->impl->p);
-  return launch_gram(plan->impl, T_dev, grief_table_rows(n), A_dev, lda, workspace_dev, workspace_bytes, sm_count(),
-                     (cudaStream_t)stream, &g_launches);
+  int rc = launch_gram(plan->impl, T_dev, grief_table_rows(n), A_dev, lda, workspace_dev, workspace_bytes, sm_count(),
+                       (cudaStream_t)stream, &g_launches);
+  if (rc == GRIEF_OK && gemm_mode() == 1) rc = ozaki_check((cudaStream_t)stream);
+  return rc;
 }
 
 size_t grief_phi_t_vec_workspace_bytes(const grief_plan* plan, int64_t n) {
@@ -202,7 +208,8 @@ size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   if (!pl->grad) return 0;
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
-  return 2 * align256((size_t)slab * pl->p_pad * sizeof(double)) + align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
+  return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) +
+         align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
          align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p * sizeof(double)) +
          align256((size_t)pl->p * pl->p_pad * sizeof(double));
 }
@@ -221,7 +228,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   const int64_t slab = slab_rows_for(n, sms);
   char* q = reinterpret_cast<char*>(workspace_dev);
   double* Z = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
-  double* PhiS = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
+  void* zscr = q; q += align256(zgemm_scratch_bytes(pl, slab));
   double* DT = reinterpret_cast<double*>(q); q += align256((size_t)slab * std::max(1, dtw) * sizeof(double));
   double* partial = reinterpret_cast<double*>(q); q += align256((size_t)contract_blocks(sms) * std::max(1, na) * sizeof(double));
   double* gvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p * sizeof(double));
@@ -231,13 +238,14 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   int rc = launch_scale_vec(b_dev, 1.0 / noise_var, pl->p, gvec, stream);
   if (rc != GRIEF_OK) return rc;
   rc = launch_permute_b(pl, G2_dev, ldg, Bperm, stream);
+  if (rc == GRIEF_OK) rc = launch_zgemm_prepare(pl, Bperm, slab, zscr, stream);
   if (rc != GRIEF_OK) return rc;
   g_launches += 2;
   const int64_t n128 = grief_table_rows(n);
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, PhiS, Z, pl->p_pad, stream, &g_launches);
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, pl->p_pad, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_dtables(pl, gd, X_dev + (size_t)r0 * ldx, ldx, rows_valid, rows_valid, DT, stream);
     if (rc != GRIEF_OK) return rc;
@@ -247,12 +255,14 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   }
   rc = launch_reduce_partials(partial, contract_blocks(sms), na, grad_dev, stream);
   if (rc == GRIEF_OK) g_launches += 1;
+  if (rc == GRIEF_OK && gemm_mode() == 1) rc = ozaki_check(stream);
   return rc;
 }
 
 size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
-  return 2 * align256((size_t)slab_rows_for(n, sm_count()) * pl->p_pad * sizeof(double)) + align256((size_t)pl->p * pl->p_pad * sizeof(double));
+  const int64_t slab = slab_rows_for(n, sm_count());
+  return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) + align256((size_t)pl->p * pl->p_pad * sizeof(double));
 }
 
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb, double* q_dev,
@@ -264,10 +274,11 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   double* Z = reinterpret_cast<double*>(workspace_dev);
-  double* PhiS = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace_dev) + align256((size_t)slab * pl->p_pad * sizeof(double)));
-  double* Bperm = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace_dev) + 2 * align256((size_t)slab * pl->p_pad * sizeof(double)));
+  void* zscr = reinterpret_cast<char*>(workspace_dev) + align256((size_t)slab * pl->p_pad * sizeof(double));
+  double* Bperm = reinterpret_cast<double*>(reinterpret_cast<char*>(zscr) + align256(zgemm_scratch_bytes(pl, slab)));
   {
     int rc0 = launch_permute_b(pl, B_dev, ldb, Bperm, stream);
+    if (rc0 == GRIEF_OK) rc0 = launch_zgemm_prepare(pl, Bperm, slab, zscr, stream);
     if (rc0 != GRIEF_OK) return rc0;
     g_launches += 1;
   }
@@ -275,13 +286,13 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, PhiS, Z, pl->p_pad, stream, &g_launches);
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, pl->p_pad, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_rowdot(pl, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, rows_valid, q_dev + r0, stream);
     if (rc != GRIEF_OK) return rc;
     g_launches += 1;
   }
-  return GRIEF_OK;
+  return gemm_mode() == 1 ? ozaki_check(stream) : GRIEF_OK;
 }
 
 int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M, int N, int K,

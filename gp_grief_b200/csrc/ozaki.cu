@@ -1,0 +1,372 @@
+// FP64 GEMM on the INT8 tensor cores (Ozaki splitting, tcgen05 kind::i8) -- the fast path of both O(n p^2) products.
+//
+//   C (M x N, f64) (+)= A (M x K, f64) * B (N x K, f64)^T
+// Every operand row is scaled by a power of two so that |x| < 1 and cut into S = 7 balanced 8-bit digits (54 bits + sign):
+//   x 2^-e = sum_s d_s 2^(-6 - 8 s),   A B^T = sum_{a,b} 2^(-12 - 8 (a + b)) D_a(A) D_b(B)^T,   pairs with a + b <= 6 kept (28 of 49;
+//   what is dropped is below 2^-54 of the row-scale product).  Each digit product is an exact int8 x int8 -> int32 GEMM; one
+//   accumulation covers at most 16384 values of K (7 pairs x 2^14 x 2^14 < 2^31), longer K is split over blockIdx.z.
+// Kernel: one CTA per 128 x 256 tile.  Work items = significance-group pairs (g, g-1) accumulated in the two TMEM
+// accumulators (2 x 256 columns x 128 lanes, int32); all digit planes an item needs for one 32-byte K chunk sit in
+// shared memory (3-D TMA boxes, SWIZZLE_32B, three 60 KB stages); warp 4 = TMA producer, warp 5 = MMA issuer (one
+// thread), warps 0-3 drain TMEM after each group pair: int32 -> f64, scaled, transposed through shared memory, added to C.
+// Measured (tools/microbench/ozaki_gemm.cu, B200): 77 TFLOP/s FP64-equivalent at 37888 x 4096 x 4096 against 35 for cuBLAS
+// DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
+// Every barrier wait is bounded: a protocol failure raises an error flag (checked by the callers) instead of hanging the GPU.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "plan.h"
+
+namespace grief {
+
+constexpr int S = 7;                     // balanced 8-bit digits per operand (54 bits + sign)
+constexpr int TM = 128, TN = 256, KC = 32, STAGES = 3;
+constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // 4 KB, 8 KB
+constexpr int STAGE_BYTES = 60 * 1024;                         // largest work item: 5 A slices + 5 B slices
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+// Work items: a significance-group pair (gh, gh-1) accumulates into the two TMEM accumulators; the pair (6,5) is cut in two
+// by A-slice range so that every stage fits 60 KB and three stages fit shared memory.
+struct Item { int gh, a_lo, a_hi, b_lo, b_hi, first, last; };
+__constant__ Item kItems[5] = {
+    {6, 0, 3, 2, 6, 1, 0},   // g=6: a=0..3 (b=6..3); g=5: a=0..3 (b=5..2)            8 MMAs, 56 KB
+    {6, 4, 6, 0, 2, 0, 1},   // g=6: a=4..6 (b=2..0); g=5: a=4..5 (b=1..0)            5 MMAs, 36 KB
+    {4, 0, 4, 0, 4, 1, 1},   // g=4: 5 pairs; g=3: 4 pairs                            9 MMAs, 60 KB
+    {2, 0, 2, 0, 2, 1, 1},   // g=2: 3 pairs; g=1: 2 pairs                            5 MMAs, 36 KB
+    {0, 0, 0, 0, 0, 1, 1},   // g=0: 1 pair                                           1 MMA,  12 KB
+};
+constexpr int kNumItems = 5;
+
+__device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+// K-major, SWIZZLE_32B: 8-row groups of 32-byte rows (SBO = 256 B), LBO = 1, descriptor version 1, layout type 6
+__device__ __forceinline__ uint64_t make_desc32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+}
+
+// ---- row scales and slicing ----
+// exps[r] = e with max_k |X[r][k]| < 2^e (0 for an all-zero row)
+__global__ void k_row_exp(const double* __restrict__ X, int64_t ld, int K, int* __restrict__ exps) {
+  const int r = blockIdx.x;
+  double m = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmax(m, fabs(X[(size_t)r * ld + k]));
+  __shared__ double sm[256];
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]); __syncthreads(); }
+  if (threadIdx.x == 0) { int e = 0; if (sm[0] > 0.0) frexp(sm[0], &e); exps[r] = e; }
+}
+// planes[s][r][k] = balanced digit s of trunc(X[r][k] * 2^(54 - exps[r])):  x 2^-e = sum_s d_s 2^(-6 - 8 s)
+__global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, int kp, const int* __restrict__ exps,
+                        int8_t* __restrict__ planes) {
+  const size_t plane = (size_t)R * kp;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / kp), k = (int)(e - (size_t)r * kp);
+    long long v = (k < K) ? __double2ll_rz(ldexp(X[(size_t)r * ld + k], 54 - exps[r])) : 0;    // |v| < 2^54, exact
+#pragma unroll
+    for (int s = S - 1; s >= 0; --s) {
+      const int d = (int)(int8_t)(v & 0xFF);
+      planes[(size_t)s * plane + e] = (int8_t)d;
+      v = (v - d) >> 8;
+    }
+  }
+}
+
+struct OzParams {
+  double* C; int64_t ldc;
+  const int* ea; const int* eb;      // row exponents of A (>= tiles_m * 128 entries) and B (>= tiles_n * 256 entries)
+  const CUtensorMap* maps;           // [0..5]: A with box depth 0..5 slices, [6..11]: B likewise (unused entries zero)
+  int chunks;                        // 32-byte K chunks in total
+  int split_chunks;                  // chunks per blockIdx.z (== chunks when K is not split)
+  int64_t c_split_stride;            // split z writes C + z * c_split_stride
+  int m_valid, n_valid;              // elements of C that exist
+  int lower_only;                    // skip tiles entirely above the diagonal
+  int accumulate;                    // 1: C += result, 0: C = result
+  int* err;
+};
+
+__global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t full = base, empty = base + 32, tfull = base + 64, tfree = base + 72, slot = base + 80;
+  const uint32_t cscale = base + 1024;               // 256 doubles: 2^eb of the tile's columns
+  const uint32_t stagebuf = base + 4096;             // 4 warps x 32 rows x 17 doubles (transpose staging for coalesced stores)
+  const uint32_t ring = base + 4096 + 20480;         // 1024-aligned
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bn = blockIdx.x, bm = blockIdx.y;
+  if (prm.lower_only && bn * TN > bm * TM + TM - 1) return;
+  const int c_begin = (int)blockIdx.z * prm.split_chunks;
+  const int nk = min(prm.split_chunks, prm.chunks - c_begin);
+  double* const Cz = prm.C + (size_t)blockIdx.z * prm.c_split_stride;
+  if (nk <= 0) {                                    // this split has no K range: its tile is zero
+    if (!prm.accumulate)
+      for (int e = tid; e < TM * TN; e += 192) {
+        const int r = bm * TM + e / TN, c = bn * TN + e % TN;
+        if (r < prm.m_valid && c < prm.n_valid) Cz[(size_t)r * prm.ldc + c] = 0.0;
+      }
+    return;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty + 8 * s));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfull));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(tfree));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int j = tid; j < TN; j += 192) {
+    const double cs = ldexp(1.0, prm.eb[bn * TN + j]);
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(cscale + 8 * j), "d"(cs) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  bool ok = true;
+  if (tid == 128) {                                 // ---- TMA producer (warp 4) ----
+    int q = 0;
+    for (int it = 0; it < kNumItems && ok; ++it) {
+      const Item w = kItems[it];
+      const int na = w.a_hi - w.a_lo + 1, nb = w.b_hi - w.b_lo + 1;
+      const uint32_t bytes = (uint32_t)(na * A_SLICE + nb * B_SLICE);
+      const CUtensorMap* mA = prm.maps + na;
+      const CUtensorMap* mB = prm.maps + 6 + nb;
+      for (int c = 0; c < nk && ok; ++c, ++q) {
+        const int s = q % STAGES;
+        if (q >= STAGES) ok = wait_bounded(empty + 8 * s, (uint32_t)(((q / STAGES) - 1) & 1));
+        if (!ok) break;
+        const uint32_t dst = ring + s * STAGE_BYTES, bar = full + 8 * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                     "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(w.a_lo), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                         dst + na * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(w.b_lo), "r"(bar) : "memory");
+      }
+    }
+    if (!ok) atomicExch(prm.err, 1);
+  } else if (tid == 160) {                          // ---- MMA issuer (warp 5) ----
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    int q = 0, drains = 0;
+    for (int it = 0; it < kNumItems && ok; ++it) {
+      const Item w = kItems[it];
+      const int na = w.a_hi - w.a_lo + 1;
+      if (w.first && drains > 0) ok = wait_bounded(tfree, (uint32_t)((drains - 1) & 1));   // accumulators drained
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < nk && ok; ++c, ++q) {
+        const int s = q % STAGES;
+        ok = wait_bounded(full + 8 * s, (uint32_t)((q / STAGES) & 1));
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = ring + s * STAGE_BYTES, sb = sa + na * A_SLICE;
+        for (int half = 0; half < 2; ++half) {      // group gh -> columns 0..255, group gh-1 -> columns 256..511
+          const int g = w.gh - half;
+          if (g < 0) break;
+          bool fresh = (c == 0) && w.first;         // first MMA of this accumulator in this K range overwrites
+          for (int a = w.a_lo; a <= w.a_hi; ++a) {
+            const int b = g - a;
+            if (b < w.b_lo || b > w.b_hi) continue;
+            const uint64_t da = make_desc32(sa + (a - w.a_lo) * A_SLICE), db = make_desc32(sb + (b - w.b_lo) * B_SLICE);
+            const uint32_t accf = fresh ? 0u : 1u;
+            fresh = false;
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+                             tmem + (uint32_t)(half * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
+      }
+      if (w.last) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
+        ++drains;
+      }
+    }
+    if (!ok) atomicExch(prm.err, 2);
+  }
+  __syncwarp();
+  // ---- drains (warps 0-3): thread = tile row (TMEM lane); FP64 tile accumulated in global memory through a transpose ----
+  if (warp < 4) {
+    const int row0 = bm * TM + warp * 32;
+    const double rs = ldexp(1.0, prm.ea[row0 + lane]);
+    const uint32_t stg = stagebuf + (uint32_t)warp * (32 * 17 * 8);
+    int drains = 0;
+    bool live = true;
+    for (int it = 0; it < kNumItems && live; ++it) {
+      const Item w = kItems[it];
+      if (!w.last) continue;
+      live = wait_bounded(tfull, (uint32_t)(drains & 1));
+      if (!live) { if (lane == 0) atomicExch(prm.err, 3); break; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const double w_hi = ldexp(1.0, -12 - 8 * w.gh) * rs, w_lo = (w.gh > 0) ? ldexp(1.0, -12 - 8 * (w.gh - 1)) * rs : 0.0;
+      for (int c0 = 0; c0 < TN; c0 += 16) {
+        uint32_t hi[16], lo[16];
+        const uint32_t t_hi = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, t_lo = t_hi + TN;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]),
+                       "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15])
+                     : "r"(t_hi));
+        if (w.gh > 0) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                       : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(lo[8]),
+                         "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(lo[12]), "=r"(lo[13]), "=r"(lo[14]), "=r"(lo[15])
+                       : "r"(t_lo));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) lo[j] = 0;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {              // own row, 16 columns -> staging [row][17]
+          const double v = w_hi * (double)(int)hi[j] + w_lo * (double)(int)lo[j];
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(stg + (uint32_t)(lane * 17 + j) * 8), "d"(v) : "memory");
+        }
+        __syncwarp();
+        // two rows per step, lanes 0-15 / 16-31 along the 16 columns: 128-byte segments; all loads before all stores
+        const int j = lane & 15;
+        double cs;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cs) : "r"(cscale + (uint32_t)(c0 + j) * 8));
+        const int col = bn * TN + c0 + j, rbase = row0 + (lane >> 4);
+        const bool col_ok = col < prm.n_valid;
+        double* dst0 = Cz + (size_t)rbase * prm.ldc + col;
+        const bool keep = (drains > 0) || prm.accumulate;
+        double old[16], val[16];
+#pragma unroll
+        for (int h = 0; h < 16; ++h) old[h] = (keep && col_ok && rbase + 2 * h < prm.m_valid) ? __ldcg(dst0 + (size_t)(2 * h) * prm.ldc) : 0.0;
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          const int r = 2 * h + (lane >> 4);
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(val[h]) : "r"(stg + (uint32_t)(r * 17 + j) * 8));
+        }
+#pragma unroll
+        for (int h = 0; h < 16; ++h)
+          if (col_ok && rbase + 2 * h < prm.m_valid) __stcg(dst0 + (size_t)(2 * h) * prm.ldc, old[h] + val[h] * cs);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tfree) : "memory");
+      ++drains;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn3 encode_fn3() {
+  static EncodeTiledFn3 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn3>(p);
+  }
+  return fn;
+}
+
+// planes: [S][rows_alloc][kp] int8; rows beyond `rows` read as zeros (TMA out-of-bounds fill)
+static int make_plane_map(CUtensorMap* m, const int8_t* planes, int rows, int64_t rows_alloc, int kp, int box_rows, int depth) {
+  EncodeTiledFn3 enc = encode_fn3();
+  if (!enc) return fail(GRIEF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[3] = {(cuuint64_t)kp, (cuuint64_t)rows, (cuuint64_t)S};
+  const cuuint64_t gstr[2] = {(cuuint64_t)kp, (cuuint64_t)kp * (cuuint64_t)rows_alloc};
+  const cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, (cuuint32_t)depth};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GRIEF_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes) failed with code %d", (int)r);
+  return GRIEF_OK;
+}
+
+static int* g_oz_err = nullptr;        // device error flag shared by all launches of this process
+static CUtensorMap* g_oz_maps = nullptr;   // ring of device-resident tensor-map sets (12 maps per launch)
+static int g_oz_map_slot = 0;
+constexpr int kMapSlots = 64;
+
+size_t ozaki_plane_bytes(int64_t rows, int K) { return (size_t)S * (size_t)rows * (size_t)((K + KC - 1) / KC * KC); }
+
+// exps[r] (r < rows; entries up to exps_len are zeroed) and digit planes of X (rows x K, ld); planes: [S][rows][kp], kp = K rounded up to 32
+int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exps_len, int8_t* planes, cudaStream_t stream) {
+  if (rows == 0) return GRIEF_OK;
+  const int kp = (K + KC - 1) / KC * KC;
+  if (exps_len > rows) GRIEF_CUDA(cudaMemsetAsync(exps + rows, 0, (size_t)(exps_len - rows) * sizeof(int), stream));
+  k_row_exp<<<rows, 256, 0, stream>>>(X, ld, K, exps);
+  k_slice<<<148 * 8, 256, 0, stream>>>(X, ld, rows, K, kp, exps, planes);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+// C (M x N, ldc) (+)= A B^T from digit planes.  pa: [S][rows_a_alloc][kp] with M valid rows, ea: >= round_up(M,128) exponents;
+// pb likewise with N rows and >= round_up(N,256) exponents.  K <= 16384 * splits.
+int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, const int8_t* pb, int64_t rows_b_alloc, const int* eb, int N,
+               int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, cudaStream_t stream,
+               int* launches) {
+  if (M <= 0 || N <= 0) return GRIEF_OK;
+  const int kp = (K + KC - 1) / KC * KC;
+  const int chunks = kp / KC;
+  splits = std::max(1, splits);
+  const int split_chunks = (chunks + splits - 1) / splits;
+  GRIEF_REQUIRE(split_chunks * KC <= 16384, "ozaki_gemm: %d values of K per accumulation exceed the int32 budget of 16384", split_chunks * KC);
+  if (!g_oz_err) {
+    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_err), sizeof(int)));
+    GRIEF_CUDA(cudaMemset(g_oz_err, 0, sizeof(int)));
+    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 12 * kMapSlots));
+  }
+  alignas(64) CUtensorMap hmaps[12];
+  memset(hmaps, 0, sizeof(hmaps));
+  for (int dpt = 1; dpt <= 5; ++dpt) {
+    int rc = make_plane_map(&hmaps[dpt], pa, M, rows_a_alloc, kp, TM, dpt);
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[6 + dpt], pb, N, rows_b_alloc, kp, TN, dpt);
+    if (rc != GRIEF_OK) return rc;
+  }
+  CUtensorMap* dmaps = g_oz_maps + 12 * (g_oz_map_slot++ % kMapSlots);
+  GRIEF_CUDA(cudaMemcpyAsync(dmaps, hmaps, sizeof(hmaps), cudaMemcpyHostToDevice, stream));
+  OzParams prm;
+  prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb; prm.maps = dmaps;
+  prm.chunks = chunks; prm.split_chunks = split_chunks; prm.c_split_stride = c_split_stride;
+  prm.m_valid = M; prm.n_valid = N; prm.lower_only = lower_only ? 1 : 0; prm.accumulate = accumulate ? 1 : 0; prm.err = g_oz_err;
+  const size_t smem = 1024 + 4096 + 20480 + 1024 + (size_t)STAGES * STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
+  k_ozaki<<<grid, 192, smem, stream>>>(prm);
+  GRIEF_CUDA(cudaGetLastError());
+  if (launches) *launches += 1;
+  return GRIEF_OK;
+}
+
+// Synchronises the stream and reports a pipeline failure inside any k_ozaki launch since the last check.
+int ozaki_check(cudaStream_t stream) {
+  if (!g_oz_err) return GRIEF_OK;
+  int flag = 0;
+  GRIEF_CUDA(cudaMemcpyAsync(&flag, g_oz_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  GRIEF_CUDA(cudaStreamSynchronize(stream));
+  if (flag != 0) {
+    cudaMemsetAsync(g_oz_err, 0, sizeof(int), stream);
+    return fail(GRIEF_ERR_CUDA, "k_ozaki: barrier wait timed out in role %d (1 = TMA producer, 2 = MMA issuer, 3 = drain)", flag);
+  }
+  return GRIEF_OK;
+}
+
+}  // namespace grief

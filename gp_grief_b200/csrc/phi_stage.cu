@@ -150,6 +150,11 @@ struct GramSchedule {
   int64_t slab_rows;
 };
 
+static int g_gemm_mode = 1;            // INT8 tensor-core arithmetic by default; 0 = FP64 DMMA
+int gemm_mode() { return g_gemm_mode; }
+void set_gemm_mode(int mode) { g_gemm_mode = mode ? 1 : 0; }
+constexpr int kOzakiKRange = 16384;   // values of K per int32 accumulation in k_ozaki
+
 static size_t g_slab_budget_bytes = (size_t)4 << 30;      // bytes of Phi^T staged per pass-1 slab
 void set_slab_budget(size_t bytes) { g_slab_budget_bytes = bytes ? bytes : ((size_t)4 << 30); }
 
@@ -171,14 +176,19 @@ GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
     if (eff >= 0.97) { best = (int)S; break; }
   }
   s.splits = best;
+  if (g_gemm_mode == 1) s.splits = (int)((s.slab_rows + kOzakiKRange - 1) / kOzakiKRange);   // one int32 accumulation per split
   return s;
 }
 
 static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
+static size_t gram_exps_len(const Plan* pl) { return (size_t)(pl->p_pad + 255) / 256 * 256; }
+
 size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms) {
   const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
-  return align256((size_t)pl->p_pad * s.slab_rows * sizeof(double)) + (size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double);
+  size_t b = align256((size_t)pl->p_pad * s.slab_rows * sizeof(double)) + align256((size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double));
+  if (g_gemm_mode == 1) b += align256(ozaki_plane_bytes(pl->p_pad, (int)s.slab_rows)) + align256(gram_exps_len(pl) * sizeof(int));
+  return b;
 }
 
 // A[perm[i]][perm[j]] = sum_s part[s][i][j] over the lower tiles (fixed split order), mirrored bit-identically.
@@ -206,8 +216,15 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
   const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
   const int pp = pl->p_pad;
-  double* PhiT = reinterpret_cast<double*>(workspace);
-  double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + align256((size_t)pp * s.slab_rows * sizeof(double)));
+  char* wq = reinterpret_cast<char*>(workspace);
+  double* PhiT = reinterpret_cast<double*>(wq); wq += align256((size_t)pp * s.slab_rows * sizeof(double));
+  double* part = reinterpret_cast<double*>(wq); wq += align256((size_t)s.splits * pp * pp * sizeof(double));
+  int8_t* planes = nullptr;
+  int* exps = nullptr;
+  if (g_gemm_mode == 1) {
+    planes = reinterpret_cast<int8_t*>(wq); wq += align256(ozaki_plane_bytes(pp, (int)s.slab_rows));
+    exps = reinterpret_cast<int*>(wq);
+  }
   const size_t part_doubles = (size_t)s.splits * pp * pp;
   if (n_pad == 0) GRIEF_CUDA(cudaMemsetAsync(part, 0, part_doubles * sizeof(double), stream));
   GemmOpts o;
@@ -218,10 +235,15 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
     const int64_t R = std::min(s.slab_rows, n_pad - r0);
     prof_begin(PROF_BUILD_T, stream);
     int rc = launch_build(pl, T + (size_t)r0 * pl->stride, R, true, PhiT, s.slab_rows, stream);
+    if (rc == GRIEF_OK && g_gemm_mode == 1)      // digit planes of the slab: rows = sorted columns of Phi, K = data rows
+      rc = ozaki_slice(PhiT, s.slab_rows, pp, (int)R, exps, (int)gram_exps_len(pl), planes, stream);
     prof_end(PROF_BUILD_T, stream);
     if (rc != GRIEF_OK) return rc;
     prof_begin(PROF_GRAM, stream);
-    rc = gemm_nt_ex(PhiT, s.slab_rows, PhiT, s.slab_rows, part, pp, pp, pp, (int)R, 1.0, r0 > 0 ? 1.0 : 0.0, o, stream, launches);
+    if (g_gemm_mode == 1)
+      rc = ozaki_gemm(planes, pp, exps, pp, planes, pp, exps, pp, (int)R, part, pp, r0 > 0, true, s.splits, (int64_t)pp * pp, stream, launches);
+    else
+      rc = gemm_nt_ex(PhiT, s.slab_rows, PhiT, s.slab_rows, part, pp, pp, pp, (int)R, 1.0, r0 > 0 ? 1.0 : 0.0, o, stream, launches);
     prof_end(PROF_GRAM, stream);
     if (rc != GRIEF_OK) return rc;
     if (launches) *launches += 1;
@@ -252,21 +274,64 @@ int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm
   return GRIEF_OK;
 }
 
-// Z (slab_rows x ldz; columns >= p are zero) = Phi(slab) * B, B symmetric given as Bperm (p x p_pad, launch_permute_b).
-// Phi_slab: scratch of slab_rows x p_pad doubles.
-int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, double* Phi_slab, double* Z, int64_t ldz,
-                 cudaStream_t stream, int* launches) {
+// Scratch of the Z = Phi B product (carved out of the callers' workspaces)
+size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows) {
+  size_t b = align256((size_t)slab_rows * pl->p_pad * sizeof(double));                       // Phi slab
+  if (g_gemm_mode == 1)
+    b += align256(ozaki_plane_bytes(slab_rows, pl->p_pad)) + align256((size_t)slab_rows * sizeof(int)) +       // digits of the slab
+         align256(ozaki_plane_bytes(pl->p_pad, pl->p_pad)) + align256(((size_t)pl->p_pad + 256) * sizeof(int));  // digits of B
+  return b;
+}
+
+struct ZScratch {
+  double* Phi;
+  int8_t* pa; int* ea;
+  int8_t* pb; int* eb;
+};
+static ZScratch carve_zscratch(const Plan* pl, int64_t slab_rows, void* scratch) {
+  ZScratch z{};
+  char* q = reinterpret_cast<char*>(scratch);
+  z.Phi = reinterpret_cast<double*>(q); q += align256((size_t)slab_rows * pl->p_pad * sizeof(double));
+  if (g_gemm_mode == 1) {
+    z.pa = reinterpret_cast<int8_t*>(q); q += align256(ozaki_plane_bytes(slab_rows, pl->p_pad));
+    z.ea = reinterpret_cast<int*>(q); q += align256((size_t)slab_rows * sizeof(int));
+    z.pb = reinterpret_cast<int8_t*>(q); q += align256(ozaki_plane_bytes(pl->p_pad, pl->p_pad));
+    z.eb = reinterpret_cast<int*>(q);
+  }
+  return z;
+}
+
+// Once per evaluation, after launch_permute_b: digit planes of B' for the INT8 path (no-op on the DMMA path).
+int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream) {
+  if (g_gemm_mode != 1) return GRIEF_OK;
+  ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
+  return ozaki_slice(Bperm, pl->p_pad, pl->p, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, stream);
+}
+
+// Z (slab_rows x ldz) = Phi(slab) * B, B symmetric given as Bperm (p x p_pad, launch_permute_b).  Columns >= p of Z are
+// zero on the DMMA path and left untouched on the INT8 path (no consumer reads them).
+// scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
+                 int64_t ldz, cudaStream_t stream, int* launches) {
   GRIEF_REQUIRE(slab_rows % kBuildRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kBuildRows);
   GRIEF_REQUIRE(ldz >= pl->p_pad, "zgemm: ldz=%lld must be >= p_pad=%d", (long long)ldz, pl->p_pad);
   if (slab_rows == 0) return GRIEF_OK;
+  ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
   prof_begin(PROF_BUILD, stream);
-  int rc = launch_build(pl, T_slab, slab_rows, false, Phi_slab, pl->p_pad, stream);
+  int rc = launch_build(pl, T_slab, slab_rows, false, z.Phi, pl->p_pad, stream);
+  if (rc == GRIEF_OK && g_gemm_mode == 1)
+    rc = ozaki_slice(z.Phi, pl->p_pad, (int)slab_rows, pl->p_pad, z.ea, (int)slab_rows, z.pa, stream);
   prof_end(PROF_BUILD, stream);
   if (rc != GRIEF_OK) return rc;
-  GemmOpts o;
-  o.rows_b = pl->p;                                   // rows p..p_pad of B' do not exist: TMA fills zeros
   prof_begin(PROF_ZGEMM, stream);
-  rc = gemm_nt_ex(Phi_slab, pl->p_pad, Bperm, pl->p_pad, Z, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);
+  if (g_gemm_mode == 1) {
+    GRIEF_REQUIRE(pl->p_pad <= kOzakiKRange, "zgemm: p_pad=%d exceeds the INT8 path's K range of %d", pl->p_pad, kOzakiKRange);
+    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p, z.eb, pl->p, pl->p_pad, Z, ldz, false, false, 1, 0, stream, launches);
+  } else {
+    GemmOpts o;
+    o.rows_b = pl->p;                                 // rows p..p_pad of B' do not exist: TMA fills zeros
+    rc = gemm_nt_ex(z.Phi, pl->p_pad, Bperm, pl->p_pad, Z, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);
+  }
   prof_end(PROF_ZGEMM, stream);
   if (rc == GRIEF_OK && launches) *launches += 1;
   return rc;

@@ -82,4 +82,15 @@ struct GemmOpts {
 int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K, double alpha,
                double beta, const GemmOpts& opts, cudaStream_t stream, int* launches);
 
+// FP64 GEMM on the INT8 tensor cores (ozaki.cu).  Digit planes: [7][rows_alloc][K rounded up to 32] int8.
+size_t ozaki_plane_bytes(int64_t rows, int K);
+int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exps_len, int8_t* planes, cudaStream_t stream);
+int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, const int8_t* pb, int64_t rows_b_alloc, const int* eb, int N,
+               int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, cudaStream_t stream,
+               int* launches);
+int ozaki_check(cudaStream_t stream);
+// 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki) for the two O(n p^2) products
+int gemm_mode();
+void set_gemm_mode(int mode);
+
 }  // namespace grief

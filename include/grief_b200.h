@@ -132,6 +132,17 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
 void grief_set_slab_budget(size_t bytes);
 
 /*
+ * Arithmetic of the two O(n p^2) products (A = Phi^T Phi and Z = Phi B):
+ *   0  FP64 DMMA GEMM (k_gemm_nt), 36 TFLOP/s
+ *   1  FP64 emulated on the INT8 tensor cores (tcgen05 kind::i8, 7 balanced 8-bit digits per operand = 54 bits + sign,
+ *      28 exact int8 x int8 -> int32 digit products), ~75 TFLOP/s FP64-equivalent; element errors are bounded by 2^-53 of
+ *      the product of the operands' row maxima times K, i.e. the accuracy class of DGEMM
+ * Workspace sizes depend on the mode: query them after changing it.  Process-wide.
+ */
+void grief_set_gemm_mode(int mode);
+int grief_get_gemm_mode(void);
+
+/*
  * Fused Gram:  A = Phi^T Phi without materialising Phi (models/gp_grief_model.py:148-149).
  *   A_dev       out, (p, lda) row-major, full symmetric matrix
  *   workspace   device scratch of at least grief_gram_workspace_bytes(plan, n) bytes
