@@ -323,7 +323,7 @@ def run_ours(args):
     roofline = None
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["k_gemm_nt_zgemm"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["k_ozaki_zgemm" if args.gemm == "int8" else "k_gemm_nt_zgemm"]
         if tr["config"] == args.config:
             traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "rows_per_launch": tr["rows_per_launch"],
                        "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "source": tr["source"]}

@@ -37,14 +37,38 @@ __device__ __forceinline__ void stage_table_rows(double* sT, uint64_t* bar, cons
   mbar_wait(bar, 0);
 }
 
-// Phi^T slab: out[c * ld + row], c = sorted column.  Lane = data row; a warp walks a run of consecutive sorted columns,
-// which share their leading slots: the product P of the first G-1 factors stays in a register and is rebuilt only where
-// sorted_level says a leading factor changed (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
-template <int G>
+// What a builder launch produces: the FP64 slab (DMMA path), or -- for the INT8 path, which never stores the FP64 slab --
+// first the binary exponents of the operand rows' maxima, then the 7 balanced 8-bit digits of every element.
+enum BuildOut : int { OUT_F64 = 0, OUT_EXP = 1, OUT_DIGITS = 2 };
+constexpr int kDigits = 7;
+
+// high word of |v|: orders like |v|, and its exponent field is all the INT8 path needs of a row maximum
+__device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
+// frexp exponent e (|x| < 2^e) from the high word of the row maximum (0 for an all-zero row)
+__device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? max((hi >> 20) - 1022, -900) : 0; }   // clamp: 2^(54-e) stays finite
+// digits d_s of trunc(v * scale), scale = 2^(54 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s)
+__device__ __forceinline__ void store_digits(double v, double scale, int8_t* __restrict__ base, size_t plane_stride) {
+  long long q = __double2ll_rz(v * scale);
+#pragma unroll
+  for (int s = kDigits - 1; s >= 0; --s) {
+    const int d = (int)(int8_t)(q & 0xFF);
+    base[(size_t)s * plane_stride] = (int8_t)d;
+    q = (q - d) >> 8;
+  }
+}
+
+// Phi^T slab, c = sorted column.  Lane = data row; a warp walks a run of consecutive sorted columns, which share their
+// leading slots: the product P of the first G-1 factors stays in a register and is rebuilt only where sorted_level says a
+// leading factor changed (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
+//   OUT_F64:    out[c * ld + row]
+//   OUT_EXP:    atomicMax(col_hi[c], high word of |Phi[row][c]|) over the slab's rows (one REDUX per column and warp)
+//   OUT_DIGITS: planes[s][c][row] (row stride ld bytes, plane stride p_pad * ld), scaled by 2^(54 - exps[c])
+template <int G, int MODE>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __restrict__ T, int stride,
                                                                const uint16_t* __restrict__ sorted_slot,
                                                                const uint8_t* __restrict__ sorted_level, int p_pad,
-                                                               double* __restrict__ out, int64_t ld) {
+                                                               double* __restrict__ out, int64_t ld, int* __restrict__ col_hi,
+                                                               const int* __restrict__ exps, int8_t* __restrict__ planes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
@@ -54,7 +78,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
   const double* trow = sT + (size_t)row * stride;
   const int cpq = p_pad / 4;                           // four warps share a row group, a quarter of the columns each
   const int c_begin = (warp >> 2) * cpq;
-  double* dst = out + (size_t)blockIdx.x * kBuildRows + row;
+  const size_t grow = (size_t)blockIdx.x * kBuildRows + row;
   constexpr int NB = 8;
   double P = 1.0;
   for (int c0 = c_begin; c0 < c_begin + cpq; c0 += NB) {
@@ -77,17 +101,41 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
         last[e] *= P;
       }
     }
+    if constexpr (MODE == OUT_F64) {
 #pragma unroll
-    for (int e = 0; e < NB; ++e) dst[(size_t)(c0 + e) * ld] = last[e];
+      for (int e = 0; e < NB; ++e) out[(size_t)(c0 + e) * ld + grow] = last[e];
+    } else if constexpr (MODE == OUT_EXP) {
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        const int m = __reduce_max_sync(0xffffffffu, abs_hi(last[e]));
+        if (lane == 0 && m > 0) atomicMax(col_hi + c0 + e, m);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        const double scale = __hiloint2double((1023 + 54 - __ldg(exps + c0 + e)) << 20, 0);
+        store_digits(last[e], scale, planes + (size_t)(c0 + e) * ld + grow, (size_t)p_pad * ld);
+      }
+    }
   }
 }
 
-// Phi slab, row-major: out[row * ldo + c].  Lane = sorted column (coalesced stores); the G slots of a column are loaded
-// once and reused for the warp's eight rows.
-template <int G>
+// exps[c] from the accumulated high words (and reset them for the next slab)
+__global__ void k_exps_from_hi(int* __restrict__ hi, int n, int n_pad, int* __restrict__ exps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { exps[i] = exp_from_hi(hi[i]); hi[i] = 0; }
+  else if (i < n_pad) exps[i] = 0;
+}
+
+// Phi slab, row-major, lane = sorted column (coalesced stores); the G slots of a column are loaded once and reused for the
+// warp's eight rows.
+//   OUT_F64:    out[row * ldo + c]
+//   OUT_DIGITS: exps[row] from the row maximum (first sweep, registers only), then planes[s][row][c] (second sweep)
+template <int G, int MODE>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __restrict__ T, int stride,
                                                              const uint16_t* __restrict__ sorted_slot, int p_pad,
-                                                             double* __restrict__ out, int64_t ldo) {
+                                                             double* __restrict__ out, int64_t ldo, int* __restrict__ exps,
+                                                             int8_t* __restrict__ planes, size_t plane_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
@@ -95,7 +143,31 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int RW = kBuildRows / (kBuildThreads / 32);   // 8 rows per warp
   const double* tbase = sT + (size_t)warp * RW * stride;
-  double* obase = out + ((size_t)blockIdx.x * kBuildRows + warp * RW) * ldo;
+  const size_t row0 = (size_t)blockIdx.x * kBuildRows + warp * RW;
+  double scale[RW];
+  if constexpr (MODE == OUT_DIGITS) {
+    int hi[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) hi[r] = 0;
+    for (int c = lane; c < p_pad; c += 32) {
+      int sl[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) sl[g] = __ldg(sorted_slot + (size_t)c * G + g);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        double v = tbase[r * stride + sl[0]];
+#pragma unroll
+        for (int g = 1; g < G; ++g) v *= tbase[r * stride + sl[g]];
+        hi[r] = max(hi[r], abs_hi(v));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const int e = exp_from_hi(__reduce_max_sync(0xffffffffu, hi[r]));
+      if (lane == 0) exps[row0 + r] = e;
+      scale[r] = __hiloint2double((1023 + 54 - e) << 20, 0);
+    }
+  }
   for (int c = lane; c < p_pad; c += 32) {
     int sl[G];
 #pragma unroll
@@ -107,39 +179,68 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
     for (int g = 1; g < G; ++g)
 #pragma unroll
       for (int r = 0; r < RW; ++r) v[r] *= tbase[r * stride + sl[g]];
+    if constexpr (MODE == OUT_F64) {
 #pragma unroll
-    for (int r = 0; r < RW; ++r) obase[(size_t)r * ldo + c] = v[r];
+      for (int r = 0; r < RW; ++r) out[(row0 + r) * ldo + c] = v[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < RW; ++r) store_digits(v[r], scale[r], planes + (row0 + r) * (size_t)p_pad + c, plane_stride);
+    }
   }
 }
 
+struct BuildArgs {
+  bool transposed = false;
+  int mode = OUT_F64;
+  double* out = nullptr; int64_t ld = 0;     // FP64 slab (OUT_F64); ld also = bytes per plane row of the transposed digits
+  int* col_hi = nullptr;                     // OUT_EXP (transposed)
+  int* exps = nullptr;                       // read (transposed OUT_DIGITS) or written (row-major OUT_DIGITS)
+  int8_t* planes = nullptr; size_t plane_stride = 0;
+};
+
 template <int G>
-static int launch_build_g(const Plan* pl, const double* T, int64_t rows, bool transposed, double* out, int64_t ld, cudaStream_t stream) {
+static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
   const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
   const unsigned grid = (unsigned)(rows / kBuildRows);
-  if (transposed) {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_build_phi_t<G><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad, out, ld);
+#define GRIEF_BT(MODE_)                                                                                                             \
+  do {                                                                                                                              \
+    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    k_build_phi_t<G, MODE_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad, \
+                                                                  a.out, a.ld, a.col_hi, a.exps, a.planes);                         \
+  } while (0)
+#define GRIEF_BN(MODE_)                                                                                                             \
+  do {                                                                                                                              \
+    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    k_build_phi<G, MODE_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, a.out, a.ld, a.exps,  \
+                                                                a.planes, a.plane_stride);                                          \
+  } while (0)
+  if (a.transposed) {
+    if (a.mode == OUT_F64) GRIEF_BT(OUT_F64);
+    else if (a.mode == OUT_EXP) GRIEF_BT(OUT_EXP);
+    else GRIEF_BT(OUT_DIGITS);
   } else {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_build_phi<G><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, out, ld);
+    if (a.mode == OUT_F64) GRIEF_BN(OUT_F64);
+    else GRIEF_BN(OUT_DIGITS);
   }
+#undef GRIEF_BT
+#undef GRIEF_BN
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
 
-// rows: multiple of 128.  transposed: out is p_pad x ld (ld >= rows); otherwise rows x ld (ld >= p_pad).
-static int launch_build(const Plan* pl, const double* T, int64_t rows, bool transposed, double* out, int64_t ld, cudaStream_t stream) {
+// rows: multiple of 128.
+static int launch_build(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
   if (rows == 0) return GRIEF_OK;
   GRIEF_REQUIRE(rows % kBuildRows == 0, "build_phi: rows=%lld is not a multiple of %d", (long long)rows, kBuildRows);
   switch (pl->n_groups) {
-    case 1: return launch_build_g<1>(pl, T, rows, transposed, out, ld, stream);
-    case 2: return launch_build_g<2>(pl, T, rows, transposed, out, ld, stream);
-    case 3: return launch_build_g<3>(pl, T, rows, transposed, out, ld, stream);
-    case 4: return launch_build_g<4>(pl, T, rows, transposed, out, ld, stream);
-    case 5: return launch_build_g<5>(pl, T, rows, transposed, out, ld, stream);
-    case 6: return launch_build_g<6>(pl, T, rows, transposed, out, ld, stream);
-    case 7: return launch_build_g<7>(pl, T, rows, transposed, out, ld, stream);
-    case 8: return launch_build_g<8>(pl, T, rows, transposed, out, ld, stream);
+    case 1: return launch_build_g<1>(pl, T, rows, a, stream);
+    case 2: return launch_build_g<2>(pl, T, rows, a, stream);
+    case 3: return launch_build_g<3>(pl, T, rows, a, stream);
+    case 4: return launch_build_g<4>(pl, T, rows, a, stream);
+    case 5: return launch_build_g<5>(pl, T, rows, a, stream);
+    case 6: return launch_build_g<6>(pl, T, rows, a, stream);
+    case 7: return launch_build_g<7>(pl, T, rows, a, stream);
+    case 8: return launch_build_g<8>(pl, T, rows, a, stream);
     default: return fail(GRIEF_ERR_UNSUPPORTED, "build_phi: %d groups", pl->n_groups);
   }
 }
@@ -184,11 +285,12 @@ static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
 static size_t gram_exps_len(const Plan* pl) { return (size_t)(pl->p_pad + 255) / 256 * 256; }
 
+// workspace: [Phi^T slab (FP64, DMMA path) | digit planes (INT8 path)] [split partials] [exps] [col_hi]
 size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms) {
   const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
-  size_t b = align256((size_t)pl->p_pad * s.slab_rows * sizeof(double)) + align256((size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double));
-  if (g_gemm_mode == 1) b += align256(ozaki_plane_bytes(pl->p_pad, (int)s.slab_rows)) + align256(gram_exps_len(pl) * sizeof(int));
-  return b;
+  const size_t slab = g_gemm_mode == 1 ? align256(ozaki_plane_bytes(pl->p_pad, (int)s.slab_rows))
+                                       : align256((size_t)pl->p_pad * s.slab_rows * sizeof(double));
+  return slab + align256((size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double)) + 2 * align256(gram_exps_len(pl) * sizeof(int));
 }
 
 // A[perm[i]][perm[j]] = sum_s part[s][i][j] over the lower tiles (fixed split order), mirrored bit-identically.
@@ -216,37 +318,51 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
   const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
   const int pp = pl->p_pad;
+  const bool i8 = g_gemm_mode == 1;
   char* wq = reinterpret_cast<char*>(workspace);
-  double* PhiT = reinterpret_cast<double*>(wq); wq += align256((size_t)pp * s.slab_rows * sizeof(double));
+  double* PhiT = reinterpret_cast<double*>(wq);
+  int8_t* planes = reinterpret_cast<int8_t*>(wq);
+  wq += i8 ? align256(ozaki_plane_bytes(pp, (int)s.slab_rows)) : align256((size_t)pp * s.slab_rows * sizeof(double));
   double* part = reinterpret_cast<double*>(wq); wq += align256((size_t)s.splits * pp * pp * sizeof(double));
-  int8_t* planes = nullptr;
-  int* exps = nullptr;
-  if (g_gemm_mode == 1) {
-    planes = reinterpret_cast<int8_t*>(wq); wq += align256(ozaki_plane_bytes(pp, (int)s.slab_rows));
-    exps = reinterpret_cast<int*>(wq);
-  }
+  int* exps = reinterpret_cast<int*>(wq); wq += align256(gram_exps_len(pl) * sizeof(int));
+  int* col_hi = reinterpret_cast<int*>(wq);
   const size_t part_doubles = (size_t)s.splits * pp * pp;
   if (n_pad == 0) GRIEF_CUDA(cudaMemsetAsync(part, 0, part_doubles * sizeof(double), stream));
+  if (i8) GRIEF_CUDA(cudaMemsetAsync(col_hi, 0, gram_exps_len(pl) * sizeof(int), stream));
   GemmOpts o;
   o.lower_only = true;
   o.splits = s.splits;
   o.c_split_stride = (int64_t)pp * pp;
   for (int64_t r0 = 0; r0 < n_pad; r0 += s.slab_rows) {
     const int64_t R = std::min(s.slab_rows, n_pad - r0);
+    const double* Ts = T + (size_t)r0 * pl->stride;
+    BuildArgs ba;
+    ba.transposed = true;
+    int rc;
     prof_begin(PROF_BUILD_T, stream);
-    int rc = launch_build(pl, T + (size_t)r0 * pl->stride, R, true, PhiT, s.slab_rows, stream);
-    if (rc == GRIEF_OK && g_gemm_mode == 1)      // digit planes of the slab: rows = sorted columns of Phi, K = data rows
-      rc = ozaki_slice(PhiT, s.slab_rows, pp, (int)R, exps, (int)gram_exps_len(pl), planes, stream);
+    if (i8) {      // exponents of the column maxima over the slab, then the digit planes [7][p_pad][R] (K = data rows)
+      ba.mode = OUT_EXP; ba.col_hi = col_hi;
+      rc = launch_build(pl, Ts, R, ba, stream);
+      if (rc == GRIEF_OK) {
+        const int n_e = (int)gram_exps_len(pl);
+        k_exps_from_hi<<<(n_e + 255) / 256, 256, 0, stream>>>(col_hi, pp, n_e, exps);
+        ba.mode = OUT_DIGITS; ba.exps = exps; ba.planes = planes; ba.ld = R;
+        rc = launch_build(pl, Ts, R, ba, stream);
+      }
+    } else {
+      ba.mode = OUT_F64; ba.out = PhiT; ba.ld = s.slab_rows;
+      rc = launch_build(pl, Ts, R, ba, stream);
+    }
     prof_end(PROF_BUILD_T, stream);
     if (rc != GRIEF_OK) return rc;
     prof_begin(PROF_GRAM, stream);
-    if (g_gemm_mode == 1)
+    if (i8)
       rc = ozaki_gemm(planes, pp, exps, pp, planes, pp, exps, pp, (int)R, part, pp, r0 > 0, true, s.splits, (int64_t)pp * pp, stream, launches);
     else
       rc = gemm_nt_ex(PhiT, s.slab_rows, PhiT, s.slab_rows, part, pp, pp, pp, (int)R, 1.0, r0 > 0 ? 1.0 : 0.0, o, stream, launches);
     prof_end(PROF_GRAM, stream);
     if (rc != GRIEF_OK) return rc;
-    if (launches) *launches += 1;
+    if (launches) *launches += i8 ? 3 : 1;
   }
   k_gram_reduce<<<dim3(s.nb, s.nb), 256, 0, stream>>>(part, pl->d_perm, pp, s.splits, lda, A);
   GRIEF_CUDA(cudaGetLastError());
@@ -276,11 +392,9 @@ int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm
 
 // Scratch of the Z = Phi B product (carved out of the callers' workspaces)
 size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows) {
-  size_t b = align256((size_t)slab_rows * pl->p_pad * sizeof(double));                       // Phi slab
-  if (g_gemm_mode == 1)
-    b += align256(ozaki_plane_bytes(slab_rows, pl->p_pad)) + align256((size_t)slab_rows * sizeof(int)) +       // digits of the slab
+  if (g_gemm_mode != 1) return align256((size_t)slab_rows * pl->p_pad * sizeof(double));                       // Phi slab
+  return align256(ozaki_plane_bytes(slab_rows, pl->p_pad)) + align256((size_t)slab_rows * sizeof(int)) +       // digits of the slab
          align256(ozaki_plane_bytes(pl->p_pad, pl->p_pad)) + align256(((size_t)pl->p_pad + 256) * sizeof(int));  // digits of B
-  return b;
 }
 
 struct ZScratch {
@@ -291,8 +405,9 @@ struct ZScratch {
 static ZScratch carve_zscratch(const Plan* pl, int64_t slab_rows, void* scratch) {
   ZScratch z{};
   char* q = reinterpret_cast<char*>(scratch);
-  z.Phi = reinterpret_cast<double*>(q); q += align256((size_t)slab_rows * pl->p_pad * sizeof(double));
-  if (g_gemm_mode == 1) {
+  if (g_gemm_mode != 1) {
+    z.Phi = reinterpret_cast<double*>(q);
+  } else {
     z.pa = reinterpret_cast<int8_t*>(q); q += align256(ozaki_plane_bytes(slab_rows, pl->p_pad));
     z.ea = reinterpret_cast<int*>(q); q += align256((size_t)slab_rows * sizeof(int));
     z.pb = reinterpret_cast<int8_t*>(q); q += align256(ozaki_plane_bytes(pl->p_pad, pl->p_pad));
@@ -317,10 +432,14 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   GRIEF_REQUIRE(ldz >= pl->p_pad, "zgemm: ldz=%lld must be >= p_pad=%d", (long long)ldz, pl->p_pad);
   if (slab_rows == 0) return GRIEF_OK;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
+  BuildArgs ba;
+  if (g_gemm_mode == 1) {      // row exponents + digit planes [7][slab_rows][p_pad] straight from the tables
+    ba.mode = OUT_DIGITS; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
+  } else {
+    ba.mode = OUT_F64; ba.out = z.Phi; ba.ld = pl->p_pad;
+  }
   prof_begin(PROF_BUILD, stream);
-  int rc = launch_build(pl, T_slab, slab_rows, false, z.Phi, pl->p_pad, stream);
-  if (rc == GRIEF_OK && g_gemm_mode == 1)
-    rc = ozaki_slice(z.Phi, pl->p_pad, (int)slab_rows, pl->p_pad, z.ea, (int)slab_rows, z.pa, stream);
+  int rc = launch_build(pl, T_slab, slab_rows, ba, stream);
   prof_end(PROF_BUILD, stream);
   if (rc != GRIEF_OK) return rc;
   prof_begin(PROF_ZGEMM, stream);
