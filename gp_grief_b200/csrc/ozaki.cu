@@ -22,22 +22,19 @@
 namespace grief {
 
 constexpr int S = 7;                     // balanced 8-bit digits per operand (54 bits + sign)
-constexpr int TM = 128, TN = 256, KC = 32, STAGES = 3;
-constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // 4 KB, 8 KB
-constexpr int STAGE_BYTES = 60 * 1024;                         // largest work item: 5 A slices + 5 B slices
+constexpr int TM = 128, TN = 128, KC = 32, STAGES = 3;
+constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // 4 KB each
+constexpr int STAGE_BYTES = S * (A_SLICE + B_SLICE);           // 56 KB: all digits of both operands for one K chunk
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
-// Work items: a significance-group pair (gh, gh-1) accumulates into the two TMEM accumulators; the pair (6,5) is cut in two
-// by A-slice range so that every stage fits 60 KB and three stages fit shared memory.
-struct Item { int gh, a_lo, a_hi, b_lo, b_hi, first, last; };
-__constant__ Item kItems[5] = {
-    {6, 0, 3, 2, 6, 1, 0},   // g=6: a=0..3 (b=6..3); g=5: a=0..3 (b=5..2)            8 MMAs, 56 KB
-    {6, 4, 6, 0, 2, 0, 1},   // g=6: a=4..6 (b=2..0); g=5: a=4..5 (b=1..0)            5 MMAs, 36 KB
-    {4, 0, 4, 0, 4, 1, 1},   // g=4: 5 pairs; g=3: 4 pairs                            9 MMAs, 60 KB
-    {2, 0, 2, 0, 2, 1, 1},   // g=2: 3 pairs; g=1: 2 pairs                            5 MMAs, 36 KB
-    {0, 0, 0, 0, 0, 1, 1},   // g=0: 1 pair                                           1 MMA,  12 KB
-};
-constexpr int kNumItems = 5;
+// Work items.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b:
+//   item 0: g = 6, 5, 4, 3   all 7 + 7 digit planes, 22 MMAs per K chunk, 56 KB per stage
+//   item 1: g = 2, 1, 0      digits 0..2 of both,     6 MMAs per K chunk, 24 KB per stage
+// Two sweeps over K per tile, two drains; 80 KB of digits per 28 MMAs and chunk (the kernel is bound by L2 -> SM traffic).
+constexpr int kNumItems = 2;
+__device__ __forceinline__ int item_g_hi(int it) { return it == 0 ? 6 : 2; }
+__device__ __forceinline__ int item_g_lo(int it) { return it == 0 ? 3 : 0; }
+__device__ __forceinline__ int item_digits(int it) { return it == 0 ? 7 : 3; }
 
 __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
   for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
@@ -48,11 +45,6 @@ __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
-// K-major, SWIZZLE_32B: 8-row groups of 32-byte rows (SBO = 256 B), LBO = 1, descriptor version 1, layout type 6
-__device__ __forceinline__ uint64_t make_desc32(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
-}
-
 // ---- row scales and slicing ----
 // exps[r] = e with max_k |X[r][k]| < 2^e (0 for an all-zero row)
 __global__ void k_row_exp(const double* __restrict__ X, int64_t ld, int K, int* __restrict__ exps) {
@@ -83,8 +75,8 @@ __global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, 
 
 struct OzParams {
   double* C; int64_t ldc;
-  const int* ea; const int* eb;      // row exponents of A (>= tiles_m * 128 entries) and B (>= tiles_n * 256 entries)
-  const CUtensorMap* maps;           // [0..5]: A with box depth 0..5 slices, [6..11]: B likewise (unused entries zero)
+  const int* ea; const int* eb;      // row exponents of A and B, padded with zeros to multiples of 128
+  const CUtensorMap* maps;           // A with box depth 7, A depth 3, B depth 7, B depth 3
   int chunks;                        // 32-byte K chunks in total
   int split_chunks;                  // chunks per blockIdx.z (== chunks when K is not split)
   int64_t c_split_stride;            // split z writes C + z * c_split_stride
@@ -98,12 +90,12 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t full = base, empty = base + 32, tfull = base + 64, tfree = base + 72, slot = base + 80;
-  const uint32_t cscale = base + 1024;               // 256 doubles: 2^eb of the tile's columns
+  const uint32_t cscale = base + 1024;               // 128 doubles: 2^eb of the tile's columns
   const uint32_t stagebuf = base + 4096;             // 4 warps x 32 rows x 17 doubles (transpose staging for coalesced stores)
   const uint32_t ring = base + 4096 + 20480;         // 1024-aligned
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bn = blockIdx.x, bm = blockIdx.y;
-  if (prm.lower_only && bn * TN > bm * TM + TM - 1) return;
+  if (prm.lower_only && bn > bm) return;
   const int c_begin = (int)blockIdx.z * prm.split_chunks;
   const int nk = min(prm.split_chunks, prm.chunks - c_begin);
   double* const Cz = prm.C + (size_t)blockIdx.z * prm.c_split_stride;
@@ -141,11 +133,10 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   if (tid == 128) {                                 // ---- TMA producer (warp 4) ----
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
-      const Item w = kItems[it];
-      const int na = w.a_hi - w.a_lo + 1, nb = w.b_hi - w.b_lo + 1;
-      const uint32_t bytes = (uint32_t)(na * A_SLICE + nb * B_SLICE);
-      const CUtensorMap* mA = prm.maps + na;
-      const CUtensorMap* mB = prm.maps + 6 + nb;
+      const int nd = item_digits(it);
+      const uint32_t bytes = (uint32_t)(nd * (A_SLICE + B_SLICE));
+      const CUtensorMap* mA = prm.maps + (it == 0 ? 0 : 1);
+      const CUtensorMap* mB = prm.maps + (it == 0 ? 2 : 3);
       for (int c = 0; c < nk && ok; ++c, ++q) {
         const int s = q % STAGES;
         if (q >= STAGES) ok = wait_bounded(empty + 8 * s, (uint32_t)(((q / STAGES) - 1) & 1));
@@ -153,19 +144,19 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
         const uint32_t dst = ring + s * STAGE_BYTES, bar = full + 8 * s;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-                     "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(w.a_lo), "r"(bar) : "memory");
+                     "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(bar) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                         dst + na * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(w.b_lo), "r"(bar) : "memory");
+                         dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(0), "r"(bar) : "memory");
       }
     }
     if (!ok) atomicExch(prm.err, 1);
   } else if (tid == 160) {                          // ---- MMA issuer (warp 5) ----
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    int q = 0, drains = 0;
+    const uint64_t dhi = (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);   // K-major SWIZZLE_32B: LBO 1, SBO 256 B, v1
+    int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
-      const Item w = kItems[it];
-      const int na = w.a_hi - w.a_lo + 1;
-      if (w.first && drains > 0) ok = wait_bounded(tfree, (uint32_t)((drains - 1) & 1));   // accumulators drained
+      const int nd = item_digits(it), g_hi = item_g_hi(it), g_lo = item_g_lo(it);
+      if (it > 0) ok = wait_bounded(tfree, (uint32_t)((it - 1) & 1));     // accumulators drained
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int c = 0; c < nk && ok; ++c, ++q) {
@@ -173,27 +164,26 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
         ok = wait_bounded(full + 8 * s, (uint32_t)((q / STAGES) & 1));
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = ring + s * STAGE_BYTES, sb = sa + na * A_SLICE;
-        for (int half = 0; half < 2; ++half) {      // group gh -> columns 0..255, group gh-1 -> columns 256..511
-          const int g = w.gh - half;
-          if (g < 0) break;
-          bool fresh = (c == 0) && w.first;         // first MMA of this accumulator in this K range overwrites
-          for (int a = w.a_lo; a <= w.a_hi; ++a) {
+        const uint32_t sa = ring + s * STAGE_BYTES, sb = sa + nd * A_SLICE;
+        const uint64_t da0 = dhi | (uint64_t)((sa >> 4) & 0x3FFF), db0 = dhi | (uint64_t)((sb >> 4) & 0x3FFF);
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {            // accumulator gi <-> group g_hi - gi, TMEM columns gi*128 ..
+          const int g = g_hi - gi;
+          if (g < g_lo) break;
+          uint32_t accf = c > 0 ? 1u : 0u;
+#pragma unroll
+          for (int a = 0; a < S; ++a) {
             const int b = g - a;
-            if (b < w.b_lo || b > w.b_hi) continue;
-            const uint64_t da = make_desc32(sa + (a - w.a_lo) * A_SLICE), db = make_desc32(sb + (b - w.b_lo) * B_SLICE);
-            const uint32_t accf = fresh ? 0u : 1u;
-            fresh = false;
+            if (a >= nd || b < 0 || b >= nd) continue;
+            const uint64_t da = da0 + (uint64_t)(a * (A_SLICE >> 4)), db = db0 + (uint64_t)(b * (B_SLICE >> 4));
             asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
-                             tmem + (uint32_t)(half * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+                             tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+            accf = 1u;
           }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
       }
-      if (w.last) {
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
-        ++drains;
-      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
     }
     if (!ok) atomicExch(prm.err, 2);
   }
@@ -203,38 +193,36 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
     const int row0 = bm * TM + warp * 32;
     const double rs = ldexp(1.0, prm.ea[row0 + lane]);
     const uint32_t stg = stagebuf + (uint32_t)warp * (32 * 17 * 8);
-    int drains = 0;
     bool live = true;
     for (int it = 0; it < kNumItems && live; ++it) {
-      const Item w = kItems[it];
-      if (!w.last) continue;
-      live = wait_bounded(tfull, (uint32_t)(drains & 1));
+      live = wait_bounded(tfull, (uint32_t)(it & 1));
       if (!live) { if (lane == 0) atomicExch(prm.err, 3); break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const double w_hi = ldexp(1.0, -12 - 8 * w.gh) * rs, w_lo = (w.gh > 0) ? ldexp(1.0, -12 - 8 * (w.gh - 1)) * rs : 0.0;
-      for (int c0 = 0; c0 < TN; c0 += 16) {
-        uint32_t hi[16], lo[16];
-        const uint32_t t_hi = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, t_lo = t_hi + TN;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                     : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]),
-                       "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15])
-                     : "r"(t_hi));
-        if (w.gh > 0) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                       : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(lo[8]),
-                         "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(lo[12]), "=r"(lo[13]), "=r"(lo[14]), "=r"(lo[15])
-                       : "r"(t_lo));
-        } else {
+      const int g_hi = item_g_hi(it), ng = g_hi - item_g_lo(it) + 1;
+      double wgt[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) lo[j] = 0;
+      for (int gi = 0; gi < 4; ++gi) wgt[gi] = gi < ng ? ldexp(1.0, -12 - 8 * (g_hi - gi)) * rs : 0.0;
+      for (int c0 = 0; c0 < TN; c0 += 16) {
+        double acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {            // least significant group first
+          if (gi >= ng) break;
+          uint32_t v[16];
+          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(gi * TN + c0);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                       : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fma(wgt[gi], (double)(int)v[j], acc[j]);
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {              // own row, 16 columns -> staging [row][17]
-          const double v = w_hi * (double)(int)hi[j] + w_lo * (double)(int)lo[j];
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"(stg + (uint32_t)(lane * 17 + j) * 8), "d"(v) : "memory");
-        }
+        for (int j = 0; j < 16; ++j)                // own row, 16 columns -> staging [row][17]
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(stg + (uint32_t)(lane * 17 + j) * 8), "d"(acc[j]) : "memory");
         __syncwarp();
         // two rows per step, lanes 0-15 / 16-31 along the 16 columns: 128-byte segments; all loads before all stores
         const int j = lane & 15;
@@ -243,7 +231,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
         const int col = bn * TN + c0 + j, rbase = row0 + (lane >> 4);
         const bool col_ok = col < prm.n_valid;
         double* dst0 = Cz + (size_t)rbase * prm.ldc + col;
-        const bool keep = (drains > 0) || prm.accumulate;
+        const bool keep = (it > 0) || prm.accumulate;
         double old[16], val[16];
 #pragma unroll
         for (int h = 0; h < 16; ++h) old[h] = (keep && col_ok && rbase + 2 * h < prm.m_valid) ? __ldcg(dst0 + (size_t)(2 * h) * prm.ldc) : 0.0;
@@ -258,14 +246,12 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tfree) : "memory");
-      ++drains;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
-
 
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -328,16 +314,18 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   if (!g_oz_err) {
     GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_err), sizeof(int)));
     GRIEF_CUDA(cudaMemset(g_oz_err, 0, sizeof(int)));
-    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 12 * kMapSlots));
+    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 4 * kMapSlots));
   }
-  alignas(64) CUtensorMap hmaps[12];
+  alignas(64) CUtensorMap hmaps[4];
   memset(hmaps, 0, sizeof(hmaps));
-  for (int dpt = 1; dpt <= 5; ++dpt) {
-    int rc = make_plane_map(&hmaps[dpt], pa, M, rows_a_alloc, kp, TM, dpt);
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[6 + dpt], pb, N, rows_b_alloc, kp, TN, dpt);
+  {
+    int rc = make_plane_map(&hmaps[0], pa, M, rows_a_alloc, kp, TM, 7);
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[1], pa, M, rows_a_alloc, kp, TM, 3);
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[2], pb, N, rows_b_alloc, kp, TN, 7);
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[3], pb, N, rows_b_alloc, kp, TN, 3);
     if (rc != GRIEF_OK) return rc;
   }
-  CUtensorMap* dmaps = g_oz_maps + 12 * (g_oz_map_slot++ % kMapSlots);
+  CUtensorMap* dmaps = g_oz_maps + 4 * (g_oz_map_slot++ % kMapSlots);
   GRIEF_CUDA(cudaMemcpyAsync(dmaps, hmaps, sizeof(hmaps), cudaMemcpyHostToDevice, stream));
   OzParams prm;
   prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb; prm.maps = dmaps;
