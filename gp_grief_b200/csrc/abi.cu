@@ -149,7 +149,7 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
 }
 
 void grief_set_slab_budget(size_t bytes) { set_slab_budget(bytes); }
-void grief_set_gemm_mode(int mode) { set_gemm_mode(mode); }
+void grief_set_gemm_mode(int mode) { set_gemm_mode(mode & 1); ozaki_set_cluster((mode >> 1) & 1); }
 int grief_get_gemm_mode(void) { return gemm_mode(); }
 
 size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n) {

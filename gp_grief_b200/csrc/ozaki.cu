@@ -76,7 +76,7 @@ __global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, 
 struct OzParams {
   double* C; int64_t ldc;
   const int* ea; const int* eb;      // row exponents of A and B, padded with zeros to multiples of 128
-  const CUtensorMap* maps;           // A with box depth 7, A depth 3, B depth 7, B depth 3
+  const CUtensorMap* maps;           // A with box depth 7, A depth 3, B depth 7, B depth 3, B half rows depth 1
   int chunks;                        // 32-byte K chunks in total
   int split_chunks;                  // chunks per blockIdx.z (== chunks when K is not split)
   int64_t c_split_stride;            // split z writes C + z * c_split_stride
@@ -86,6 +86,10 @@ struct OzParams {
   int* err;
 };
 
+// CL = CTAs per cluster along M (1 or 2).  With CL = 2 the pair shares its B digits: each CTA loads half of the B rows and
+// multicasts them into both CTAs' shared memory, and every stage is released to both producers (multicast commit), which
+// cuts the L2 -> SM operand traffic of the pair by a quarter.
+template <int CL>
 __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -95,7 +99,9 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   const uint32_t ring = base + 4096 + 20480;         // 1024-aligned
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bn = blockIdx.x, bm = blockIdx.y;
-  if (prm.lower_only && bn > bm) return;
+  if (prm.lower_only && bn > (CL == 2 ? (bm | 1) : bm)) return;      // uniform over the cluster
+  uint32_t crank = 0;
+  if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int c_begin = (int)blockIdx.z * prm.split_chunks;
   const int nk = min(prm.split_chunks, prm.chunks - c_begin);
   double* const Cz = prm.C + (size_t)blockIdx.z * prm.c_split_stride;
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full + 8 * s));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty + 8 * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * s), "r"(CL));
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfull));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(tfree));
@@ -126,6 +132,10 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL == 2) {                                    // barriers of both CTAs exist before anything is signalled remotely
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
@@ -145,8 +155,18 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                      "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                         dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(0), "r"(bar) : "memory");
+        if (CL == 1) {
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                           dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(0), "r"(bar) : "memory");
+        } else {                                    // my half of the B rows, digit by digit, into both CTAs of the pair
+          const CUtensorMap* mH = prm.maps + 4;
+          for (int d = 0; d < nd; ++d)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                    dst + nd * A_SLICE + d * B_SLICE + crank * (B_SLICE / 2)),
+                "l"(mH), "r"((c_begin + c) * KC), "r"(bn * TN + (int)crank * (TN / 2)), "r"(d), "r"(bar), "h"((uint16_t)3)
+                : "memory");
+        }
       }
     }
     if (!ok) atomicExch(prm.err, 1);
@@ -181,7 +201,11 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
             accf = 1u;
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
+        if (CL == 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
+        else
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                           empty + 8 * s), "h"((uint16_t)3) : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
     }
@@ -191,7 +215,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   // ---- drains (warps 0-3): thread = tile row (TMEM lane); FP64 tile accumulated in global memory through a transpose ----
   if (warp < 4) {
     const int row0 = bm * TM + warp * 32;
-    const double rs = ldexp(1.0, prm.ea[row0 + lane]);
+    const double rs = (row0 + lane < prm.m_valid) ? ldexp(1.0, prm.ea[row0 + lane]) : 0.0;
     const uint32_t stg = stagebuf + (uint32_t)warp * (32 * 17 * 8);
     bool live = true;
     for (int it = 0; it < kNumItems && live; ++it) {
@@ -250,6 +274,10 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL == 2) {                                    // nobody leaves while the partner can still write or signal into this CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
@@ -285,6 +313,9 @@ static int make_plane_map(CUtensorMap* m, const int8_t* planes, int rows, int64_
 static int* g_oz_err = nullptr;        // device error flag shared by all launches of this process
 static CUtensorMap* g_oz_maps = nullptr;   // ring of device-resident tensor-map sets (12 maps per launch)
 static int g_oz_map_slot = 0;
+static int g_oz_cluster = 0;           // CTA pairs with multicast B digits (ozaki_set_cluster).  Measured at C3: correct, and no
+                                       // faster than single CTAs -- with the digits arriving faster the tensor cores draw more
+                                       // power and the clock drops under sw_power_cap (1721 -> 1642 MHz); kept for the next round
 constexpr int kMapSlots = 64;
 
 size_t ozaki_plane_bytes(int64_t rows, int K) { return (size_t)S * (size_t)rows * (size_t)((K + KC - 1) / KC * KC); }
@@ -314,18 +345,19 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   if (!g_oz_err) {
     GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_err), sizeof(int)));
     GRIEF_CUDA(cudaMemset(g_oz_err, 0, sizeof(int)));
-    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 4 * kMapSlots));
+    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 5 * kMapSlots));
   }
-  alignas(64) CUtensorMap hmaps[4];
+  alignas(64) CUtensorMap hmaps[5];
   memset(hmaps, 0, sizeof(hmaps));
   {
     int rc = make_plane_map(&hmaps[0], pa, M, rows_a_alloc, kp, TM, 7);
     if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[1], pa, M, rows_a_alloc, kp, TM, 3);
     if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[2], pb, N, rows_b_alloc, kp, TN, 7);
     if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[3], pb, N, rows_b_alloc, kp, TN, 3);
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[4], pb, N, rows_b_alloc, kp, TN / 2, 1);      // half of the B rows, one digit (cluster path)
     if (rc != GRIEF_OK) return rc;
   }
-  CUtensorMap* dmaps = g_oz_maps + 4 * (g_oz_map_slot++ % kMapSlots);
+  CUtensorMap* dmaps = g_oz_maps + 5 * (g_oz_map_slot++ % kMapSlots);
   GRIEF_CUDA(cudaMemcpyAsync(dmaps, hmaps, sizeof(hmaps), cudaMemcpyHostToDevice, stream));
   OzParams prm;
   prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb; prm.maps = dmaps;
@@ -334,15 +366,30 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   const size_t smem = 1024 + 4096 + 20480 + 1024 + (size_t)STAGES * STAGE_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
-  k_ozaki<<<grid, 192, smem, stream>>>(prm);
+  const int tiles_m = (M + TM - 1) / TM;
+  if (g_oz_cluster && tiles_m >= 2) {               // CTA pairs along M; an odd last pair runs one CTA on zero rows
+    dim3 grid((N + TN - 1) / TN, (tiles_m + 1) / 2 * 2, splits);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GRIEF_CUDA(cudaLaunchKernelEx(&cfg, k_ozaki<2>, prm));
+  } else {
+    dim3 grid((N + TN - 1) / TN, tiles_m, splits);
+    k_ozaki<1><<<grid, 192, smem, stream>>>(prm);
+  }
   GRIEF_CUDA(cudaGetLastError());
   if (launches) *launches += 1;
   return GRIEF_OK;
 }
+
+void ozaki_set_cluster(int on) { g_oz_cluster = on ? 1 : 0; }
 
 // Synchronises the stream and reports a pipeline failure inside any k_ozaki launch since the last check.
 int ozaki_check(cudaStream_t stream) {

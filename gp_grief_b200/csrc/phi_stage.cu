@@ -22,19 +22,25 @@ namespace grief {
 constexpr int kBuildRows = 128;       // table rows per builder CTA
 constexpr int kBuildThreads = 512;
 
-// table rows [rb*128, rb*128+128) -> shared memory (bulk async copy in 16-row pieces), one barrier
-__device__ __forceinline__ void stage_table_rows(double* sT, uint64_t* bar, const double* T, int stride, int64_t rb) {
+// table rows [rb*128, rb*128+128) -> shared memory (bulk async copy in 16-row pieces); `use` = how often this CTA has
+// staged rows before (barrier parity).  The barrier is initialised by the caller (init_stage_barrier).
+__device__ __forceinline__ void init_stage_barrier(uint64_t* bar) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void stage_table_rows(double* sT, uint64_t* bar, const double* T, int stride, int64_t rb, int use) {
+  __syncthreads();                                   // everybody is done with the previous rows
+  if (threadIdx.x == 0) {
     const uint32_t piece = (uint32_t)(16 * stride * sizeof(double));
     fence_proxy_async();
     mbar_arrive_expect_tx(bar, piece * (kBuildRows / 16));
     for (int i = 0; i < kBuildRows / 16; ++i)
       bulk_g2s(sT + (size_t)i * 16 * stride, T + ((size_t)rb * kBuildRows + i * 16) * stride, piece, bar);
   }
-  __syncthreads();
-  mbar_wait(bar, 0);
+  mbar_wait(bar, (uint32_t)(use & 1));
 }
 
 // What a builder launch produces: the FP64 slab (DMMA path), or -- for the INT8 path, which never stores the FP64 slab --
@@ -66,57 +72,69 @@ __device__ __forceinline__ void store_digits(double v, double scale, int8_t* __r
 template <int G, int MODE>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __restrict__ T, int stride,
                                                                const uint16_t* __restrict__ sorted_slot,
-                                                               const uint8_t* __restrict__ sorted_level, int p_pad,
+                                                               const uint8_t* __restrict__ sorted_level, int p_pad, int n_blocks,
                                                                double* __restrict__ out, int64_t ld, int* __restrict__ col_hi,
                                                                const int* __restrict__ exps, int8_t* __restrict__ planes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
-  stage_table_rows(sT, bar, T, stride, blockIdx.x);
+  int* s_hi = reinterpret_cast<int*>(smem_raw + 128 + (size_t)kBuildRows * stride * sizeof(double));   // OUT_EXP: p_pad column maxima
+  if constexpr (MODE == OUT_EXP)
+    for (int c = threadIdx.x; c < p_pad; c += kBuildThreads) s_hi[c] = 0;
+  init_stage_barrier(bar);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = (warp & 3) * 32 + lane;
   const double* trow = sT + (size_t)row * stride;
   const int cpq = p_pad / 4;                           // four warps share a row group, a quarter of the columns each
   const int c_begin = (warp >> 2) * cpq;
-  const size_t grow = (size_t)blockIdx.x * kBuildRows + row;
   constexpr int NB = 8;
-  double P = 1.0;
-  for (int c0 = c_begin; c0 < c_begin + cpq; c0 += NB) {
-    double last[NB];
-    int lv[NB];
+  int use = 0;
+  for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x, ++use) {   // persistent over 128-row blocks
+    stage_table_rows(sT, bar, T, stride, rb, use);
+    const size_t grow = (size_t)rb * kBuildRows + row;
+    double P = 1.0;
+    for (int c0 = c_begin; c0 < c_begin + cpq; c0 += NB) {
+      double last[NB];
+      int lv[NB];
 #pragma unroll
-    for (int e = 0; e < NB; ++e) {
-      lv[e] = (c0 + e == c_begin) ? 0 : (int)__ldg(sorted_level + c0 + e);
-      last[e] = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + (G - 1))];
-    }
+      for (int e = 0; e < NB; ++e) {
+        lv[e] = (c0 + e == c_begin) ? 0 : (int)__ldg(sorted_level + c0 + e);
+        last[e] = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + (G - 1))];
+      }
 #pragma unroll
-    for (int e = 0; e < NB; ++e) {
-      if constexpr (G > 1) {
-        if (lv[e] < G - 1) {
-          double q = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G)];
+      for (int e = 0; e < NB; ++e) {
+        if constexpr (G > 1) {
+          if (lv[e] < G - 1) {
+            double q = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G)];
 #pragma unroll
-          for (int g = 1; g < G - 1; ++g) q *= trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + g)];
-          P = q;
+            for (int g = 1; g < G - 1; ++g) q *= trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + g)];
+            P = q;
+          }
+          last[e] *= P;
         }
-        last[e] *= P;
+      }
+      if constexpr (MODE == OUT_F64) {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) out[(size_t)(c0 + e) * ld + grow] = last[e];
+      } else if constexpr (MODE == OUT_EXP) {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+          const int m = __reduce_max_sync(0xffffffffu, abs_hi(last[e]));
+          if (lane == 0 && m > s_hi[c0 + e]) atomicMax(s_hi + c0 + e, m);     // shared-memory maximum over this CTA's rows
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) {
+          const double scale = __hiloint2double((1023 + 54 - __ldg(exps + c0 + e)) << 20, 0);
+          store_digits(last[e], scale, planes + (size_t)(c0 + e) * ld + grow, (size_t)p_pad * ld);
+        }
       }
     }
-    if constexpr (MODE == OUT_F64) {
-#pragma unroll
-      for (int e = 0; e < NB; ++e) out[(size_t)(c0 + e) * ld + grow] = last[e];
-    } else if constexpr (MODE == OUT_EXP) {
-#pragma unroll
-      for (int e = 0; e < NB; ++e) {
-        const int m = __reduce_max_sync(0xffffffffu, abs_hi(last[e]));
-        if (lane == 0 && m > 0) atomicMax(col_hi + c0 + e, m);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < NB; ++e) {
-        const double scale = __hiloint2double((1023 + 54 - __ldg(exps + c0 + e)) << 20, 0);
-        store_digits(last[e], scale, planes + (size_t)(c0 + e) * ld + grow, (size_t)p_pad * ld);
-      }
-    }
+  }
+  if constexpr (MODE == OUT_EXP) {                     // one global maximum per column and CTA
+    __syncthreads();
+    for (int c = threadIdx.x; c < p_pad; c += kBuildThreads)
+      if (s_hi[c] > 0) atomicMax(col_hi + c, s_hi[c]);
   }
 }
 
@@ -139,7 +157,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
-  stage_table_rows(sT, bar, T, stride, blockIdx.x);
+  init_stage_barrier(bar);
+  stage_table_rows(sT, bar, T, stride, blockIdx.x, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int RW = kBuildRows / (kBuildThreads / 32);   // 8 rows per warp
   const double* tbase = sT + (size_t)warp * RW * stride;
@@ -200,16 +219,21 @@ struct BuildArgs {
 
 template <int G>
 static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
-  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
-  const unsigned grid = (unsigned)(rows / kBuildRows);
+  const size_t smem_rows = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
+  const int n_blocks = (int)(rows / kBuildRows);
+  const unsigned grid = (unsigned)n_blocks;
 #define GRIEF_BT(MODE_)                                                                                                             \
   do {                                                                                                                              \
+    const size_t smem = smem_rows + (MODE_ == OUT_EXP ? (size_t)pl->p_pad * sizeof(int) : 0);                                       \
+    const unsigned g = MODE_ == OUT_EXP ? std::min<unsigned>(grid, 148u * 2u) : grid;                                                \
+    GRIEF_REQUIRE(smem <= 227 * 1024, "build_phi_t: %zu bytes of shared memory", smem);                                             \
     GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    k_build_phi_t<G, MODE_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad, \
-                                                                  a.out, a.ld, a.col_hi, a.exps, a.planes);                         \
+    k_build_phi_t<G, MODE_><<<g, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad,    \
+                                                               n_blocks, a.out, a.ld, a.col_hi, a.exps, a.planes);                  \
   } while (0)
 #define GRIEF_BN(MODE_)                                                                                                             \
   do {                                                                                                                              \
+    const size_t smem = smem_rows;                                                                                                  \
     GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
     k_build_phi<G, MODE_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, a.out, a.ld, a.exps,  \
                                                                 a.planes, a.plane_stride);                                          \

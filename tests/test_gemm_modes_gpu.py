@@ -10,7 +10,7 @@ import test_api_gpu as ta
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["int8", "fp64"])
+@pytest.fixture(params=[1, 0, 3], ids=["int8", "fp64", "int8-cluster"])
 def int8_mode(request):
     before = nat.lib().grief_get_gemm_mode()
     nat.lib().grief_set_gemm_mode(request.param)
@@ -38,7 +38,7 @@ def test_lml_and_adjoint_gradient_int8(int8_mode, name):
 
 @pytest.mark.gpu
 def test_larger_shapes_int8(int8_mode):
-    assert nat.lib().grief_get_gemm_mode() == int8_mode
+    assert nat.lib().grief_get_gemm_mode() == (int8_mode & 1)
     tn.test_gram_larger_random_shape_vs_materialised_phi()
     tn.test_gram_and_quadform_over_several_slabs()
 
