@@ -52,15 +52,19 @@ constexpr int kDigits = 7;
 __device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
 // frexp exponent e (|x| < 2^e) from the high word of the row maximum (0 for an all-zero row)
 __device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? max((hi >> 20) - 1022, -900) : 0; }   // clamp: 2^(54-e) stays finite
-// digits d_s of trunc(v * scale), scale = 2^(54 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s)
+// digits d_s of q = trunc(v * scale), scale = 2^(54 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s), d_s in [-128, 127].
+// Balanced base-256 digits without a carry chain: add 128 to every byte position (q + 0x80..80 is positive and below 2^56),
+// then byte k of the sum, minus 128 (= XOR 0x80 read as int8), is the digit of 256^k.
 __device__ __forceinline__ void store_digits(double v, double scale, int8_t* __restrict__ base, size_t plane_stride) {
-  long long q = __double2ll_rz(v * scale);
-#pragma unroll
-  for (int s = kDigits - 1; s >= 0; --s) {
-    const int d = (int)(int8_t)(q & 0xFF);
-    base[(size_t)s * plane_stride] = (int8_t)d;
-    q = (q - d) >> 8;
-  }
+  const unsigned long long w = ((unsigned long long)__double2ll_rz(v * scale) + 0x0080808080808080ull) ^ 0x0080808080808080ull;
+  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  base[0 * plane_stride] = (int8_t)(hi >> 16);       // digit 0 = byte 6 (most significant)
+  base[1 * plane_stride] = (int8_t)(hi >> 8);
+  base[2 * plane_stride] = (int8_t)hi;
+  base[3 * plane_stride] = (int8_t)(lo >> 24);
+  base[4 * plane_stride] = (int8_t)(lo >> 16);
+  base[5 * plane_stride] = (int8_t)(lo >> 8);
+  base[6 * plane_stride] = (int8_t)lo;
 }
 
 // Phi^T slab, c = sorted column.  Lane = data row; a warp walks a run of consecutive sorted columns, which share their
