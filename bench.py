@@ -308,7 +308,7 @@ def run_ours(args):
     # work actually issued by the GEMM launches (padded rows / columns, full diagonal tiles)
     flops = {"k_zgemm": 2.0 * rows128 * p_pad * p_pad, "k_gram": float(rows128) * p_pad * (p_pad + 128)}
     gk = "k_ozaki" if args.gemm == "int8" else "k_gemm_nt"
-    sl = " + k_row_exp + k_slice" if args.gemm == "int8" else ""
+    sl = " (exponents + int8 digit planes)" if args.gemm == "int8" else ""
     label = {"k_zgemm": gk + " [Z = Phi*G2, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
              "k_build_phi": "k_build_phi%s [Phi slab, pass 2]" % sl, "k_build_phi_t": "k_build_phi_t%s [Phi^T slab, pass 1]" % sl,
              "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)"}

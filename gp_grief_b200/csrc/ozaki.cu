@@ -5,12 +5,17 @@
 //   x 2^-e = sum_s d_s 2^(-6 - 8 s),   A B^T = sum_{a,b} 2^(-12 - 8 (a + b)) D_a(A) D_b(B)^T,   pairs with a + b <= 6 kept (28 of 49;
 //   what is dropped is below 2^-54 of the row-scale product).  Each digit product is an exact int8 x int8 -> int32 GEMM; one
 //   accumulation covers at most 16384 values of K (7 pairs x 2^14 x 2^14 < 2^31), longer K is split over blockIdx.z.
-// Kernel: one CTA per 128 x 256 tile.  Work items = significance-group pairs (g, g-1) accumulated in the two TMEM
-// accumulators (2 x 256 columns x 128 lanes, int32); all digit planes an item needs for one 32-byte K chunk sit in
-// shared memory (3-D TMA boxes, SWIZZLE_32B, three 60 KB stages); warp 4 = TMA producer, warp 5 = MMA issuer (one
-// thread), warps 0-3 drain TMEM after each group pair: int32 -> f64, scaled, transposed through shared memory, added to C.
-// Measured (tools/microbench/ozaki_gemm.cu, B200): 77 TFLOP/s FP64-equivalent at 37888 x 4096 x 4096 against 35 for cuBLAS
-// DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
+// Kernel: one CTA per 128 x 128 tile.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b;
+// two sweeps over K (g = 6..3 with all 7 + 7 digit planes, then g = 2..0 with digits 0..2), each followed by a drain.  All digit
+// planes a sweep needs for one 32-byte K chunk sit in shared memory (3-D TMA boxes over [digit][row][32 B], SWIZZLE_32B, three
+// 56 KB stages); warp 4 = TMA producer, warp 5 = MMA issuer (one thread, tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32),
+// warps 0-3 drain TMEM: tcgen05.ld -> f64 -> sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared memory
+// -> added to C.  k_ozaki<2> is the same kernel for CTA pairs that multicast their halves of the B digits to each other.
+// Measured (B200, pass-2 shape 37888 x 4096 x 4096): 14.4 ms = 88 TFLOP/s FP64-equivalent alone, 81 inside the benchmark (power
+// cap), against 35 for cuBLAS DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
+// Variants measured and not adopted (profiles/r01_gram_design_notes.md): 128 x 256 tiles with two accumulators and five work
+// items (16.7 ms), CTA pairs with multicast B (same time, lower clock), 64-byte K stages for the light sweep (slower),
+// cta_group::2 MMAs on 256 x 256 tiles (tools/microbench/ozaki_gemm_2cta.cu, 15.4 ms).
 // Every barrier wait is bounded: a protocol failure raises an error flag (checked by the callers) instead of hanging the GPU.
 #include <cuda.h>
 

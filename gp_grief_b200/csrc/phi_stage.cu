@@ -6,11 +6,14 @@
 //   pass 2 / predictive var.    Z = Phi B     :  Phi slab (R x p_pad, sorted columns contiguous)
 //                                               -> GEMM against the column-permuted symmetric B
 //
+// Two arithmetic modes (grief_set_gemm_mode): 1 (default) -- the builders emit power-of-two row scales and seven int8 digit planes
+// and k_ozaki (ozaki.cu) multiplies them on the tcgen05 INT8 tensor cores; 0 -- the builders emit the FP64 slab for k_gemm_nt.
+//
 // Why staged and not fused (round-1 measurements, profiles/r01_gram_design_notes.md): DMUL, DFMA and DMMA share ONE FP64
 // pipe per SM sub-partition.  With the Phi tiles built inside the GEMM CTAs the builder's DMULs queue behind the DMMAs
 // (32 % of warp samples in stall_math) and the kernels stop at 25-28 TFLOP/s; the same DMMA loop fed by TMA alone runs at
-// 33 TFLOP/s.  The slab costs 8 B written + 8 B read per element of Phi, 1-2 % of the GEMM time at HBM speed, and
-// HBM is otherwise idle during these passes.
+// 36 TFLOP/s.  The slab costs 7-8 B written + read per element of Phi, a few % of the GEMM time, on an HBM that is otherwise
+// idle during these passes.
 #include <cuda.h>
 
 #include <algorithm>

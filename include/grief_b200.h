@@ -145,7 +145,8 @@ void grief_set_gemm_mode(int mode);
 int grief_get_gemm_mode(void);
 
 /*
- * Fused Gram:  A = Phi^T Phi without materialising Phi (models/gp_grief_model.py:148-149).
+ * Gram matrix A = Phi^T Phi (models/gp_grief_model.py:148-149).  Phi is never held whole: one slab of rows at a time is staged in
+ * the workspace (as int8 digit planes in arithmetic mode 1, as FP64 in mode 0) and consumed by the library's GEMM.
  *   A_dev       out, (p, lda) row-major, full symmetric matrix
  *   workspace   device scratch of at least grief_gram_workspace_bytes(plan, n) bytes
  */
