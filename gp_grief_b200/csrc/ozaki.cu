@@ -52,15 +52,23 @@ __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
 }
 // ---- row scales and slicing ----
 // exps[r] = e with max_k |X[r][k]| < 2^e (0 for an all-zero row)
-__global__ void k_row_exp(const double* __restrict__ X, int64_t ld, int K, int* __restrict__ exps) {
+__global__ void k_row_exp(const double* __restrict__ X, int64_t ld, int K, int* __restrict__ exps, int* __restrict__ err) {
   const int r = blockIdx.x;
   double m = 0.0;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmax(m, fabs(X[(size_t)r * ld + k]));
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const double a = fabs(X[(size_t)r * ld + k]);
+    m = (a != a) ? 1.0 / 0.0 : fmax(m, a);            // NaN counts as non-finite
+  }
   __shared__ double sm[256];
   sm[threadIdx.x] = m;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]); __syncthreads(); }
-  if (threadIdx.x == 0) { int e = 0; if (sm[0] > 0.0) frexp(sm[0], &e); exps[r] = e; }
+  if (threadIdx.x == 0) {
+    int e = 0;
+    if (sm[0] > 0.0) frexp(sm[0], &e);
+    if (!(sm[0] <= 1.7976931348623157e308)) { e = 0; atomicExch(err, 4); }     // Inf or NaN (fmax drops NaN: checked below too)
+    exps[r] = e;
+  }
 }
 // planes[s][r][k] = balanced digit s of trunc(X[r][k] * 2^(54 - exps[r])):  x 2^-e = sum_s d_s 2^(-6 - 8 s)
 __global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, int kp, const int* __restrict__ exps,
@@ -323,6 +331,15 @@ static int g_oz_cluster = 0;           // CTA pairs with multicast B digits (oza
                                        // power and the clock drops under sw_power_cap (1721 -> 1642 MHz); kept for the next round
 constexpr int kMapSlots = 64;
 
+// Device flag raised by the kernels of the INT8 path: 1-3 = a barrier wait of k_ozaki timed out, 4 = a non-finite operand value.
+int* ozaki_err_flag() {
+  if (!g_oz_err) {
+    if (cudaMalloc(reinterpret_cast<void**>(&g_oz_err), sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_oz_err, 0, sizeof(int));
+  }
+  return g_oz_err;
+}
+
 size_t ozaki_plane_bytes(int64_t rows, int K) { return (size_t)S * (size_t)rows * (size_t)((K + KC - 1) / KC * KC); }
 
 // exps[r] (r < rows; entries up to exps_len are zeroed) and digit planes of X (rows x K, ld); planes: [S][rows][kp], kp = K rounded up to 32
@@ -330,7 +347,7 @@ int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exp
   if (rows == 0) return GRIEF_OK;
   const int kp = (K + KC - 1) / KC * KC;
   if (exps_len > rows) GRIEF_CUDA(cudaMemsetAsync(exps + rows, 0, (size_t)(exps_len - rows) * sizeof(int), stream));
-  k_row_exp<<<rows, 256, 0, stream>>>(X, ld, K, exps);
+  k_row_exp<<<rows, 256, 0, stream>>>(X, ld, K, exps, ozaki_err_flag());
   k_slice<<<148 * 8, 256, 0, stream>>>(X, ld, rows, K, kp, exps, planes);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
@@ -347,11 +364,8 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   splits = std::max(1, splits);
   const int split_chunks = (chunks + splits - 1) / splits;
   GRIEF_REQUIRE(split_chunks * KC <= 16384, "ozaki_gemm: %d values of K per accumulation exceed the int32 budget of 16384", split_chunks * KC);
-  if (!g_oz_err) {
-    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_err), sizeof(int)));
-    GRIEF_CUDA(cudaMemset(g_oz_err, 0, sizeof(int)));
-    GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 5 * kMapSlots));
-  }
+  if (ozaki_err_flag() == nullptr) return fail(GRIEF_ERR_CUDA, "ozaki_gemm: cudaMalloc of the error flag failed");
+  if (!g_oz_maps) GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 5 * kMapSlots));
   alignas(64) CUtensorMap hmaps[5];
   memset(hmaps, 0, sizeof(hmaps));
   {
@@ -404,6 +418,7 @@ int ozaki_check(cudaStream_t stream) {
   GRIEF_CUDA(cudaStreamSynchronize(stream));
   if (flag != 0) {
     cudaMemsetAsync(g_oz_err, 0, sizeof(int), stream);
+    if (flag == 4) return fail(GRIEF_ERR_BAD_ARG, "non-finite value (NaN / Inf) in the basis matrix Phi or in the p x p operand");
     return fail(GRIEF_ERR_CUDA, "k_ozaki: barrier wait timed out in role %d (1 = TMA producer, 2 = MMA issuer, 3 = drain)", flag);
   }
   return GRIEF_OK;

@@ -54,7 +54,7 @@ constexpr int kDigits = 7;
 // high word of |v|: orders like |v|, and its exponent field is all the INT8 path needs of a row maximum
 __device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
 // frexp exponent e (|x| < 2^e) from the high word of the row maximum (0 for an all-zero row)
-__device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? max((hi >> 20) - 1022, -900) : 0; }   // clamp: 2^(54-e) stays finite
+__device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? min(max((hi >> 20) - 1022, -900), 1024) : 0; }   // clamp: 2^(54-e) stays finite
 // digits d_s of q = trunc(v * scale), scale = 2^(54 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s), d_s in [-128, 127].
 // Balanced base-256 digits without a carry chain: add 128 to every byte position (q + 0x80..80 is positive and below 2^56),
 // then byte k of the sum, minus 128 (= XOR 0x80 read as int8), is the digit of 256^k.
@@ -146,9 +146,13 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
 }
 
 // exps[c] from the accumulated high words (and reset them for the next slab)
-__global__ void k_exps_from_hi(int* __restrict__ hi, int n, int n_pad, int* __restrict__ exps) {
+__global__ void k_exps_from_hi(int* __restrict__ hi, int n, int n_pad, int* __restrict__ exps, int* __restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { exps[i] = exp_from_hi(hi[i]); hi[i] = 0; }
+  if (i < n) {
+    if (hi[i] >= 0x7ff00000) atomicExch(err, 4);      // Inf / NaN in the column
+    exps[i] = exp_from_hi(hi[i]);
+    hi[i] = 0;
+  }
   else if (i < n_pad) exps[i] = 0;
 }
 
@@ -160,7 +164,7 @@ template <int G, int MODE>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __restrict__ T, int stride,
                                                              const uint16_t* __restrict__ sorted_slot, int p_pad,
                                                              double* __restrict__ out, int64_t ldo, int* __restrict__ exps,
-                                                             int8_t* __restrict__ planes, size_t plane_stride) {
+                                                             int8_t* __restrict__ planes, size_t plane_stride, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
@@ -189,8 +193,12 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
     }
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
-      const int e = exp_from_hi(__reduce_max_sync(0xffffffffu, hi[r]));
-      if (lane == 0) exps[row0 + r] = e;
+      const int mh = __reduce_max_sync(0xffffffffu, hi[r]);
+      const int e = exp_from_hi(mh);
+      if (lane == 0) {
+        exps[row0 + r] = e;
+        if (mh >= 0x7ff00000) atomicExch(err, 4);   // Inf / NaN in the row
+      }
       scale[r] = __hiloint2double((1023 + 54 - e) << 20, 0);
     }
   }
@@ -243,7 +251,7 @@ static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const B
     const size_t smem = smem_rows;                                                                                                  \
     GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
     k_build_phi<G, MODE_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, a.out, a.ld, a.exps,  \
-                                                                a.planes, a.plane_stride);                                          \
+                                                                a.planes, a.plane_stride, ozaki_err_flag());                        \
   } while (0)
   if (a.transposed) {
     if (a.mode == OUT_F64) GRIEF_BT(OUT_F64);
@@ -376,7 +384,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
       rc = launch_build(pl, Ts, R, ba, stream);
       if (rc == GRIEF_OK) {
         const int n_e = (int)gram_exps_len(pl);
-        k_exps_from_hi<<<(n_e + 255) / 256, 256, 0, stream>>>(col_hi, pp, n_e, exps);
+        k_exps_from_hi<<<(n_e + 255) / 256, 256, 0, stream>>>(col_hi, pp, n_e, exps, ozaki_err_flag());
         ba.mode = OUT_DIGITS; ba.exps = exps; ba.planes = planes; ba.ld = R;
         rc = launch_build(pl, Ts, R, ba, stream);
       }

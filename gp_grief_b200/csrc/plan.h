@@ -89,6 +89,7 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
                int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, cudaStream_t stream,
                int* launches);
 int ozaki_check(cudaStream_t stream);
+int* ozaki_err_flag();               // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value
 void ozaki_set_cluster(int on);     // 1: 2-CTA clusters along M with TMA-multicast B digits (experimental, off by default)
 // 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki) for the two O(n p^2) products
 int gemm_mode();

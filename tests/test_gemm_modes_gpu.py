@@ -54,3 +54,26 @@ def test_models_int8(int8_mode):
     ta.test_reference_test_gp_grief_model()
     ta.test_checkgrad_and_optimize_type2()
     ta.test_grief_to_web_model_shares_statistics()
+
+
+@pytest.mark.gpu
+def test_non_finite_inputs_are_reported_not_swallowed():
+    """INT8 mode cuts operands into integer digits: a NaN must surface as an error, not silently become zero."""
+    import numpy as np
+    import torch
+    from gp_grief_b200 import device
+    rng = np.random.default_rng(3)
+    d, m, p, n = 3, 5, 40, 600
+    xg = [np.linspace(0, 1, m) for _ in range(d)]
+    basis = tn.orc.setup_inducing_cov(["RBF"] * d, [1.0] * d, [0.4] * d, xg, p)
+    plan = tn._plan_from_basis(dict(d=d, names=["RBF"] * d, variances=[1.0] * d, lengthscales=[0.4] * d, xg=xg), basis)
+    X = rng.random((n, d))
+    X[17, 1] = np.nan
+    T = plan.build_tables(torch.from_numpy(X).cuda())
+    assert nat.lib().grief_get_gemm_mode() == 1
+    with pytest.raises(ValueError, match="non-finite"):
+        plan.gram(T, n)
+    X[17, 1] = 0.5                                   # the flag is cleared: the next call works
+    T = plan.build_tables(torch.from_numpy(X).cuda())
+    A = plan.gram(T, n).cpu().numpy()
+    assert np.all(np.isfinite(A))
