@@ -226,10 +226,28 @@ def run_ours(args):
                                    reweight_eig_funs=False, opt_kernel_params=True)
         return gp.models.GPGriefModel(x_pin.numpy(), y_pin.numpy(), kern, noise_var=0.1, distributed=distributed)
 
-    nat.lib().grief_set_gemm_mode(1 if args.gemm == "int8" else 0)
     peak_burst = peak_sust = None
+    arith = None
     if rank == 0:
         peak_burst, peak_sust = fp64_peak(torch)
+        # same workload on a row sample in BOTH arithmetic modes (outside the timed region): the INT8 tensor-core path must reproduce
+        # the FP64 DMMA path -- evidence inside the bench line that the timed arithmetic is double-precision class
+        ns = min(n_local, 200000)
+        res = {}
+        for mode in (0, 1):
+            nat.lib().grief_set_gemm_mode(mode)
+            kern = gp.kern.GriefKernel([gp.kern.RBF(1, variance=1.0, lengthscale=l) for l in step_lengthscales(d, 0)], grid, n_eigs=p,
+                                       reweight_eig_funs=False, opt_kernel_params=True)
+            ms_ = gp.models.GPGriefModel(x_pin.numpy()[:ns], y_pin.numpy()[:ns], kern, noise_var=0.1)
+            l_, g_ = ms_.log_likelihood(return_gradient=True)
+            res[mode] = (float(np.asarray(l_).squeeze()), np.asarray(g_, dtype=float).copy())
+            del ms_, kern
+        torch.cuda.empty_cache()
+        ok_ = ~np.isnan(res[0][1])
+        arith = {"rows": ns, "lml_fp64_dmma": res[0][0], "lml_int8_tensor": res[1][0],
+                 "lml_rel_diff": abs(res[1][0] - res[0][0]) / abs(res[0][0]),
+                 "grad_max_abs_diff_over_max_abs": float(np.abs(res[1][1][ok_] - res[0][1][ok_]).max() / np.abs(res[0][1][ok_]).max())}
+    nat.lib().grief_set_gemm_mode(1 if args.gemm == "int8" else 0)
 
     # ---- device-resident leg: one model, data stays in HBM, new hyper-parameters every step ----
     model = make_model(0)
@@ -365,7 +383,7 @@ def run_ours(args):
                                                                "theta-gradient" % world,
                        "l2": "inputs (X %.1f GB, tables %.1f GB per GPU) exceed the 126 MB L2" % (n_local * d * 8e-9, rows128 * 105 * 8e-9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "check": {"lml": lml_val, "grad_finite": bool(np.all(np.isfinite(grad[~np.isnan(grad)])))},
+            "check": {"lml": lml_val, "grad_finite": bool(np.all(np.isfinite(grad[~np.isnan(grad)]))), "int8_vs_fp64_on_sample": arith},
             "tflops_whole_eval": 3.0 * n_total * p * p * value * 1e-12}
     print(json.dumps(line))
     if distributed:
