@@ -185,6 +185,24 @@ def gemm_nt(A, B, alpha=1.0, beta=0.0, out=None):
     return out
 
 
+def kron_matvec(factors, x):
+    """(K_1 kron ... kron K_d) x on the device: one GEMM per factor (reference tensors/kron_matrix.py:52-97, host loop there).
+
+    factors: list of 2-D NumPy arrays, x: (N,) or (N, 1) NumPy array.  Returns a NumPy column vector.
+    The running vector is kept as a (rest, cols_i) row-major matrix Yc (the memory image of the reference's F-ordered
+    reshape), factor i is applied as Yc @ K_i^T through grief_gemm_nt, and the result is transposed for the next factor.
+    """
+    torch = _torch()
+    y = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))).cuda()
+    for Ki in reversed(list(factors)):
+        Kd = torch.as_tensor(np.ascontiguousarray(Ki, dtype=np.float64)).cuda()
+        rows_i, cols_i = Kd.shape
+        Yc = y.view(-1, cols_i)
+        out = gemm_nt(Yc, Kd)                      # (rest, rows_i) = Yc @ K_i^T
+        y = out.t().contiguous().view(-1)
+    return y.cpu().numpy().reshape((-1, 1))
+
+
 def _even_ld(B):
     """TMA needs 16-byte aligned rows: unit column stride, even row stride, aligned base -- else a padded copy (small operands)."""
     if B.stride(1) == 1 and B.stride(0) % 2 == 0 and B.data_ptr() % 16 == 0 and B.stride(0) >= B.shape[1]:

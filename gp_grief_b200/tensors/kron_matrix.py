@@ -55,10 +55,14 @@ class KronMatrix(object):
         raise AttributeError("Attribute is Read only.")
 
     # ---------------------------------------------------------------- products
-    def kronvec_prod(self, x):
-        """K x for a column vector x (M,1) -> (N,1)."""
+    def kronvec_prod(self, x, device=False):
+        """K x for a column vector x (M,1) -> (N,1).  device=True runs the per-factor products on the GPU (dense factors only)."""
         if x.shape != (self.shape[1], 1):
             raise ValueError('x is the wrong shape, must be (%d,1), not %s' % (self.shape[1], repr(x.shape)))
+        if device:
+            assert all(isinstance(Ki, np.ndarray) and Ki.ndim == 2 for Ki in self.K), "device mat-vec needs dense 2-D factors"
+            from ..device import kron_matvec
+            return kron_matvec(list(self.K), x)
 
         def apply(i, Y):
             Ki = self.K[i]
