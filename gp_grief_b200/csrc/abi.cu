@@ -34,6 +34,7 @@ int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t
 int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream);
 int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream);
 int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream);
+int launch_permute_vec(const Plan* pl, const double* in, double scale, double* out, cudaStream_t stream);
 size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows);
 int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream);
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
@@ -210,8 +211,8 @@ size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   const int64_t slab = slab_rows_for(n, sms);
   return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) +
          align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
-         align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p * sizeof(double)) +
-         align256((size_t)pl->p * pl->p_pad * sizeof(double));
+         align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p_pad * sizeof(double)) +
+         align256((size_t)pl->p_pad * pl->p_pad * sizeof(double));
 }
 
 int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev, int64_t n,
@@ -231,11 +232,11 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   void* zscr = q; q += align256(zgemm_scratch_bytes(pl, slab));
   double* DT = reinterpret_cast<double*>(q); q += align256((size_t)slab * std::max(1, dtw) * sizeof(double));
   double* partial = reinterpret_cast<double*>(q); q += align256((size_t)contract_blocks(sms) * std::max(1, na) * sizeof(double));
-  double* gvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p * sizeof(double));
+  double* gvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p_pad * sizeof(double));
   double* Bperm = reinterpret_cast<double*>(q);
   if (na == 0) return GRIEF_OK;
   GRIEF_CUDA(cudaMemsetAsync(partial, 0, (size_t)contract_blocks(sms) * na * sizeof(double), stream));
-  int rc = launch_scale_vec(b_dev, 1.0 / noise_var, pl->p, gvec, stream);
+  int rc = launch_permute_vec(pl, b_dev, 1.0 / noise_var, gvec, stream);      // g = b / sigma^2 in sorted column order
   if (rc != GRIEF_OK) return rc;
   rc = launch_permute_b(pl, G2_dev, ldg, Bperm, stream);
   if (rc == GRIEF_OK) rc = launch_zgemm_prepare(pl, Bperm, slab, zscr, stream);
@@ -262,7 +263,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
 size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
   const int64_t slab = slab_rows_for(n, sm_count());
-  return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) + align256((size_t)pl->p * pl->p_pad * sizeof(double));
+  return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) + align256((size_t)pl->p_pad * pl->p_pad * sizeof(double));
 }
 
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb, double* q_dev,

@@ -4,7 +4,8 @@
 //   dLML/dtheta = sum_n sum_j Zt[n,j] * dPhi[n,j]/dtheta,    Zt = Phi * G2 + y g^T,
 //   G2 = -(P^-1 + b b^T/sigma^2),  g = b/sigma^2                                
 //
-// Z = Phi*G2 comes from launch_zgemm (phi_stage.cu: Phi slab builder + k_gemm_nt), one slab of rows at a time.  For a parameter theta of
+// Z = Phi*G2 comes from launch_zgemm (phi_stage.cu: slab builder + GEMM), one slab of rows at a time, with its columns in the
+// plan's SORTED order (so do gvec and the slot table handed to k_contract / k_rowdot).  For a parameter theta of
 // input dimension i (group g of the table layout) only the factor of dimension i changes:
 //   dPhi[n,j]/dtheta = DT_theta[n, t_g(j)] * prod_{g' != g} H_g'[n, t_g'(j)]
 //   DT_theta[n,t]    = dF_i[n,k_i(t)]/dtheta * prod_{i' in g, i' != i} F_i'[n,k_i'(t)]
@@ -389,8 +390,9 @@ int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t
   if (rows == 0 || gd->n_active == 0) return GRIEF_OK;
   ContractParams P;
   P.Z = Z; P.ldz = ldz; P.T = T; P.stride = pl->stride; P.DT = DT; P.dt_width = gd->dt_width; P.y = y; P.gvec = gvec;
-  P.col_slot = pl->d_col_slot; P.g_np = gd->d_g_np; P.g_dtoff = gd->d_g_dtoff; P.g_slot0 = gd->d_g_slot0;
-  P.p = pl->p; P.max_np = gd->max_np; P.rows = rows; P.partial = partial; P.ga = gd->d_ga; P.n_active = gd->n_active;
+  P.col_slot = pl->d_sorted_gslot; P.g_np = gd->d_g_np; P.g_dtoff = gd->d_g_dtoff; P.g_slot0 = gd->d_g_slot0;
+  // Z, gvec and the slot table are in the sorted column order (padding columns contribute 0)
+  P.p = pl->p_pad; P.max_np = gd->max_np; P.rows = rows; P.partial = partial; P.ga = gd->d_ga; P.n_active = gd->n_active;
   const int nw = 8;
   const size_t smem = ((size_t)nw * (pl->stride + gd->dt_width) + (size_t)nw * gd->n_active) * sizeof(double);
   if (smem > 200 * 1024) return fail(GRIEF_ERR_UNSUPPORTED, "contract: %zu bytes of shared memory per block", smem);
@@ -422,7 +424,7 @@ int launch_reduce_partials(const double* partial, int nblk, int n_active, double
 int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream) {
   if (rows == 0) return GRIEF_OK;
   const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, 148 * 8);
-#define RD(Gv) k_rowdot<Gv><<<blocks, 256, 0, stream>>>(Z, ldz, T, pl->stride, pl->d_col_slot, pl->p, rows, out)
+#define RD(Gv) k_rowdot<Gv><<<blocks, 256, 0, stream>>>(Z, ldz, T, pl->stride, pl->d_sorted_gslot, pl->p_pad, rows, out)
   switch (pl->n_groups) {
     case 1: RD(1); break; case 2: RD(2); break; case 3: RD(3); break; case 4: RD(4); break;
     case 5: RD(5); break; case 6: RD(6); break; case 7: RD(7); break; case 8: RD(8); break;

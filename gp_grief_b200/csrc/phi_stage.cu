@@ -410,21 +410,34 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
 }
 
 // ---- pass 2 / predictive variance: Z = Phi B ----
-// B'[c][k] = B[c][perm[k]] (0 for padding columns): the K dimension of Z = Phi * B is walked in sorted column order.
+// B'[c][k] = B[perm[c]][perm[k]] (0 for padding rows / columns): both the K dimension of Z = Phi * B and the columns of Z are in
+// the plan's SORTED column order, so neighbouring lanes of the consumers (k_contract, k_rowdot) share their leading slots.
 __global__ void __launch_bounds__(256)
-k_permute_cols(const double* __restrict__ B, int64_t ldb, const int* __restrict__ perm, int p, int p_pad, double* __restrict__ out) {
-  const int64_t total = (int64_t)p * p_pad;
+k_permute_sym(const double* __restrict__ B, int64_t ldb, const int* __restrict__ perm, int p_pad, double* __restrict__ out) {
+  const int64_t total = (int64_t)p_pad * p_pad;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(e / p_pad), k = (int)(e - (int64_t)c * p_pad);
-    const int src = perm[k];
-    out[e] = src >= 0 ? B[(size_t)c * ldb + src] : 0.0;
+    const int sc = perm[c], sk = perm[k];
+    out[e] = (sc >= 0 && sk >= 0) ? B[(size_t)sc * ldb + sk] : 0.0;
   }
 }
 
+// Bperm: p_pad x p_pad doubles
 int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream) {
-  const int64_t total = (int64_t)pl->p * pl->p_pad;
+  const int64_t total = (int64_t)pl->p_pad * pl->p_pad;
   const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  k_permute_cols<<<blocks, 256, 0, stream>>>(B, ldb, pl->d_perm, pl->p, pl->p_pad, Bperm);
+  k_permute_sym<<<blocks, 256, 0, stream>>>(B, ldb, pl->d_perm, pl->p_pad, Bperm);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+// out[c] = perm[c] >= 0 ? scale * in[perm[c]] : 0   (a p-vector brought into the sorted column order)
+__global__ void k_permute_vec(const double* __restrict__ in, double scale, const int* __restrict__ perm, int p_pad, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < p_pad) out[c] = perm[c] >= 0 ? scale * in[perm[c]] : 0.0;
+}
+int launch_permute_vec(const Plan* pl, const double* in, double scale, double* out, cudaStream_t stream) {
+  k_permute_vec<<<(pl->p_pad + 255) / 256, 256, 0, stream>>>(in, scale, pl->d_perm, pl->p_pad, out);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
@@ -459,11 +472,10 @@ static ZScratch carve_zscratch(const Plan* pl, int64_t slab_rows, void* scratch)
 int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream) {
   if (g_gemm_mode != 1) return GRIEF_OK;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
-  return ozaki_slice(Bperm, pl->p_pad, pl->p, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, stream);
+  return ozaki_slice(Bperm, pl->p_pad, pl->p_pad, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, stream);
 }
 
-// Z (slab_rows x ldz) = Phi(slab) * B, B symmetric given as Bperm (p x p_pad, launch_permute_b).  Columns >= p of Z are
-// zero on the DMMA path and left untouched on the INT8 path (no consumer reads them).
+// Z (slab_rows x ldz, columns in SORTED order) = Phi(slab) * B, B symmetric given as Bperm (p_pad x p_pad, launch_permute_b).
 // scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
                  int64_t ldz, cudaStream_t stream, int* launches) {
@@ -484,10 +496,9 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   prof_begin(PROF_ZGEMM, stream);
   if (g_gemm_mode == 1) {
     GRIEF_REQUIRE(pl->p_pad <= kOzakiKRange, "zgemm: p_pad=%d exceeds the INT8 path's K range of %d", pl->p_pad, kOzakiKRange);
-    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p, z.eb, pl->p, pl->p_pad, Z, ldz, false, false, 1, 0, stream, launches);
+    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p_pad, z.eb, pl->p_pad, pl->p_pad, Z, ldz, false, false, 1, 0, stream, launches);
   } else {
     GemmOpts o;
-    o.rows_b = pl->p;                                 // rows p..p_pad of B' do not exist: TMA fills zeros
     rc = gemm_nt_ex(z.Phi, pl->p_pad, Bperm, pl->p_pad, Z, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);
   }
   prof_end(PROF_ZGEMM, stream);

@@ -57,6 +57,7 @@ struct Plan {
   // consecutive columns then share their leading slots and only the factors from `level` on are re-gathered.
   uint16_t* d_sorted_slot = nullptr;    // p_pad x G: slots of sorted column c, listed in key order
   uint8_t* d_sorted_level = nullptr;    // p_pad: first key position where sorted column c differs from c-1 (G: identical)
+  uint16_t* d_sorted_gslot = nullptr;   // p_pad x G: slots of sorted column c in GROUP order (consumers of Z, which is in sorted order)
   int* d_perm = nullptr;                // p_pad: external column of sorted column c (-1 for padding columns)
   std::vector<int> perm_h;
   int device = 0;
