@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=1 << 13, help="rows per CPU-baseline sample chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gemm", default="int8", choices=["int8", "fp64"],
+    ap.add_argument("--gemm", default="int8", choices=["int8", "int8x2", "fp64"],
                     help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores (54-bit operands, "
                          "same parity tests) or the FP64 DMMA GEMM")
     return ap.parse_args()
@@ -247,7 +247,7 @@ def run_ours(args):
         arith = {"rows": ns, "lml_fp64_dmma": res[0][0], "lml_int8_tensor": res[1][0],
                  "lml_rel_diff": abs(res[1][0] - res[0][0]) / abs(res[0][0]),
                  "grad_max_abs_diff_over_max_abs": float(np.abs(res[1][1][ok_] - res[0][1][ok_]).max() / np.abs(res[0][1][ok_]).max())}
-    nat.lib().grief_set_gemm_mode(1 if args.gemm == "int8" else 0)
+    nat.lib().grief_set_gemm_mode({"int8": 1, "int8x2": 3, "fp64": 0}[args.gemm])
 
     # ---- device-resident leg: one model, data stays in HBM, new hyper-parameters every step ----
     model = make_model(0)
@@ -324,8 +324,8 @@ def run_ours(args):
     kern_rows = []
     # work actually issued by the GEMM launches (padded rows / columns, full diagonal tiles)
     flops = {"k_zgemm": 2.0 * rows128 * p_pad * p_pad, "k_gram": float(rows128) * p_pad * (p_pad + 128)}
-    gk = "k_ozaki" if args.gemm == "int8" else "k_gemm_nt"
-    sl = " (exponents + int8 digit planes)" if args.gemm == "int8" else ""
+    gk = {"int8": "k_ozaki<1>", "int8x2": "k_ozaki<2> (cta_group::2 pairs)", "fp64": "k_gemm_nt"}[args.gemm]
+    sl = " (exponents + int8 digit planes)" if args.gemm != "fp64" else ""
     label = {"k_zgemm": gk + " [Z = Phi*G2, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
              "k_build_phi": "k_build_phi%s [Phi slab, pass 2]" % sl, "k_build_phi_t": "k_build_phi_t%s [Phi^T slab, pass 1]" % sl,
              "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)"}
@@ -340,7 +340,7 @@ def run_ours(args):
     roofline = None
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["k_ozaki_zgemm" if args.gemm == "int8" else "k_gemm_nt_zgemm"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["k_ozaki_zgemm" if args.gemm != "fp64" else "k_gemm_nt_zgemm"]
         if tr["config"] == args.config:
             traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "rows_per_launch": tr["rows_per_launch"],
                        "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "source": tr["source"]}
@@ -351,7 +351,7 @@ def run_ours(args):
         common = {"traffic": traffic, "avg_launch_ms": dom["ms_total"] / dom["launches"], "kernels": kern_rows,
                   "fp64_equivalent_tflops": algo, "cublas_dgemm_tflops_this_run": peak_sust, "fp64_dmma_issue_peak_tflops": 37.2,
                   "whole_eval_fp64_equivalent_tflops": 3.0 * n_total * p * p * value / world * 1e-12}
-        if args.gemm == "int8":
+        if args.gemm != "fp64":
             # 28 exact int8 digit GEMMs per FP64 GEMM; peak = dense INT8 = 2 x the dense bf16 rate measured on this pool
             tops = 28.0 * flops["k_zgemm"] * args.steps / (dom["ms_total"] * 1e-3) * 1e-12
             try:

@@ -10,12 +10,12 @@
 // planes a sweep needs for one 32-byte K chunk sit in shared memory (3-D TMA boxes over [digit][row][32 B], SWIZZLE_32B, three
 // 56 KB stages); warp 4 = TMA producer, warp 5 = MMA issuer (one thread, tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32),
 // warps 0-3 drain TMEM: tcgen05.ld -> f64 -> sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared memory
-// -> added to C.  k_ozaki<2> is the same kernel for CTA pairs that multicast their halves of the B digits to each other.
+// -> added to C.  k_ozaki<2> computes 256 x 128 tiles with CTA pairs and tcgen05.mma.cta_group::2 (see the template comment).
 // Measured (B200, pass-2 shape 37888 x 4096 x 4096): 14.4 ms = 88 TFLOP/s FP64-equivalent alone, 81 inside the benchmark (power
 // cap), against 35 for cuBLAS DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
 // Variants measured and not adopted (profiles/r01_gram_design_notes.md): 128 x 256 tiles with two accumulators and five work
-// items (16.7 ms), CTA pairs with multicast B (same time, lower clock), 64-byte K stages for the light sweep (slower),
-// cta_group::2 MMAs on 256 x 256 tiles (tools/microbench/ozaki_gemm_2cta.cu, 15.4 ms).
+// items (16.7 ms), CTA pairs with multicast B or with cta_group::2 MMAs (same time or slower, lower clock), 64-byte K stages for
+// the light sweep (slower), accumulator-interleaved MMA order (slower).
 // Every barrier wait is bounded: a protocol failure raises an error flag (checked by the callers) instead of hanging the GPU.
 #include <cuda.h>
 
@@ -89,7 +89,7 @@ __global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, 
 struct OzParams {
   double* C; int64_t ldc;
   const int* ea; const int* eb;      // row exponents of A and B, padded with zeros to multiples of 128
-  const CUtensorMap* maps;           // A with box depth 7, A depth 3, B depth 7, B depth 3, B half rows depth 1
+  const CUtensorMap* maps;           // A depth 7, A depth 3, B depth 7, B depth 3, B half rows depth 7, B half rows depth 3
   int chunks;                        // 32-byte K chunks in total
   int split_chunks;                  // chunks per blockIdx.z (== chunks when K is not split)
   int64_t c_split_stride;            // split z writes C + z * c_split_stride
@@ -99,9 +99,11 @@ struct OzParams {
   int* err;
 };
 
-// CL = CTAs per cluster along M (1 or 2).  With CL = 2 the pair shares its B digits: each CTA loads half of the B rows and
-// multicasts them into both CTAs' shared memory, and every stage is released to both producers (multicast commit), which
-// cuts the L2 -> SM operand traffic of the pair by a quarter.
+// CL = CTAs per tile (1 or 2).  CL = 2: a 256 x 128 tile is computed by a PAIR of CTAs (thread-block cluster (2,1,1), adjacent in x)
+// with tcgen05.mma.cta_group::2: each CTA stages its own 128 A rows and HALF of the B rows (64), the leader CTA issues the MMAs
+// (M = 256, N = 128, K = 32), each CTA's TMEM receives its 128 rows of the four accumulators and each CTA drains its own rows.
+// Both CTAs' TMA loads complete on the LEADER's full barrier (peer bit of the barrier address cleared), the leader's commits are
+// multicast to both CTAs' empty / tfull barriers, the drain threads of both CTAs arrive on the leader's tfree barrier.
 template <int CL>
 __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   extern __shared__ unsigned char smem_dyn[];
@@ -110,11 +112,15 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   const uint32_t cscale = base + 1024;               // 128 doubles: 2^eb of the tile's columns
   const uint32_t stagebuf = base + 4096;             // 4 warps x 32 rows x 17 doubles (transpose staging for coalesced stores)
   const uint32_t ring = base + 4096 + 20480;         // 1024-aligned
+  constexpr int kBSlice = B_SLICE / CL;              // this CTA's share of a B digit plane: 128 or 64 rows of 32 bytes
+  constexpr int kStageBytes = S * (A_SLICE + kBSlice);
+  constexpr int kStages = CL == 2 ? 4 : 3;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bn = blockIdx.x, bm = blockIdx.y;
+  const int bn = CL == 2 ? blockIdx.y : blockIdx.x, bm = CL == 2 ? blockIdx.x : blockIdx.y;   // CTA pairs are adjacent in x
   if (prm.lower_only && bn > (CL == 2 ? (bm | 1) : bm)) return;      // uniform over the cluster
   uint32_t crank = 0;
   if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const bool leader = crank == 0;
   const int c_begin = (int)blockIdx.z * prm.split_chunks;
   const int nk = min(prm.split_chunks, prm.chunks - c_begin);
   double* const Cz = prm.C + (size_t)blockIdx.z * prm.c_split_stride;
@@ -127,17 +133,22 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
     return;
   }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full + 8 * s));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty + 8 * s), "r"(CL));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty + 8 * s));
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tfull));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(tfree));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tfree), "r"(128 * CL));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(slot) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(slot) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(slot) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   for (int j = tid; j < TN; j += 192) {
     const double cs = ldexp(1.0, prm.eb[bn * TN + j]);
@@ -157,34 +168,33 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
       const int nd = item_digits(it);
-      const uint32_t bytes = (uint32_t)(nd * (A_SLICE + B_SLICE));
+      const uint32_t bytes = (uint32_t)(nd * (A_SLICE + kBSlice));
       const CUtensorMap* mA = prm.maps + (it == 0 ? 0 : 1);
-      const CUtensorMap* mB = prm.maps + (it == 0 ? 2 : 3);
+      const CUtensorMap* mB = prm.maps + (CL == 2 ? (it == 0 ? 4 : 5) : (it == 0 ? 2 : 3));
       for (int c = 0; c < nk && ok; ++c, ++q) {
-        const int s = q % STAGES;
-        if (q >= STAGES) ok = wait_bounded(empty + 8 * s, (uint32_t)(((q / STAGES) - 1) & 1));
+        const int s = q % kStages;
+        if (q >= kStages) ok = wait_bounded(empty + 8 * s, (uint32_t)(((q / kStages) - 1) & 1));
         if (!ok) break;
-        const uint32_t dst = ring + s * STAGE_BYTES, bar = full + 8 * s;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-                     "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(bar) : "memory");
+        const uint32_t dst = ring + s * kStageBytes, bar = full + 8 * s;
         if (CL == 1) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                       "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(bar) : "memory");
           asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                            dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(0), "r"(bar) : "memory");
-        } else {                                    // my half of the B rows, digit by digit, into both CTAs of the pair
-          const CUtensorMap* mH = prm.maps + 4;
-          for (int d = 0; d < nd; ++d)
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
-                    dst + nd * A_SLICE + d * B_SLICE + crank * (B_SLICE / 2)),
-                "l"(mH), "r"((c_begin + c) * KC), "r"(bn * TN + (int)crank * (TN / 2)), "r"(d), "r"(bar), "h"((uint16_t)3)
-                : "memory");
+        } else {                                    // both CTAs' bytes are counted on the leader's barrier
+          const uint32_t lbar = bar & 0xFEFFFFFFu;
+          if (leader) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                           dst), "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(lbar) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                           dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN + (int)crank * (TN / 2)), "r"(0), "r"(lbar) : "memory");
         }
       }
     }
     if (!ok) atomicExch(prm.err, 1);
-  } else if (tid == 160) {                          // ---- MMA issuer (warp 5) ----
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  } else if (tid == 160 && leader) {                // ---- MMA issuer (warp 5; of the leader CTA when CL = 2) ----
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((CL * TM) >> 4) << 24);
     const uint64_t dhi = (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);   // K-major SWIZZLE_32B: LBO 1, SBO 256 B, v1
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
@@ -193,11 +203,11 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int c = 0; c < nk && ok; ++c, ++q) {
-        const int s = q % STAGES;
-        ok = wait_bounded(full + 8 * s, (uint32_t)((q / STAGES) & 1));
+        const int s = q % kStages;
+        ok = wait_bounded(full + 8 * s, (uint32_t)((q / kStages) & 1));
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = ring + s * STAGE_BYTES, sb = sa + nd * A_SLICE;
+        const uint32_t sa = ring + s * kStageBytes, sb = sa + nd * A_SLICE;
         const uint64_t da0 = dhi | (uint64_t)((sa >> 4) & 0x3FFF), db0 = dhi | (uint64_t)((sb >> 4) & 0x3FFF);
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {            // accumulator gi <-> group g_hi - gi, TMEM columns gi*128 ..
@@ -208,19 +218,27 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
           for (int a = 0; a < S; ++a) {
             const int b = g - a;
             if (a >= nd || b < 0 || b >= nd) continue;
-            const uint64_t da = da0 + (uint64_t)(a * (A_SLICE >> 4)), db = db0 + (uint64_t)(b * (B_SLICE >> 4));
-            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
-                             tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+            const uint64_t da = da0 + (uint64_t)(a * (A_SLICE >> 4)), db = db0 + (uint64_t)(b * (kBSlice >> 4));
+            if (CL == 1)
+              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+                               tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+            else
+              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+                               tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
             accf = 1u;
           }
         }
         if (CL == 1)
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
         else
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                            empty + 8 * s), "h"((uint16_t)3) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
+      if (CL == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull) : "memory");
+      else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tfull),
+                     "h"((uint16_t)3) : "memory");
     }
     if (!ok) atomicExch(prm.err, 2);
   }
@@ -282,7 +300,13 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
           if (col_ok && rbase + 2 * h < prm.m_valid) __stcg(dst0 + (size_t)(2 * h) * prm.ldc, old[h] + val[h] * cs);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tfree) : "memory");
+      if (CL == 1) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tfree) : "memory");
+      } else {                                      // the issuer lives in the leader CTA
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(tfree), "r"(0));
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -291,7 +315,10 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if (warp == 0) {
+    if (CL == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
 }
 
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -326,9 +353,9 @@ static int make_plane_map(CUtensorMap* m, const int8_t* planes, int rows, int64_
 static int* g_oz_err = nullptr;        // device error flag shared by all launches of this process
 static CUtensorMap* g_oz_maps = nullptr;   // ring of device-resident tensor-map sets (12 maps per launch)
 static int g_oz_map_slot = 0;
-static int g_oz_cluster = 0;           // CTA pairs with multicast B digits (ozaki_set_cluster).  Measured at C3: correct, and no
-                                       // faster than single CTAs -- with the digits arriving faster the tensor cores draw more
-                                       // power and the clock drops under sw_power_cap (1721 -> 1642 MHz); kept for the next round
+static int g_oz_cluster = 0;           // CTA pairs with cta_group::2 MMAs (ozaki_set_cluster).  Measured at C3: correct, and no
+                                       // faster than single CTAs (402 vs 423 ms per 1M rows in pass 2; the clock drops further
+                                       // under sw_power_cap, 1747 -> 1691 MHz); kept selectable for the next round
 constexpr int kMapSlots = 64;
 
 // Device flag raised by the kernels of the INT8 path: 1-3 = a barrier wait of k_ozaki timed out, 4 = a non-finite operand value.
@@ -365,43 +392,45 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   const int split_chunks = (chunks + splits - 1) / splits;
   GRIEF_REQUIRE(split_chunks * KC <= 16384, "ozaki_gemm: %d values of K per accumulation exceed the int32 budget of 16384", split_chunks * KC);
   if (ozaki_err_flag() == nullptr) return fail(GRIEF_ERR_CUDA, "ozaki_gemm: cudaMalloc of the error flag failed");
-  if (!g_oz_maps) GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 5 * kMapSlots));
-  alignas(64) CUtensorMap hmaps[5];
+  if (!g_oz_maps) GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 6 * kMapSlots));
+  alignas(64) CUtensorMap hmaps[6];
   memset(hmaps, 0, sizeof(hmaps));
   {
     int rc = make_plane_map(&hmaps[0], pa, M, rows_a_alloc, kp, TM, 7);
     if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[1], pa, M, rows_a_alloc, kp, TM, 3);
     if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[2], pb, N, rows_b_alloc, kp, TN, 7);
     if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[3], pb, N, rows_b_alloc, kp, TN, 3);
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[4], pb, N, rows_b_alloc, kp, TN / 2, 1);      // half of the B rows, one digit (cluster path)
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[4], pb, N, rows_b_alloc, kp, TN / 2, 7);      // half of the B rows (CTA-pair path)
+    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[5], pb, N, rows_b_alloc, kp, TN / 2, 3);
     if (rc != GRIEF_OK) return rc;
   }
-  CUtensorMap* dmaps = g_oz_maps + 5 * (g_oz_map_slot++ % kMapSlots);
+  CUtensorMap* dmaps = g_oz_maps + 6 * (g_oz_map_slot++ % kMapSlots);
   GRIEF_CUDA(cudaMemcpyAsync(dmaps, hmaps, sizeof(hmaps), cudaMemcpyHostToDevice, stream));
   OzParams prm;
   prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb; prm.maps = dmaps;
   prm.chunks = chunks; prm.split_chunks = split_chunks; prm.c_split_stride = c_split_stride;
   prm.m_valid = M; prm.n_valid = N; prm.lower_only = lower_only ? 1 : 0; prm.accumulate = accumulate ? 1 : 0; prm.err = g_oz_err;
-  const size_t smem = 1024 + 4096 + 20480 + 1024 + (size_t)STAGES * STAGE_BYTES;
+  const size_t smem1 = 1024 + 4096 + 20480 + 1024 + (size_t)3 * S * (A_SLICE + B_SLICE);
+  const size_t smem2 = 1024 + 4096 + 20480 + 1024 + (size_t)4 * S * (A_SLICE + B_SLICE / 2);
   static bool attr_set = false;
   if (!attr_set) {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     attr_set = true;
   }
-  const int tiles_m = (M + TM - 1) / TM;
-  if (g_oz_cluster && tiles_m >= 2) {               // CTA pairs along M; an odd last pair runs one CTA on zero rows
-    dim3 grid((N + TN - 1) / TN, (tiles_m + 1) / 2 * 2, splits);
+  const int tiles_m = (M + TM - 1) / TM, tiles_n = (N + TN - 1) / TN;
+  if (g_oz_cluster && tiles_m >= 2) {               // CTA pairs adjacent in x (cluster (2,1,1)); an odd last pair runs one CTA on zero rows
+    dim3 grid((tiles_m + 1) / 2 * 2, tiles_n, splits);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     GRIEF_CUDA(cudaLaunchKernelEx(&cfg, k_ozaki<2>, prm));
   } else {
-    dim3 grid((N + TN - 1) / TN, tiles_m, splits);
-    k_ozaki<1><<<grid, 192, smem, stream>>>(prm);
+    dim3 grid(tiles_n, tiles_m, splits);
+    k_ozaki<1><<<grid, 192, smem1, stream>>>(prm);
   }
   GRIEF_CUDA(cudaGetLastError());
   if (launches) *launches += 1;

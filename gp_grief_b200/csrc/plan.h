@@ -91,7 +91,7 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
                int* launches);
 int ozaki_check(cudaStream_t stream);
 int* ozaki_err_flag();               // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value
-void ozaki_set_cluster(int on);     // 1: 2-CTA clusters along M with TMA-multicast B digits (experimental, off by default)
+void ozaki_set_cluster(int on);     // 1: CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles (off by default)
 // 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki) for the two O(n p^2) products
 int gemm_mode();
 void set_gemm_mode(int mode);

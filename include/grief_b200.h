@@ -137,8 +137,9 @@ void grief_set_slab_budget(size_t bytes);
  *   1  FP64 emulated on the INT8 tensor cores (tcgen05 kind::i8, 7 balanced 8-bit digits per operand = 54 bits + sign,
  *      28 exact int8 x int8 -> int32 digit products), ~75 TFLOP/s FP64-equivalent; element errors are bounded by 2^-53 of
  *      the product of the operands' row maxima times K, i.e. the accuracy class of DGEMM
- *   3  as 1, with 2-CTA thread-block clusters whose CTAs multicast their halves of the B digits to each other (TMA multicast,
- *      multicast tcgen05.commit); correct and tested, not faster on a power-capped B200, off by default
+ *   3  as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2 (each CTA stages
+ *      its A rows and half of the B rows; multicast tcgen05.commit; leader-side barriers); correct and tested, not faster on a
+ *      power-capped B200, off by default
  * Workspace sizes depend on the mode: query them after changing it.  Process-wide.
  */
 void grief_set_gemm_mode(int mode);
