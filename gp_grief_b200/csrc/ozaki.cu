@@ -27,15 +27,14 @@
 namespace grief {
 
 constexpr int S = 7;                     // balanced 8-bit digits per operand (54 bits + sign)
-constexpr int TM = 128, TN = 128, KC = 32, STAGES = 3;
-constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // 4 KB each
-constexpr int STAGE_BYTES = S * (A_SLICE + B_SLICE);           // 56 KB: all digits of both operands for one K chunk
+constexpr int TM = 128, TN = 128, KC = 32;
+constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // one digit plane of a tile and K chunk: 4 KB each
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // Work items.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b:
 //   item 0: g = 6, 5, 4, 3   all 7 + 7 digit planes, 22 MMAs per K chunk, 56 KB per stage
 //   item 1: g = 2, 1, 0      digits 0..2 of both,     6 MMAs per K chunk, 24 KB per stage
-// Two sweeps over K per tile, two drains; 80 KB of digits per 28 MMAs and chunk (the kernel is bound by L2 -> SM traffic).
+// Two sweeps over K per tile, two drains; 80 KB of digits per 28 MMAs and chunk.
 constexpr int kNumItems = 2;
 __device__ __forceinline__ int item_g_hi(int it) { return it == 0 ? 6 : 2; }
 __device__ __forceinline__ int item_g_lo(int it) { return it == 0 ? 3 : 0; }
