@@ -316,7 +316,8 @@ GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
     if (eff >= 0.97) { best = (int)S; break; }
   }
   s.splits = best;
-  if (g_gemm_mode == 1) s.splits = (int)((s.slab_rows + kOzakiKRange - 1) / kOzakiKRange);   // one int32 accumulation per split
+  if (g_gemm_mode == 1)      // at most 16384 rows per int32 accumulation; more splits when that is needed to fill the SMs
+    s.splits = std::max(best, (int)((s.slab_rows + kOzakiKRange - 1) / kOzakiKRange));
   return s;
 }
 
