@@ -170,3 +170,47 @@ def test_sharding_and_layout():
             assert cover == list(range(n))
     lay = stats_layout(4)
     assert lay["A"] == (0, 16) and lay["r"] == (16, 20) and lay["s"] == (20, 21) and lay["size"] == 21
+
+
+def test_int8_digit_scheme_is_double_precision_class():
+    """NumPy restatement of the arithmetic of csrc/ozaki.cu + phi_stage.cu:store_digits (no GPU involved).
+
+    Each operand row is scaled by 2^-e (e = frexp exponent of the row maximum), truncated to 54 bits and cut into 7 balanced
+    base-256 digits by the carry-free bias trick; A B^T is rebuilt from the exact integer products of the digit planes with
+    a + b <= 6.  The result must agree with the float64 product to a few ulps of the row-maxima product times K.
+    """
+    rng = np.random.RandomState(7)
+    M, N, K = 24, 40, 300
+    A = (rng.rand(M, K) - 0.5) * np.exp(4 * (rng.rand(M, K) - 0.5))
+    B = (rng.rand(N, K) - 0.5) * np.exp(4 * (rng.rand(N, K) - 0.5))
+    A[3] = 0.0                                        # an all-zero row keeps exponent 0 and all-zero digits
+
+    def digits(X):
+        amax = np.abs(X).max(axis=1)
+        e = np.where(amax > 0, np.frexp(amax)[1], 0).astype(np.int64)
+        q = np.trunc(np.ldexp(X, (54 - e)[:, None])).astype(np.int64)               # |q| < 2^54, exact
+        bias = np.int64(0x0080808080808080)
+        w = (q + bias) ^ bias                                                       # byte k of w, read as int8, is the digit of 256^k
+        d = np.stack([((w >> np.int64(8 * (6 - s))) & np.int64(0xFF)).astype(np.uint8).view(np.int8).astype(np.int64)
+                      for s in range(7)])                                           # digit 0 = most significant
+        recon = sum(d[s] * np.int64(256) ** (6 - s) for s in range(7))
+        assert np.array_equal(recon, q)                                             # the digits represent q exactly
+        assert d.min() >= -128 and d.max() <= 127
+        return d, e
+
+    dA, eA = digits(A)
+    dB, eB = digits(B)
+    C = np.zeros((M, N))
+    for g in range(6, -1, -1):                                                      # least significant group first, as the drain does
+        acc = np.zeros((M, N), dtype=np.int64)
+        for a in range(g + 1):
+            acc += dA[a].dot(dB[g - a].T)                                           # exact integer GEMM (int32 on the tensor cores)
+        assert np.abs(acc).max() < 2 ** 31
+        C += np.ldexp(acc.astype(np.float64), -12 - 8 * g)
+    C = np.ldexp(C, eA[:, None] + eB[None, :])
+    ref = A.dot(B.T)
+    scale = np.abs(A).max(axis=1)[:, None] * np.abs(B).max(axis=1)[None, :] * K
+    scale[scale == 0] = 1.0
+    assert np.abs(C - ref).max() / np.abs(ref).max() < 5e-15
+    assert (np.abs(C - ref) / scale).max() < 2.0 ** -52
+    assert np.all(C[3] == 0.0)
