@@ -13,8 +13,7 @@
 #include <vector>
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
-constexpr int TM = 128, TN = 256, KC = 128, STAGES = 4;
-constexpr int A_BYTES = TM * KC, B_BYTES = TN * KC, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TM = 128, TN = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -27,17 +26,21 @@ __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B: LBO = 1, SBO = 1024 B, version 1
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major; SWIZZLE_128B (SBO 1024 B, type 2) or SWIZZLE_32B (SBO 256 B, type 6)
+  return KC == 128 ? ((uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61))
+                   : ((uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61));
 }
 
+template <int KC, int STAGES>
 __global__ void __launch_bounds__(128, 1)
 k_umma_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int32_t* __restrict__ C, int N, int K,
           int* __restrict__ err) {
+  constexpr int A_BYTES = TM * KC, B_BYTES = TN * KC, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t bars = base;                       // full[4], empty[4], tmem_full, tmem_slot
-  const uint32_t full = bars, empty = bars + 32, tfull = bars + 64, slot = bars + 72;
+  const uint32_t bars = base;                       // full[STAGES], empty[STAGES], tmem_full, tmem_slot
+  const uint32_t full = bars, empty = bars + 256, tfull = bars + 512, slot = bars + 520;
   const uint32_t ring = base + 1024;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bn = blockIdx.x, bm = blockIdx.y;
@@ -84,7 +87,7 @@ k_umma_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       const uint32_t sa = ring + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
       for (int k = 0; k < KC / 32; ++k) {           // K = 32 per instruction = 32 bytes = 2 descriptor address units
-        const uint64_t da = make_desc(sa) + (uint64_t)(2 * k), db = make_desc(sb) + (uint64_t)(2 * k);
+        const uint64_t da = make_desc<KC>(sa) + (uint64_t)(2 * k), db = make_desc<KC>(sb) + (uint64_t)(2 * k);
         const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
                      "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
@@ -125,7 +128,7 @@ k_umma_i8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static void make_map(CUtensorMap* m, const int8_t* p, int rows, int K, int box_rows) {
+static void make_map(CUtensorMap* m, const int8_t* p, int rows, int K, int box_rows, int KC) {
   static EncodeFn enc = nullptr;
   if (!enc) {
     void* f = nullptr; cudaDriverEntryPointQueryResult q;
@@ -137,11 +140,14 @@ static void make_map(CUtensorMap* m, const int8_t* p, int rows, int K, int box_r
   const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
   const cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)p, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   KC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
 }
 
+template <int KC, int STAGES>
 static int run(int M, int N, int K, bool check) {
+  constexpr int STAGE_BYTES = (TM + TN) * KC;
   std::vector<int8_t> hA((size_t)M * K), hB((size_t)N * K);
   uint64_t st = 0x9E3779B97F4A7C15ull;
   auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
@@ -152,17 +158,17 @@ static int run(int M, int N, int K, bool check) {
   CK(cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4)); CK(cudaMemset(dErr, 0, 4));
   alignas(64) CUtensorMap mA, mB;
-  make_map(&mA, dA, M, K, TM); make_map(&mB, dB, N, K, TN);
+  make_map(&mA, dA, M, K, TM, KC); make_map(&mB, dB, N, K, TN, KC);
   const size_t smem = 1024 + 1024 + (size_t)STAGES * STAGE_BYTES;
-  CK(cudaFuncSetAttribute(k_umma_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_umma_i8<KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(N / TN, M / TM);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  k_umma_i8<<<grid, 128, smem>>>(mA, mB, dC, N, K, dErr);
+  k_umma_i8<KC, STAGES><<<grid, 128, smem>>>(mA, mB, dC, N, K, dErr);
   CK(cudaDeviceSynchronize());
   int herr = 0; CK(cudaMemcpy(&herr, dErr, 4, cudaMemcpyDeviceToHost));
   const int reps = check ? 1 : 5;
   CK(cudaEventRecord(e0));
-  for (int r = 0; r < reps; ++r) k_umma_i8<<<grid, 128, smem>>>(mA, mB, dC, N, K, dErr);
+  for (int r = 0; r < reps; ++r) k_umma_i8<KC, STAGES><<<grid, 128, smem>>>(mA, mB, dC, N, K, dErr);
   CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
   long long bad = 0;
@@ -176,7 +182,7 @@ static int run(int M, int N, int K, bool check) {
         if ((int32_t)s != hC[(size_t)i * N + j]) { if (bad < 5) printf("  mismatch (%d,%d): got %d want %lld\n", i, j, hC[(size_t)i * N + j], s); ++bad; }
       }
   }
-  printf("M=%d N=%d K=%d: %.3f ms  %.1f TOPS  err_flag=%d%s\n", M, N, K, ms, 2.0 * M * N * K / ms * 1e-9, herr,
+  printf("KC=%d stages=%d M=%d N=%d K=%d: %.3f ms  %.1f TOPS  err_flag=%d%s\n", KC, STAGES, M, N, K, ms, 2.0 * M * N * K / ms * 1e-9, herr,
          check ? (bad ? "  MISMATCH" : "  exact") : "");
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dErr);
   return (herr || bad) ? 1 : 0;
@@ -184,10 +190,14 @@ static int run(int M, int N, int K, bool check) {
 
 int main() {
   int rc = 0;
-  rc |= run(128, 256, 128, true);
-  rc |= run(256, 512, 1024, true);
+  rc |= run<128, 4>(128, 256, 128, true);
+  rc |= run<128, 4>(256, 512, 1024, true);
+  rc |= run<32, 16>(256, 512, 1024, true);
   if (rc) { printf("correctness failed; skipping the throughput runs\n"); return 1; }
-  run(8192, 8192, 8192, false);
-  run(4096, 4096, 131072, false);
+  // same tile, same bytes in flight (192 KB): 128-byte K rows (4 MMAs per stage) against 32-byte K rows (1 MMA per stage)
+  run<128, 4>(8192, 8192, 8192, false);
+  run<32, 16>(8192, 8192, 8192, false);
+  run<128, 4>(4096, 4096, 131072, false);
+  run<32, 16>(4096, 4096, 131072, false);
   return 0;
 }
