@@ -36,6 +36,7 @@ SIGNATURES = {
     "grief_plan_info": (c_int, [c_void, c_int]),
     "grief_table_rows": (c_i64, [c_i64]),
     "grief_build_tables": (c_int, [c_void, c_void, c_i64, c_i64, c_void, c_void]),
+    "grief_build_tables_dx": (c_int, [c_void, c_void, c_i64, c_i64, c_int, c_void, c_void]),
     "grief_phi_rows": (c_int, [c_void, c_void, c_i64, c_void, c_void]),
     "grief_gram_workspace_bytes": (c_size, [c_void, c_i64]),
     "grief_gram": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_size, c_void]),

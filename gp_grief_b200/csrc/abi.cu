@@ -11,7 +11,8 @@ void solve_ctx_destroy(SolveCtx* c);
 int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* r, const double* yty, const double* w,
               double noise, int64_t n_rows, double* L, double* b, double* Pinv, double* grad_w, double* G2,
               double* scalars_host, int* info_out, cudaStream_t stream, int* launches);
-int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64_t n_pad, double* T, cudaStream_t stream);
+int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64_t n_pad, double* T, cudaStream_t stream,
+                  int deriv_dim);
 int launch_phi_rows(const Plan* pl, const double* T, int64_t n, double* Phi, cudaStream_t stream);
 int phi_t_vec_blocks(int64_t n);
 int launch_phi_t_vec(const Plan* pl, const double* T, int64_t n, const double* v, double* out, double* ws, cudaStream_t stream);
@@ -137,7 +138,16 @@ int64_t grief_table_rows(int64_t n) { return (n + kRowBlock - 1) / kRowBlock * k
 int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, double* T_dev, void* stream) {
   GRIEF_REQUIRE(plan && T_dev && (X_dev || n == 0), "grief_build_tables: null pointer");
   GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d, "grief_build_tables: n=%lld ldx=%lld d=%d", (long long)n, (long long)ldx, plan->impl->d);
-  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream);
+  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, -1);
+  if (rc == GRIEF_OK && n > 0) g_launches += 1;
+  return rc;
+}
+
+int grief_build_tables_dx(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, int dim, double* T_dev, void* stream) {
+  GRIEF_REQUIRE(plan && T_dev && (X_dev || n == 0), "grief_build_tables_dx: null pointer");
+  GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d, "grief_build_tables_dx: n=%lld ldx=%lld d=%d", (long long)n, (long long)ldx, plan->impl->d);
+  GRIEF_REQUIRE(dim >= 0 && dim < plan->impl->d, "grief_build_tables_dx: dim=%d outside [0,%d)", dim, plan->impl->d);
+  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, dim);
   if (rc == GRIEF_OK && n > 0) g_launches += 1;
   return rc;
 }

@@ -36,12 +36,39 @@ __device__ __forceinline__ double kern_eval(int kernel, double x, double u, doub
   }
 }
 
+// d k(x, u) / d x  (kern/stationary.py grad_x of the in-house kernels; the reference needs GPy's gradients_X for this,
+// kern/grid_kernel.py:196-199)
+__device__ __forceinline__ double kern_eval_dx(int kernel, double x, double u, double variance, double lengthscale) {
+  const double diff = x - u;
+  const double l2 = lengthscale * lengthscale;
+  switch (kernel) {
+    case KERN_RBF:
+      if (lengthscale < 1e-6) return 0.0;
+      return -variance * exp(-0.5 * diff * diff / l2) * diff / l2;
+    case KERN_EXPONENTIAL: {
+      const double sgn = diff > 0.0 ? 1.0 : (diff < 0.0 ? -1.0 : 0.0);
+      return -variance * exp(-fabs(diff) / lengthscale) * sgn / lengthscale;
+    }
+    case KERN_MATERN32: {
+      const double s3 = 1.7320508075688772;
+      return -variance * 3.0 * diff * exp(-s3 * fabs(diff) / lengthscale) / l2;
+    }
+    default: {  // KERN_MATERN52
+      const double s5 = 2.23606797749979;
+      const double r = fabs(diff) / lengthscale;
+      return -variance * (5.0 / 3.0) * diff * (1.0 + s5 * r) * exp(-s5 * r) / l2;
+    }
+  }
+}
+
 // One block = RB data rows.  smem: sK[RB][sum_m], sF[RB][sum_u].
+// deriv_dim >= 0: the kernel of that input dimension is replaced by its derivative with respect to x, so that the
+// table products become d Phi / d x[:, deriv_dim] (models/gp_grief_model.py:127-134, kern/grief_kernel.py:113-126).
 __global__ void __launch_bounds__(256)
 k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, const double* __restrict__ qs,
          const uint8_t* __restrict__ slot_k, const int* __restrict__ slot_group, const int* __restrict__ group_begin,
          int d, int sum_m, int sum_u, int width, int stride, int max_group_dims, const double* __restrict__ X,
-         int64_t ldx, int64_t n, int64_t n_pad, double* __restrict__ T, int RB) {
+         int64_t ldx, int64_t n, int64_t n_pad, double* __restrict__ T, int RB, int deriv_dim) {
   extern __shared__ double sm[];
   double* sK = sm;
   double* sF = sm + (size_t)RB * sum_m;
@@ -58,7 +85,9 @@ k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, cons
     const DimDesc dd = dims[i];
     const int64_t row = row0 + r;
     double v = 0.0;
-    if (row < n) v = kern_eval(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale);
+    if (row < n)
+      v = (i == deriv_dim) ? kern_eval_dx(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale)
+                           : kern_eval(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale);
     sK[(size_t)r * sum_m + c] = v;
   }
   __syncthreads();
@@ -98,7 +127,7 @@ k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, cons
 }
 
 int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64_t n_pad, double* T,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int deriv_dim) {
   const size_t per_row = (size_t)(pl->sum_m + pl->sum_u) * sizeof(double);
   int RB = (int)std::min<size_t>(32, (160 * 1024) / per_row);
   if (RB < 1) return fail(GRIEF_ERR_UNSUPPORTED, "tables: %d grid points + %d factors per row exceed shared memory",
@@ -110,7 +139,7 @@ int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64
   prof_begin(PROF_TABLES, stream);
   k_tables<<<(unsigned)blocks, 256, smem, stream>>>(pl->d_dims, pl->d_grid, pl->d_qs, pl->d_slot_k, pl->d_slot_group,
                                                     pl->d_group_begin, pl->d, pl->sum_m, pl->sum_u, pl->width,
-                                                    pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB);
+                                                    pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB, deriv_dim);
   prof_end(PROF_TABLES, stream);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;

@@ -85,8 +85,10 @@ class DevicePlan(object):
             pass
 
     # ---- row kernels ----
-    def build_tables(self, X_dev):
-        """X_dev: (n, d) float64 CUDA tensor (row-major).  Returns the (n_pad, stride) table tensor."""
+    def build_tables(self, X_dev, deriv_dim=None):
+        """X_dev: (n, d) float64 CUDA tensor (row-major).  Returns the (n_pad, stride) table tensor.
+
+        deriv_dim: input dimension whose kernel is replaced by its x-derivative (tables of d Phi / d x[:, deriv_dim])."""
         torch = _torch()
         assert X_dev.is_cuda and X_dev.dtype == torch.float64 and X_dev.dim() == 2 and X_dev.shape[1] == self.d
         assert X_dev.stride(1) == 1 or X_dev.shape[0] == 0
@@ -94,7 +96,11 @@ class DevicePlan(object):
         rows = nat.lib().grief_table_rows(n)
         T = torch.empty((rows, self.stride), dtype=torch.float64, device=X_dev.device)
         ldx = X_dev.stride(0) if n > 1 else self.d
-        nat.check(nat.lib().grief_build_tables(self._h, nat.dev_ptr(X_dev), ldx, n, nat.dev_ptr(T), nat.stream_ptr()))
+        if deriv_dim is None:
+            nat.check(nat.lib().grief_build_tables(self._h, nat.dev_ptr(X_dev), ldx, n, nat.dev_ptr(T), nat.stream_ptr()))
+        else:
+            nat.check(nat.lib().grief_build_tables_dx(self._h, nat.dev_ptr(X_dev), ldx, n, int(deriv_dim), nat.dev_ptr(T),
+                                                      nat.stream_ptr()))
         return T
 
     def phi_rows(self, T, n):

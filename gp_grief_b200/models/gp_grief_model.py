@@ -288,10 +288,15 @@ class GPGriefModel(BaseModel):
         return Yhat, Yhatvar.cpu().numpy()
 
     def d_Yhat_d_x(self, Xnew, dim):
-        """d Yhat / d x[:, dim] (reference :127-134)."""
+        """d Yhat / d x[:, dim] (reference :127-134) on the device: the basis tables of Xnew with the kernel of dimension `dim`
+        replaced by its x-derivative, times alpha_p.  (`kern.cov_grad` keeps the host evaluation of d Phi / d x.)"""
         self.predict_precompute(Xnew)
-        dPhi = self.kern.cov_grad(Xnew, dim)
-        return dPhi.dot(self._alpha_p)
+        t = self._torch
+        plan = self.kern.device_plan()
+        out = self._cov_setup(want_grad=False)
+        Xd = t.as_tensor(np.ascontiguousarray(Xnew, dtype=np.float64)).cuda()
+        Tn = plan.build_tables(Xd, deriv_dim=int(dim))
+        return plan.phi_vec(Tn, Xnew.shape[0], out['b']).cpu().numpy().reshape((-1, 1))      # alpha_p == b
 
     # ------------------------------------------------------------------ covariance operators (inspection-sized n)
     def _mv_cov(self, x):

@@ -121,6 +121,14 @@ int64_t grief_table_rows(int64_t n);
  */
 int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, double* T_dev, void* stream);
 
+/*
+ * Same tables with the kernel of input dimension `dim` replaced by its derivative with respect to x: every product formed from
+ * them (grief_phi_rows, grief_phi_vec, ...) is then d/dx[:, dim] of the corresponding quantity.  grief_phi_vec on these tables with
+ * v = alpha_p gives GPGriefModel.d_Yhat_d_x (models/gp_grief_model.py:127-134; the reference needs GPy for the kernel derivative,
+ * kern/grid_kernel.py:181-206).
+ */
+int grief_build_tables_dx(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, int dim, double* T_dev, void* stream);
+
 /* Phi (n, p) row-major from the tables: GriefKernel.cov(x)[0] (kern/grief_kernel.py:68-111). Small n only. */
 int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, double* Phi_dev, void* stream);
 

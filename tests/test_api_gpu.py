@@ -239,3 +239,31 @@ def test_kron_matvec_on_device_matches_host():
     np.testing.assert_allclose(y_dev, y_host, rtol=0, atol=1e-12 * np.abs(y_host).max())
     dense = np.kron(np.kron(np.kron(K.K[0], K.K[1]), K.K[2]), K.K[3])
     np.testing.assert_allclose(y_dev, dense.dot(x), rtol=0, atol=1e-11 * np.abs(y_host).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kname", ["RBF", "Matern32", "Matern52", "Exponential"])
+def test_d_yhat_d_x_on_device(kname):
+    """input gradient of the predictive mean (reference models/gp_grief_model.py:127-134) -- device tables with
+    one kernel replaced by its x-derivative, against the host evaluation of d Phi / d x and against central differences."""
+    import gp_grief_b200 as gp
+    rng = np.random.RandomState(11)
+    n, d, m, p = 400, 3, 7, 40
+    X = rng.rand(n, d)
+    Y = np.sin(3 * X[:, :1]) + X[:, 1:2] ** 2 + 0.05 * rng.randn(n, 1)
+    grid = gp.grid.InducingGrid(xg=[np.linspace(0, 1, m).reshape(-1, 1)] * d)
+    K = getattr(gp.kern, kname)
+    kern = gp.kern.GriefKernel([K(1, lengthscale=0.35 + 0.1 * i) for i in range(d)], grid, n_eigs=p, reweight_eig_funs=False)
+    mdl = gp.models.GPGriefModel(X, Y, kern, noise_var=0.05)
+    Xnew = 0.1 + 0.8 * rng.rand(25, d) + 0.0137                 # away from the grid points (Exponential has a kink there)
+    for dim in range(d):
+        g_dev = mdl.d_Yhat_d_x(Xnew, dim)
+        assert g_dev.shape == (25, 1)
+        g_host = mdl.kern.cov_grad(Xnew, dim).dot(mdl._alpha_p)
+        np.testing.assert_allclose(g_dev, g_host.reshape(-1, 1), rtol=0, atol=1e-10 * max(1.0, np.abs(g_host).max()))
+        h = 1e-6
+        Xp, Xm = Xnew.copy(), Xnew.copy()
+        Xp[:, dim] += h
+        Xm[:, dim] -= h
+        fd = (mdl.predict(Xp, compute_var=None) - mdl.predict(Xm, compute_var=None)) / (2 * h)
+        np.testing.assert_allclose(g_dev, fd, rtol=0, atol=2e-5 * max(1.0, np.abs(fd).max()))
