@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libgrief_b200.so")
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_NOT_PD, ERR_UNSUPPORTED, ERR_LIBRARY = 0, 1, 2, 3, 4, 5
 SC_LML, SC_YT_ALPHA, SC_LOGDET, SC_GRAD_NOISE, SC_RTB, SC_ALPHA_SQ, SC_TRACE, SC_COUNT = range(8)
 KERNEL_IDS = {"RBF": 0, "Exponential": 1, "Matern32": 2, "Matern52": 3}
+OPT_GEMM_MODE, OPT_DIGITS_GRAM, OPT_DIGITS_Z, OPT_SLAB_BUDGET = 0, 1, 2, 3
 
 c_int, c_i64, c_size, c_void, c_dbl = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_double
 _P = ctypes.POINTER
@@ -50,6 +51,11 @@ SIGNATURES = {
                                  c_void, c_size, c_void]),
     "grief_quadform_workspace_bytes": (c_size, [c_void, c_i64]),
     "grief_quadform_rows": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_void, c_size, c_void]),
+    "grief_gram_ry": (c_int, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_size, c_void]),
+    "grief_set_default_option": (c_int, [c_int, c_i64]),
+    "grief_get_default_option": (c_i64, [c_int]),
+    "grief_plan_set_option": (c_int, [c_void, c_int, c_i64]),
+    "grief_plan_get_option": (c_i64, [c_void, c_int]),
     "grief_set_slab_budget": (None, [c_size]),
     "grief_set_gemm_mode": (None, [c_int]),
     "grief_get_gemm_mode": (c_int, []),

@@ -19,9 +19,8 @@ int launch_phi_t_vec(const Plan* pl, const double* T, int64_t n, const double* v
 int launch_phi_vec(const Plan* pl, const double* T, int64_t n, const double* v, double* out, cudaStream_t stream);
 int launch_sumsq(const double* y, int64_t n, double* out, double* ws, cudaStream_t stream);
 size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms);
-void set_slab_budget(size_t bytes);
-int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, void* workspace, size_t ws_bytes,
-                int sms, cudaStream_t stream, int* launches);
+int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, const double* y, int64_t n, double* r,
+                void* workspace, size_t ws_bytes, int sms, cudaStream_t stream, int* launches);
 int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const double* logeig_host, int p, int32_t* idx_dev,
                 double* loglam_dev, int* n_out_host, cudaStream_t stream, int* launches);
 
@@ -50,6 +49,14 @@ static int64_t slab_rows_for(int64_t n, int sms) {
   return std::min<int64_t>(n128, (int64_t)sms * kRowBlock * 2);
 }
 static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+// a plan's buffers live on the device that was current when it was created
+#define GRIEF_PLAN_DEVICE(pl_)                                                                                          \
+  do {                                                                                                                  \
+    int dev__ = -1;                                                                                                     \
+    cudaGetDevice(&dev__);                                                                                              \
+    GRIEF_REQUIRE(dev__ == (pl_)->device, "plan was created on device %d, the current device is %d", (pl_)->device, dev__); \
+  } while (0)
 
 static int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -136,7 +143,8 @@ int grief_plan_info(const grief_plan* plan, int what) {
 int64_t grief_table_rows(int64_t n) { return (n + kRowBlock - 1) / kRowBlock * kRowBlock; }
 
 int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, double* T_dev, void* stream) {
-  GRIEF_REQUIRE(plan && T_dev && (X_dev || n == 0), "grief_build_tables: null pointer");
+  GRIEF_REQUIRE(plan && (n == 0 || (T_dev && X_dev)), "grief_build_tables: null pointer");
+  GRIEF_PLAN_DEVICE(plan->impl);
   GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d, "grief_build_tables: n=%lld ldx=%lld d=%d", (long long)n, (long long)ldx, plan->impl->d);
   int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, -1);
   if (rc == GRIEF_OK && n > 0) g_launches += 1;
@@ -144,7 +152,8 @@ int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx,
 }
 
 int grief_build_tables_dx(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, int dim, double* T_dev, void* stream) {
-  GRIEF_REQUIRE(plan && T_dev && (X_dev || n == 0), "grief_build_tables_dx: null pointer");
+  GRIEF_REQUIRE(plan && (n == 0 || (T_dev && X_dev)), "grief_build_tables_dx: null pointer");
+  GRIEF_PLAN_DEVICE(plan->impl);
   GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d, "grief_build_tables_dx: n=%lld ldx=%lld d=%d", (long long)n, (long long)ldx, plan->impl->d);
   GRIEF_REQUIRE(dim >= 0 && dim < plan->impl->d, "grief_build_tables_dx: dim=%d outside [0,%d)", dim, plan->impl->d);
   int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, dim);
@@ -159,20 +168,61 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
   return rc;
 }
 
-void grief_set_slab_budget(size_t bytes) { set_slab_budget(bytes); }
-void grief_set_gemm_mode(int mode) { set_gemm_mode(mode & 1); ozaki_set_cluster((mode >> 1) & 1); }
-int grief_get_gemm_mode(void) { return gemm_mode(); }
+// ---- options: thread-local defaults for new plans, and per-plan values ----
+static int set_opt(PlanOpts& o, int what, int64_t value) {
+  switch (what) {
+    case GRIEF_OPT_GEMM_MODE:
+      GRIEF_REQUIRE(value == 0 || value == 1 || value == 3, "option gemm_mode: %lld is not 0, 1 or 3", (long long)value);
+      o.gemm_mode = (int)(value & 1); o.cluster = (int)((value >> 1) & 1);
+      return GRIEF_OK;
+    case GRIEF_OPT_DIGITS_GRAM:
+    case GRIEF_OPT_DIGITS_Z:
+      GRIEF_REQUIRE(value >= kOzMinDigits && value <= kOzMaxDigits, "option digits: %lld outside [%d,%d]", (long long)value, kOzMinDigits, kOzMaxDigits);
+      (what == GRIEF_OPT_DIGITS_GRAM ? o.digits_gram : o.digits_z) = (int)value;
+      return GRIEF_OK;
+    case GRIEF_OPT_SLAB_BUDGET:
+      GRIEF_REQUIRE(value >= 0, "option slab_budget: %lld", (long long)value);
+      o.slab_budget = value ? (size_t)value : ((size_t)4 << 30);
+      return GRIEF_OK;
+    default: return fail(GRIEF_ERR_BAD_ARG, "unknown option %d", what);
+  }
+}
+static int64_t get_opt(const PlanOpts& o, int what) {
+  switch (what) {
+    case GRIEF_OPT_GEMM_MODE: return o.gemm_mode | (o.cluster << 1);
+    case GRIEF_OPT_DIGITS_GRAM: return o.digits_gram;
+    case GRIEF_OPT_DIGITS_Z: return o.digits_z;
+    case GRIEF_OPT_SLAB_BUDGET: return (int64_t)o.slab_budget;
+    default: return -1;
+  }
+}
+int grief_set_default_option(int what, int64_t value) { return set_opt(default_plan_opts(), what, value); }
+int64_t grief_get_default_option(int what) { return get_opt(default_plan_opts(), what); }
+int grief_plan_set_option(grief_plan* plan, int what, int64_t value) {
+  GRIEF_REQUIRE(plan != nullptr, "grief_plan_set_option: null plan");
+  return set_opt(plan->impl->opts, what, value);
+}
+int64_t grief_plan_get_option(const grief_plan* plan, int what) { return plan ? get_opt(plan->impl->opts, what) : -1; }
+void grief_set_slab_budget(size_t bytes) { set_opt(default_plan_opts(), GRIEF_OPT_SLAB_BUDGET, (int64_t)bytes); }
+void grief_set_gemm_mode(int mode) { set_opt(default_plan_opts(), GRIEF_OPT_GEMM_MODE, mode); }
+int grief_get_gemm_mode(void) { return default_plan_opts().gemm_mode; }
 
 size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n) {
   return gram_workspace_bytes(plan->impl, grief_table_rows(n), sm_count());
 }
 int grief_gram(const grief_plan* plan, const double* T_dev, int64_t n, double* A_dev, int64_t lda, void* workspace_dev,
                size_t workspace_bytes, void* stream) {
+  return grief_gram_ry(plan, T_dev, n, nullptr, A_dev, lda, nullptr, workspace_dev, workspace_bytes, stream);
+}
+int grief_gram_ry(const grief_plan* plan, const double* T_dev, int64_t n, const double* y_dev, double* A_dev, int64_t lda, double* r_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream) {
   GRIEF_REQUIRE(plan && A_dev && workspace_dev && (T_dev || n == 0), "grief_gram: null pointer");
+  GRIEF_REQUIRE(r_dev == nullptr || y_dev != nullptr || n == 0, "grief_gram_ry: r needs y");
   GRIEF_REQUIRE(lda >= plan->impl->p, "grief_gram: lda=%lld < p=%d", (long long)lda, plan->impl->p);
-  int rc = launch_gram(plan->impl, T_dev, grief_table_rows(n), A_dev, lda, workspace_dev, workspace_bytes, sm_count(),
+  GRIEF_PLAN_DEVICE(plan->impl);
+  int rc = launch_gram(plan->impl, T_dev, grief_table_rows(n), A_dev, lda, y_dev, n, r_dev, workspace_dev, workspace_bytes, sm_count(),
                        (cudaStream_t)stream, &g_launches);
-  if (rc == GRIEF_OK && gemm_mode() == 1) rc = ozaki_check((cudaStream_t)stream);
+  if (rc == GRIEF_OK && plan->impl->opts.gemm_mode == 1) rc = ozaki_check(plan->impl->d_err, (cudaStream_t)stream);
   return rc;
 }
 
@@ -231,6 +281,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   GRIEF_REQUIRE(plan && plan->impl->grad, "grief_grad_theta: call grief_grad_setup first");
   GRIEF_REQUIRE(G2_dev && b_dev && grad_dev && workspace_dev && (n == 0 || (T_dev && X_dev && y_dev)), "grief_grad_theta: null pointer");
   GRIEF_REQUIRE(workspace_bytes >= grief_grad_workspace_bytes(plan, n), "grief_grad_theta: workspace too small");
+  GRIEF_PLAN_DEVICE(plan->impl);
   const Plan* pl = plan->impl;
   const GradDesc* gd = pl->grad;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -266,7 +317,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   }
   rc = launch_reduce_partials(partial, contract_blocks(sms), na, grad_dev, stream);
   if (rc == GRIEF_OK) g_launches += 1;
-  if (rc == GRIEF_OK && gemm_mode() == 1) rc = ozaki_check(stream);
+  if (rc == GRIEF_OK && pl->opts.gemm_mode == 1) rc = ozaki_check(pl->d_err, stream);
   return rc;
 }
 
@@ -280,6 +331,7 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
                         void* workspace_dev, size_t workspace_bytes, void* stream_) {
   GRIEF_REQUIRE(plan && B_dev && workspace_dev && (n == 0 || (T_dev && q_dev)), "grief_quadform_rows: null pointer");
   GRIEF_REQUIRE(workspace_bytes >= grief_quadform_workspace_bytes(plan, n), "grief_quadform_rows: workspace too small");
+  GRIEF_PLAN_DEVICE(plan->impl);
   const Plan* pl = plan->impl;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int sms = sm_count();
@@ -303,7 +355,7 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
     if (rc != GRIEF_OK) return rc;
     g_launches += 1;
   }
-  return gemm_mode() == 1 ? ozaki_check(stream) : GRIEF_OK;
+  return pl->opts.gemm_mode == 1 ? ozaki_check(pl->d_err, stream) : GRIEF_OK;
 }
 
 int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M, int N, int K,

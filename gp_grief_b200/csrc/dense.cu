@@ -237,11 +237,8 @@ int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, doubl
   prm.split_chunks = splits > 1 ? (chunks + splits - 1) / splits : 0;
   prm.c_split_stride = o.c_split_stride;
   const size_t smem = 1024 + 1024 + (size_t)kGemmStages * kGemmStageBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // function attributes are per device: set on every launch (a host-side table lookup in the runtime)
+  GRIEF_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prm.m_valid = m_valid;
   prm.n_valid = n_valid;
   prm.tiles_m = M / kDB;
@@ -490,11 +487,7 @@ int dense_work_reserve(DenseWork* wk, int q) {
 // zeroed, blocks above the diagonal keep their input values and are never read).  Inverses of the diagonal blocks -> wk->Linv.
 int dense_potrf(DenseWork* wk, int q, int* d_info, cudaStream_t stream, int* launches) {
   const size_t smem = ((size_t)kDB * (kDB + 1) + kDB + 1) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  GRIEF_CUDA(cudaFuncSetAttribute(k_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
   double* A = wk->P;
   for (int k0 = 0; k0 < q; k0 += kDB) {
     k_potf2_inv<<<1, 512, smem, stream>>>(A, q, k0, wk->Linv + (size_t)(k0 / kDB) * kDB * kDB, d_info);

@@ -1,16 +1,21 @@
 // FP64 GEMM on the INT8 tensor cores (Ozaki splitting, tcgen05 kind::i8) -- the fast path of both O(n p^2) products.
 //
 //   C (M x N, f64) (+)= A (M x K, f64) * B (N x K, f64)^T
-// Every operand row is scaled by a power of two so that |x| < 1 and cut into S = 7 balanced 8-bit digits (54 bits + sign):
-//   x 2^-e = sum_s d_s 2^(-6 - 8 s),   A B^T = sum_{a,b} 2^(-12 - 8 (a + b)) D_a(A) D_b(B)^T,   pairs with a + b <= 6 kept (28 of 49;
-//   what is dropped is below 2^-54 of the row-scale product).  Each digit product is an exact int8 x int8 -> int32 GEMM; one
-//   accumulation covers at most 16384 values of K (7 pairs x 2^14 x 2^14 < 2^31), longer K is split over blockIdx.z.
+// Every operand row is scaled by a power of two so that |x| < 1 and cut into SD balanced 8-bit digits (SD = 4..7; 8 SD - 2 bits
+// + sign, rounded to nearest):
+//   x 2^-e = sum_s d_s 2^(-6 - 8 s),   A B^T = sum_{a,b} 2^(-12 - 8 (a + b)) D_a(A) D_b(B)^T,   pairs with a + b <= SD - 1 kept
+//   (SD (SD + 1) / 2 products: 28 / 21 / 15 / 10; what is dropped is below ~2^(2 - 8 SD) of the row-scale product).  Each digit
+//   product is an exact int8 x int8 -> int32 GEMM; one accumulation covers at most 16384 values of K (7 pairs x 2^14 x 2^14 < 2^31),
+//   longer K is split over blockIdx.z.
 // Kernel: one CTA per 128 x 128 tile.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b;
-// two sweeps over K (g = 6..3 with all 7 + 7 digit planes, then g = 2..0 with digits 0..2), each followed by a drain.  All digit
-// planes a sweep needs for one 32-byte K chunk sit in shared memory (3-D TMA boxes over [digit][row][32 B], SWIZZLE_32B, three
-// 56 KB stages); warp 4 = TMA producer, warp 5 = MMA issuer (one thread, tcgen05.mma.cta_group::1.kind::i8, M = N = 128, K = 32),
-// warps 0-3 drain TMEM: tcgen05.ld -> f64 -> sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared memory
-// -> added to C.  k_ozaki<2> computes 256 x 128 tiles with CTA pairs and tcgen05.mma.cta_group::2 (see the template comment).
+// two sweeps over K (g = SD-1..SD-4 with all SD + SD digit planes, then g = SD-5..0 with digits 0..SD-5; the second sweep walks K
+// backwards so that it starts on the chunks the first one left in L2), each followed by a drain.  All digit planes a sweep needs
+// for one 32-byte K chunk sit in shared memory (3-D TMA boxes over [digit][row][32 B], SWIZZLE_32B; three 56 KB stages at SD = 7,
+// more at fewer digits); warp 4 = TMA producer, warp 5 = MMA issuer (one thread, tcgen05.mma.cta_group::1.kind::i8, M = N = 128,
+// K = 32), warps 0-3 drain TMEM: tcgen05.ld -> f64 -> sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared
+// memory -> added to C.  The six tensor maps travel as __grid_constant__ kernel parameters (no descriptor is ever re-written in
+// global memory).  Tiles are rasterised in groups of `group_n` column tiles so that the B digits of a group stay L2-resident while
+// all row tiles pass.  k_ozaki<2, SD> computes 256 x 128 tiles with CTA pairs and tcgen05.mma.cta_group::2 (see the template comment).
 // Measured (B200, pass-2 shape 37888 x 4096 x 4096): 14.4 ms = 88 TFLOP/s FP64-equivalent alone, 81 inside the benchmark (power
 // cap), against 35 for cuBLAS DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
 // Variants measured and not adopted (profiles/r01_gram_design_notes.md): 128 x 256 tiles with two accumulators and five work
@@ -26,19 +31,23 @@
 
 namespace grief {
 
-constexpr int S = 7;                     // balanced 8-bit digits per operand (54 bits + sign)
 constexpr int TM = 128, TN = 128, KC = 32;
 constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // one digit plane of a tile and K chunk: 4 KB each
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
+constexpr int kStageBudget = 196 * 1024;                       // bytes of shared memory for the operand ring
 
 // Work items.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b:
-//   item 0: g = 6, 5, 4, 3   all 7 + 7 digit planes, 22 MMAs per K chunk, 56 KB per stage
-//   item 1: g = 2, 1, 0      digits 0..2 of both,     6 MMAs per K chunk, 24 KB per stage
-// Two sweeps over K per tile, two drains; 80 KB of digits per 28 MMAs and chunk.
-constexpr int kNumItems = 2;
-__device__ __forceinline__ int item_g_hi(int it) { return it == 0 ? 6 : 2; }
-__device__ __forceinline__ int item_g_lo(int it) { return it == 0 ? 3 : 0; }
-__device__ __forceinline__ int item_digits(int it) { return it == 0 ? 7 : 3; }
+//   item 0: g = SD-1 .. SD-4   all SD + SD digit planes   (SD = 7: 22 MMAs per K chunk, 56 KB per stage)
+//   item 1: g = SD-5 .. 0      digits 0 .. SD-5 of both   (SD = 7:  6 MMAs per K chunk, 24 KB per stage); absent at SD = 4
+// Two sweeps over K per tile, two drains.
+template <int SD> __device__ __forceinline__ constexpr int num_items() { return SD > 4 ? 2 : 1; }
+template <int SD> __device__ __forceinline__ int item_g_hi(int it) { return it == 0 ? SD - 1 : SD - 5; }
+template <int SD> __device__ __forceinline__ int item_g_lo(int it) { return it == 0 ? (SD > 4 ? SD - 4 : 0) : 0; }
+template <int SD> __device__ __forceinline__ int item_digits(int it) { return it == 0 ? SD : SD - 4; }
+
+constexpr int oz_stage_bytes(int cl, int sd) { return sd * (A_SLICE + B_SLICE / cl); }
+constexpr int oz_stages(int cl, int sd) { return kStageBudget / oz_stage_bytes(cl, sd) > 6 ? 6 : kStageBudget / oz_stage_bytes(cl, sd); }
+constexpr size_t oz_smem_bytes(int cl, int sd) { return 1024 + 4096 + 20480 + 1024 + (size_t)oz_stages(cl, sd) * oz_stage_bytes(cl, sd); }
 
 __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
   for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
@@ -69,15 +78,14 @@ __global__ void k_row_exp(const double* __restrict__ X, int64_t ld, int K, int* 
     exps[r] = e;
   }
 }
-// planes[s][r][k] = balanced digit s of trunc(X[r][k] * 2^(54 - exps[r])):  x 2^-e = sum_s d_s 2^(-6 - 8 s)
-__global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, int kp, const int* __restrict__ exps,
+// planes[s][r][k] = balanced digit s of rint(X[r][k] * 2^(8 sd - 2 - exps[r])):  x 2^-e = sum_s d_s 2^(-6 - 8 s)
+__global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, int kp, int sd, const int* __restrict__ exps,
                         int8_t* __restrict__ planes) {
   const size_t plane = (size_t)R * kp;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(e / kp), k = (int)(e - (size_t)r * kp);
-    long long v = (k < K) ? __double2ll_rz(ldexp(X[(size_t)r * ld + k], 54 - exps[r])) : 0;    // |v| < 2^54, exact
-#pragma unroll
-    for (int s = S - 1; s >= 0; --s) {
+    long long v = (k < K) ? __double2ll_rn(ldexp(X[(size_t)r * ld + k], 8 * sd - 2 - exps[r])) : 0;    // |v| <= 2^(8 sd - 2), exact
+    for (int s = sd - 1; s >= 0; --s) {
       const int d = (int)(int8_t)(v & 0xFF);
       planes[(size_t)s * plane + e] = (int8_t)d;
       v = (v - d) >> 8;
@@ -85,16 +93,18 @@ __global__ void k_slice(const double* __restrict__ X, int64_t ld, int R, int K, 
   }
 }
 
+struct OzMaps { CUtensorMap m[6]; };   // A heavy, A light, B heavy, B light, B half rows heavy, B half rows light
+
 struct OzParams {
   double* C; int64_t ldc;
   const int* ea; const int* eb;      // row exponents of A and B, padded with zeros to multiples of 128
-  const CUtensorMap* maps;           // A depth 7, A depth 3, B depth 7, B depth 3, B half rows depth 7, B half rows depth 3
   int chunks;                        // 32-byte K chunks in total
   int split_chunks;                  // chunks per blockIdx.z (== chunks when K is not split)
   int64_t c_split_stride;            // split z writes C + z * c_split_stride
   int m_valid, n_valid;              // elements of C that exist
   int lower_only;                    // skip tiles entirely above the diagonal
   int accumulate;                    // 1: C += result, 0: C = result
+  int group_n;                       // column tiles per rasterisation group (CL = 1; 0: plain row-major tile order)
   int* err;
 };
 
@@ -103,19 +113,32 @@ struct OzParams {
 // (M = 256, N = 128, K = 32), each CTA's TMEM receives its 128 rows of the four accumulators and each CTA drains its own rows.
 // Both CTAs' TMA loads complete on the LEADER's full barrier (peer bit of the barrier address cleared), the leader's commits are
 // multicast to both CTAs' empty / tfull barriers, the drain threads of both CTAs arrive on the leader's tfree barrier.
-template <int CL>
-__global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
+// SD = digits per operand.
+template <int CL, int SD>
+__global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps maps, const OzParams prm) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  const uint32_t full = base, empty = base + 32, tfull = base + 64, tfree = base + 72, slot = base + 80;
+  const uint32_t full = base, empty = base + 64, tfull = base + 128, tfree = base + 136, slot = base + 144;
   const uint32_t cscale = base + 1024;               // 128 doubles: 2^eb of the tile's columns
   const uint32_t stagebuf = base + 4096;             // 4 warps x 32 rows x 17 doubles (transpose staging for coalesced stores)
   const uint32_t ring = base + 4096 + 20480;         // 1024-aligned
   constexpr int kBSlice = B_SLICE / CL;              // this CTA's share of a B digit plane: 128 or 64 rows of 32 bytes
-  constexpr int kStageBytes = S * (A_SLICE + kBSlice);
-  constexpr int kStages = CL == 2 ? 4 : 3;
+  constexpr int kStageBytes = oz_stage_bytes(CL, SD);
+  constexpr int kStages = oz_stages(CL, SD);
+  constexpr int kNumItems = num_items<SD>();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bn = CL == 2 ? blockIdx.y : blockIdx.x, bm = CL == 2 ? blockIdx.x : blockIdx.y;   // CTA pairs are adjacent in x
+  int bn = CL == 2 ? blockIdx.y : blockIdx.x, bm = CL == 2 ? blockIdx.x : blockIdx.y;   // CTA pairs are adjacent in x
+  if (CL == 1 && prm.group_n > 0) {                  // grouped rasterisation: all row tiles pass over group_n column tiles at a time
+    const int tiles_n = gridDim.x, tiles_m = gridDim.y;
+    const int L = (int)blockIdx.y * tiles_n + (int)blockIdx.x;
+    const int per_group = prm.group_n * tiles_m;
+    const int grp = L / per_group;
+    const int first = grp * prm.group_n;
+    const int gw = min(prm.group_n, tiles_n - first);
+    const int within = L - grp * per_group;
+    bm = within / gw;
+    bn = first + (within - bm * gw);
+  }
   if (prm.lower_only && bn > (CL == 2 ? (bm | 1) : bm)) return;      // uniform over the cluster
   uint32_t crank = 0;
   if (CL == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -166,28 +189,29 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
   if (tid == 128) {                                 // ---- TMA producer (warp 4) ----
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
-      const int nd = item_digits(it);
+      const int nd = item_digits<SD>(it);
       const uint32_t bytes = (uint32_t)(nd * (A_SLICE + kBSlice));
-      const CUtensorMap* mA = prm.maps + (it == 0 ? 0 : 1);
-      const CUtensorMap* mB = prm.maps + (CL == 2 ? (it == 0 ? 4 : 5) : (it == 0 ? 2 : 3));
+      const CUtensorMap* mA = &maps.m[it == 0 ? 0 : 1];
+      const CUtensorMap* mB = &maps.m[CL == 2 ? (it == 0 ? 4 : 5) : (it == 0 ? 2 : 3)];
       for (int c = 0; c < nk && ok; ++c, ++q) {
         const int s = q % kStages;
         if (q >= kStages) ok = wait_bounded(empty + 8 * s, (uint32_t)(((q / kStages) - 1) & 1));
         if (!ok) break;
         const uint32_t dst = ring + s * kStageBytes, bar = full + 8 * s;
+        const int kc = (c_begin + (it == 0 ? c : nk - 1 - c)) * KC;      // the second sweep walks K backwards (L2 reuse; integer sums commute)
         if (CL == 1) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
           asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-                       "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(bar) : "memory");
+                       "l"(mA), "r"(kc), "r"(bm * TM), "r"(0), "r"(bar) : "memory");
           asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                           dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN), "r"(0), "r"(bar) : "memory");
+                           dst + nd * A_SLICE), "l"(mB), "r"(kc), "r"(bn * TN), "r"(0), "r"(bar) : "memory");
         } else {                                    // both CTAs' bytes are counted on the leader's barrier
           const uint32_t lbar = bar & 0xFEFFFFFFu;
           if (leader) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
           asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                           dst), "l"(mA), "r"((c_begin + c) * KC), "r"(bm * TM), "r"(0), "r"(lbar) : "memory");
+                           dst), "l"(mA), "r"(kc), "r"(bm * TM), "r"(0), "r"(lbar) : "memory");
           asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                           dst + nd * A_SLICE), "l"(mB), "r"((c_begin + c) * KC), "r"(bn * TN + (int)crank * (TN / 2)), "r"(0), "r"(lbar) : "memory");
+                           dst + nd * A_SLICE), "l"(mB), "r"(kc), "r"(bn * TN + (int)crank * (TN / 2)), "r"(0), "r"(lbar) : "memory");
         }
       }
     }
@@ -197,7 +221,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
     const uint64_t dhi = (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);   // K-major SWIZZLE_32B: LBO 1, SBO 256 B, v1
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
-      const int nd = item_digits(it), g_hi = item_g_hi(it), g_lo = item_g_lo(it);
+      const int nd = item_digits<SD>(it), g_hi = item_g_hi<SD>(it), g_lo = item_g_lo<SD>(it);
       if (it > 0) ok = wait_bounded(tfree, (uint32_t)((it - 1) & 1));     // accumulators drained
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -214,7 +238,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
           if (g < g_lo) break;
           uint32_t accf = c > 0 ? 1u : 0u;
 #pragma unroll
-          for (int a = 0; a < S; ++a) {
+          for (int a = 0; a < SD; ++a) {
             const int b = g - a;
             if (a >= nd || b < 0 || b >= nd) continue;
             const uint64_t da = da0 + (uint64_t)(a * (A_SLICE >> 4)), db = db0 + (uint64_t)(b * (kBSlice >> 4));
@@ -252,7 +276,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const OzParams prm) {
       live = wait_bounded(tfull, (uint32_t)(it & 1));
       if (!live) { if (lane == 0) atomicExch(prm.err, 3); break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int g_hi = item_g_hi(it), ng = g_hi - item_g_lo(it) + 1;
+      const int g_hi = item_g_hi<SD>(it), ng = g_hi - item_g_lo<SD>(it) + 1;
       double wgt[4];
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) wgt[gi] = gi < ng ? ldexp(1.0, -12 - 8 * (g_hi - gi)) * rs : 0.0;
@@ -324,7 +348,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn3 encode_fn3() {
-  static EncodeTiledFn3 fn = nullptr;
+  static EncodeTiledFn3 fn = nullptr;            // a driver entry point: the same for every device and thread
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -335,11 +359,11 @@ static EncodeTiledFn3 encode_fn3() {
   return fn;
 }
 
-// planes: [S][rows_alloc][kp] int8; rows beyond `rows` read as zeros (TMA out-of-bounds fill)
-static int make_plane_map(CUtensorMap* m, const int8_t* planes, int rows, int64_t rows_alloc, int kp, int box_rows, int depth) {
+// planes: [digits][rows_alloc][kp] int8; rows beyond `rows` read as zeros (TMA out-of-bounds fill)
+static int make_plane_map(CUtensorMap* m, const int8_t* planes, int rows, int64_t rows_alloc, int kp, int box_rows, int depth, int digits) {
   EncodeTiledFn3 enc = encode_fn3();
-  if (!enc) return fail(GRIEF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t gdim[3] = {(cuuint64_t)kp, (cuuint64_t)rows, (cuuint64_t)S};
+  if (!enc) return fail(GRIEF_ERR_LIBRARY, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[3] = {(cuuint64_t)kp, (cuuint64_t)rows, (cuuint64_t)digits};
   const cuuint64_t gstr[2] = {(cuuint64_t)kp, (cuuint64_t)kp * (cuuint64_t)rows_alloc};
   const cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, (cuuint32_t)depth};
   const cuuint32_t es[3] = {1, 1, 1};
@@ -349,103 +373,107 @@ static int make_plane_map(CUtensorMap* m, const int8_t* planes, int rows, int64_
   return GRIEF_OK;
 }
 
-static int* g_oz_err = nullptr;        // device error flag shared by all launches of this process
-static CUtensorMap* g_oz_maps = nullptr;   // ring of device-resident tensor-map sets (12 maps per launch)
-static int g_oz_map_slot = 0;
-static int g_oz_cluster = 0;           // CTA pairs with cta_group::2 MMAs (ozaki_set_cluster).  Measured at C3: correct, and no
-                                       // faster than single CTAs (402 vs 423 ms per 1M rows in pass 2; the clock drops further
-                                       // under sw_power_cap, 1747 -> 1691 MHz); kept selectable for the next round
-constexpr int kMapSlots = 64;
+// Planes are always laid out for kOzMaxDigits digits (buffer sizes do not depend on the digit count in use).
+size_t ozaki_plane_bytes(int64_t rows, int K) { return (size_t)kOzMaxDigits * (size_t)rows * (size_t)((K + KC - 1) / KC * KC); }
 
-// Device flag raised by the kernels of the INT8 path: 1-3 = a barrier wait of k_ozaki timed out, 4 = a non-finite operand value.
-int* ozaki_err_flag() {
-  if (!g_oz_err) {
-    if (cudaMalloc(reinterpret_cast<void**>(&g_oz_err), sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(g_oz_err, 0, sizeof(int));
-  }
-  return g_oz_err;
-}
-
-size_t ozaki_plane_bytes(int64_t rows, int K) { return (size_t)S * (size_t)rows * (size_t)((K + KC - 1) / KC * KC); }
-
-// exps[r] (r < rows; entries up to exps_len are zeroed) and digit planes of X (rows x K, ld); planes: [S][rows][kp], kp = K rounded up to 32
-int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exps_len, int8_t* planes, cudaStream_t stream) {
+// exps[r] (r < rows; entries up to exps_len are zeroed) and digit planes of X (rows x K, ld); planes: [digits][rows][kp], kp = K rounded up to 32
+int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exps_len, int8_t* planes, int digits, int* err, cudaStream_t stream) {
   if (rows == 0) return GRIEF_OK;
+  GRIEF_REQUIRE(digits >= kOzMinDigits && digits <= kOzMaxDigits, "ozaki_slice: %d digits outside [%d,%d]", digits, kOzMinDigits, kOzMaxDigits);
   const int kp = (K + KC - 1) / KC * KC;
   if (exps_len > rows) GRIEF_CUDA(cudaMemsetAsync(exps + rows, 0, (size_t)(exps_len - rows) * sizeof(int), stream));
-  k_row_exp<<<rows, 256, 0, stream>>>(X, ld, K, exps, ozaki_err_flag());
-  k_slice<<<148 * 8, 256, 0, stream>>>(X, ld, rows, K, kp, exps, planes);
+  k_row_exp<<<rows, 256, 0, stream>>>(X, ld, K, exps, err);
+  k_slice<<<148 * 8, 256, 0, stream>>>(X, ld, rows, K, kp, digits, exps, planes);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
 
-// C (M x N, ldc) (+)= A B^T from digit planes.  pa: [S][rows_a_alloc][kp] with M valid rows, ea: >= round_up(M,128) exponents;
+template <int CL, int SD>
+static int launch_ozaki(const OzMaps& maps, const OzParams& prm, dim3 grid, cudaStream_t stream) {
+  constexpr size_t smem = oz_smem_bytes(CL, SD);
+  static_assert(smem <= 227 * 1024, "k_ozaki: shared memory");
+  // function attributes are per device: set on every launch (a host-side table lookup in the runtime)
+  GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<CL, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GRIEF_CUDA(cudaLaunchKernelEx(&cfg, k_ozaki<CL, SD>, maps, prm));
+  } else {
+    k_ozaki<CL, SD><<<grid, 192, smem, stream>>>(maps, prm);
+  }
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+// C (M x N, ldc) (+)= A B^T from digit planes.  pa: [digits][rows_a_alloc][kp] with M valid rows, ea: >= round_up(M,128) exponents;
 // pb likewise with N rows and >= round_up(N,256) exponents.  K <= 16384 * splits.
 int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, const int8_t* pb, int64_t rows_b_alloc, const int* eb, int N,
-               int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, cudaStream_t stream,
-               int* launches) {
+               int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, const OzOpts& opt,
+               cudaStream_t stream, int* launches) {
   if (M <= 0 || N <= 0) return GRIEF_OK;
+  const int SD = opt.digits;
+  GRIEF_REQUIRE(SD >= kOzMinDigits && SD <= kOzMaxDigits, "ozaki_gemm: %d digits outside [%d,%d]", SD, kOzMinDigits, kOzMaxDigits);
+  GRIEF_REQUIRE(opt.err != nullptr, "ozaki_gemm: no error flag");
   const int kp = (K + KC - 1) / KC * KC;
   const int chunks = kp / KC;
   splits = std::max(1, splits);
   const int split_chunks = (chunks + splits - 1) / splits;
   GRIEF_REQUIRE(split_chunks * KC <= 16384, "ozaki_gemm: %d values of K per accumulation exceed the int32 budget of 16384", split_chunks * KC);
-  if (ozaki_err_flag() == nullptr) return fail(GRIEF_ERR_CUDA, "ozaki_gemm: cudaMalloc of the error flag failed");
-  if (!g_oz_maps) GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_oz_maps), sizeof(CUtensorMap) * 6 * kMapSlots));
-  alignas(64) CUtensorMap hmaps[6];
-  memset(hmaps, 0, sizeof(hmaps));
+  alignas(64) OzMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int light = SD - 4;                          // digit planes of the second sweep (none at SD = 4)
   {
-    int rc = make_plane_map(&hmaps[0], pa, M, rows_a_alloc, kp, TM, 7);
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[1], pa, M, rows_a_alloc, kp, TM, 3);
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[2], pb, N, rows_b_alloc, kp, TN, 7);
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[3], pb, N, rows_b_alloc, kp, TN, 3);
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[4], pb, N, rows_b_alloc, kp, TN / 2, 7);      // half of the B rows (CTA-pair path)
-    if (rc == GRIEF_OK) rc = make_plane_map(&hmaps[5], pb, N, rows_b_alloc, kp, TN / 2, 3);
+    int rc = make_plane_map(&maps.m[0], pa, M, rows_a_alloc, kp, TM, SD, SD);
+    if (rc == GRIEF_OK) rc = make_plane_map(&maps.m[2], pb, N, rows_b_alloc, kp, TN, SD, SD);
+    if (rc == GRIEF_OK) rc = make_plane_map(&maps.m[4], pb, N, rows_b_alloc, kp, TN / 2, SD, SD);      // half of the B rows (CTA-pair path)
+    if (light > 0) {
+      if (rc == GRIEF_OK) rc = make_plane_map(&maps.m[1], pa, M, rows_a_alloc, kp, TM, light, SD);
+      if (rc == GRIEF_OK) rc = make_plane_map(&maps.m[3], pb, N, rows_b_alloc, kp, TN, light, SD);
+      if (rc == GRIEF_OK) rc = make_plane_map(&maps.m[5], pb, N, rows_b_alloc, kp, TN / 2, light, SD);
+    }
     if (rc != GRIEF_OK) return rc;
   }
-  CUtensorMap* dmaps = g_oz_maps + 6 * (g_oz_map_slot++ % kMapSlots);
-  GRIEF_CUDA(cudaMemcpyAsync(dmaps, hmaps, sizeof(hmaps), cudaMemcpyHostToDevice, stream));
   OzParams prm;
-  prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb; prm.maps = dmaps;
+  prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb;
   prm.chunks = chunks; prm.split_chunks = split_chunks; prm.c_split_stride = c_split_stride;
-  prm.m_valid = M; prm.n_valid = N; prm.lower_only = lower_only ? 1 : 0; prm.accumulate = accumulate ? 1 : 0; prm.err = g_oz_err;
-  const size_t smem1 = 1024 + 4096 + 20480 + 1024 + (size_t)3 * S * (A_SLICE + B_SLICE);
-  const size_t smem2 = 1024 + 4096 + 20480 + 1024 + (size_t)4 * S * (A_SLICE + B_SLICE / 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    attr_set = true;
-  }
+  prm.m_valid = M; prm.n_valid = N; prm.lower_only = lower_only ? 1 : 0; prm.accumulate = accumulate ? 1 : 0; prm.err = opt.err;
   const int tiles_m = (M + TM - 1) / TM, tiles_n = (N + TN - 1) / TN;
-  if (g_oz_cluster && tiles_m >= 2) {               // CTA pairs adjacent in x (cluster (2,1,1)); an odd last pair runs one CTA on zero rows
-    dim3 grid((tiles_m + 1) / 2 * 2, tiles_n, splits);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    GRIEF_CUDA(cudaLaunchKernelEx(&cfg, k_ozaki<2>, prm));
-  } else {
-    dim3 grid(tiles_n, tiles_m, splits);
-    k_ozaki<1><<<grid, 192, smem1, stream>>>(prm);
+  // rasterisation: the B digit panels of one group of column tiles (128 rows x K of a CTA x SD bytes each) take <= ~60 MB of the 126 MB L2
+  prm.group_n = 0;
+  if (!lower_only && tiles_m > 1) {
+    const int64_t panel = (int64_t)TN * std::min<int64_t>(kp, (int64_t)split_chunks * KC) * SD;
+    const int gmax = (int)std::max<int64_t>(1, ((int64_t)60 << 20) / panel);
+    const int ngroups = (tiles_n + gmax - 1) / gmax;
+    prm.group_n = (tiles_n + ngroups - 1) / ngroups;
+    if (prm.group_n >= tiles_n) prm.group_n = 0;
   }
-  GRIEF_CUDA(cudaGetLastError());
+  const bool pairs = opt.cluster && tiles_m >= 2;     // CTA pairs adjacent in x (cluster (2,1,1)); an odd last pair runs one CTA on zero rows
+  const dim3 grid = pairs ? dim3((tiles_m + 1) / 2 * 2, tiles_n, splits) : dim3(tiles_n, tiles_m, splits);
+  int rc;
+#define GRIEF_OZ(SD_)                                                                                              \
+  case SD_: rc = pairs ? launch_ozaki<2, SD_>(maps, prm, grid, stream) : launch_ozaki<1, SD_>(maps, prm, grid, stream); break
+  switch (SD) {
+    GRIEF_OZ(4); GRIEF_OZ(5); GRIEF_OZ(6); GRIEF_OZ(7);
+    default: return fail(GRIEF_ERR_BAD_ARG, "ozaki_gemm: %d digits", SD);
+  }
+#undef GRIEF_OZ
+  if (rc != GRIEF_OK) return rc;
   if (launches) *launches += 1;
   return GRIEF_OK;
 }
 
-void ozaki_set_cluster(int on) { g_oz_cluster = on ? 1 : 0; }
-
-// Synchronises the stream and reports a pipeline failure inside any k_ozaki launch since the last check.
-int ozaki_check(cudaStream_t stream) {
-  if (!g_oz_err) return GRIEF_OK;
+// Synchronises the stream and reports a pipeline failure inside any k_ozaki launch on this flag since the last check.
+int ozaki_check(int* err, cudaStream_t stream) {
+  if (!err) return GRIEF_OK;
   int flag = 0;
-  GRIEF_CUDA(cudaMemcpyAsync(&flag, g_oz_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  GRIEF_CUDA(cudaMemcpyAsync(&flag, err, sizeof(int), cudaMemcpyDeviceToHost, stream));
   GRIEF_CUDA(cudaStreamSynchronize(stream));
   if (flag != 0) {
-    cudaMemsetAsync(g_oz_err, 0, sizeof(int), stream);
+    cudaMemsetAsync(err, 0, sizeof(int), stream);
     if (flag == 4) return fail(GRIEF_ERR_BAD_ARG, "non-finite value (NaN / Inf) in the basis matrix Phi or in the p x p operand");
     return fail(GRIEF_ERR_CUDA, "k_ozaki: barrier wait timed out in role %d (1 = TMA producer, 2 = MMA issuer, 3 = drain)", flag);
   }

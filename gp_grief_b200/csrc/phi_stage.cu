@@ -6,8 +6,9 @@
 //   pass 2 / predictive var.    Z = Phi B     :  Phi slab (R x p_pad, sorted columns contiguous)
 //                                               -> GEMM against the column-permuted symmetric B
 //
-// Two arithmetic modes (grief_set_gemm_mode): 1 (default) -- the builders emit power-of-two row scales and seven int8 digit planes
+// Two arithmetic modes (per plan, PlanOpts): 1 (default) -- the builders emit power-of-two row scales and 4..7 int8 digit planes
 // and k_ozaki (ozaki.cu) multiplies them on the tcgen05 INT8 tensor cores; 0 -- the builders emit the FP64 slab for k_gemm_nt.
+// r = Phi^T y is formed inside the pass-1 builder (the values are in registers there).
 //
 // Why staged and not fused (round-1 measurements, profiles/r01_gram_design_notes.md): DMUL, DFMA and DMMA share ONE FP64
 // pipe per SM sub-partition.  With the Phi tiles built inside the GEMM CTAs the builder's DMULs queue behind the DMMAs
@@ -47,67 +48,119 @@ __device__ __forceinline__ void stage_table_rows(double* sT, uint64_t* bar, cons
 }
 
 // What a builder launch produces: the FP64 slab (DMMA path), or -- for the INT8 path, which never stores the FP64 slab --
-// first the binary exponents of the operand rows' maxima, then the 7 balanced 8-bit digits of every element.
-enum BuildOut : int { OUT_F64 = 0, OUT_EXP = 1, OUT_DIGITS = 2 };
-constexpr int kDigits = 7;
+// the `sd` balanced 8-bit digits of every element, scaled by the power of two of its operand row (exponents come first).
+enum BuildOut : int { OUT_F64 = 0, OUT_DIGITS = 2 };
 
 // high word of |v|: orders like |v|, and its exponent field is all the INT8 path needs of a row maximum
 __device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
 // frexp exponent e (|x| < 2^e) from the high word of the row maximum (0 for an all-zero row)
-__device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? min(max((hi >> 20) - 1022, -900), 1024) : 0; }   // clamp: 2^(54-e) stays finite
-// digits d_s of q = trunc(v * scale), scale = 2^(54 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s), d_s in [-128, 127].
-// Balanced base-256 digits without a carry chain: add 128 to every byte position (q + 0x80..80 is positive and below 2^56),
-// then byte k of the sum, minus 128 (= XOR 0x80 read as int8), is the digit of 256^k.
-__device__ __forceinline__ void store_digits(double v, double scale, int8_t* __restrict__ base, size_t plane_stride) {
-  const unsigned long long w = ((unsigned long long)__double2ll_rz(v * scale) + 0x0080808080808080ull) ^ 0x0080808080808080ull;
+__device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? min(max((hi >> 20) - 1022, -900), 1024) : 0; }   // clamp: 2^(8 sd - 2 - e) stays finite
+// 2^(8 sd - 2 - e): multiplies a value below 2^e in magnitude into the range of sd digits
+__device__ __forceinline__ double digit_scale(int sd, int e) { return __hiloint2double((1023 + 8 * sd - 2 - e) << 20, 0); }
+// digits d_s of q = rint(v * scale), scale = 2^(8 sd - 2 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s), d_s in [-128, 127], s < sd.
+// Balanced base-256 digits without a carry chain: add 128 to every byte position (q + 0x80..80 is positive and below 2^(8 sd)),
+// then byte k of the sum, minus 128 (= XOR 0x80 read as int8), is the digit of 256^k.  Digit 0 (most significant) is moved to byte 6.
+__device__ __forceinline__ void store_digits(double v, double scale, int sd, int8_t* __restrict__ base, size_t plane_stride) {
+  const unsigned long long bias = 0x0080808080808080ull >> (8 * (7 - sd));
+  const unsigned long long w = (((unsigned long long)__double2ll_rn(v * scale) + bias) ^ bias) << (8 * (7 - sd));
   const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
   base[0 * plane_stride] = (int8_t)(hi >> 16);       // digit 0 = byte 6 (most significant)
   base[1 * plane_stride] = (int8_t)(hi >> 8);
   base[2 * plane_stride] = (int8_t)hi;
   base[3 * plane_stride] = (int8_t)(lo >> 24);
-  base[4 * plane_stride] = (int8_t)(lo >> 16);
-  base[5 * plane_stride] = (int8_t)(lo >> 8);
-  base[6 * plane_stride] = (int8_t)lo;
+  if (sd > 4) base[4 * plane_stride] = (int8_t)(lo >> 16);
+  if (sd > 5) base[5 * plane_stride] = (int8_t)(lo >> 8);
+  if (sd > 6) base[6 * plane_stride] = (int8_t)lo;
 }
 
-// Phi^T slab, c = sorted column.  Lane = data row; a warp walks a run of consecutive sorted columns, which share their
-// leading slots: the product P of the first G-1 factors stays in a register and is rebuilt only where sorted_level says a
-// leading factor changed (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
-//   OUT_F64:    out[c * ld + row]
-//   OUT_EXP:    atomicMax(col_hi[c], high word of |Phi[row][c]|) over the slab's rows (one REDUX per column and warp)
-//   OUT_DIGITS: planes[s][c][row] (row stride ld bytes, plane stride p_pad * ld), scaled by 2^(54 - exps[c])
-template <int G, int MODE>
+// ---- exponents of the Phi^T operand rows (= basis columns) of a slab, without a pass over Phi ----
+// |Phi[n][c]| = prod_g |T[n][slot_g(c)]| <= prod_g max_n |T[n][slot_g(c)]|: one sweep over the slab's TABLE rows (stride doubles per
+// data row instead of p) gives per-slot maxima, and the product of a column's G maxima bounds the column.  The bound costs at
+// most a bit or two of the 8 sd - 2 (the factors of a column peak at different rows); it replaces a second evaluation of all of Phi.
+__global__ void __launch_bounds__(256) k_slot_hi(const double* __restrict__ T, int stride, int64_t total, int* __restrict__ slot_hi) {
+  extern __shared__ int s_hi_slots[];
+  for (int s = threadIdx.x; s < stride; s += blockDim.x) s_hi_slots[s] = 0;
+  __syncthreads();
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int h = abs_hi(T[e]);
+    const int s = (int)(e % stride);
+    if (h > s_hi_slots[s]) atomicMax(s_hi_slots + s, h);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < stride; s += blockDim.x)
+    if (s_hi_slots[s] > 0) atomicMax(slot_hi + s, s_hi_slots[s]);
+}
+// exps[c] from the slot maxima (c = sorted column); entries c in [n, n_pad) are zeroed
+__global__ void k_col_exps(const int* __restrict__ slot_hi, const uint16_t* __restrict__ sorted_slot, int G, int n, int n_pad,
+                           int* __restrict__ exps, int* __restrict__ err) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) {
+    double bound = 1.0;
+    bool bad = false;
+    for (int g = 0; g < G; ++g) {
+      const int h = slot_hi[sorted_slot[(size_t)c * G + g]];
+      if (h >= 0x7ff00000 - 2) bad = true;            // Inf / NaN in a table entry
+      bound *= h > 0 ? __hiloint2double(h + 2, 0) : 0.0;   // the slot maximum rounded UP in its high word (covers the product's roundings)
+    }
+    const int hb = abs_hi(bound);
+    if (bad || hb >= 0x7ff00000) atomicExch(err, 4);
+    exps[c] = exp_from_hi(hb);
+  } else if (c < n_pad) exps[c] = 0;
+}
+
+// Phi^T slab, c = sorted column, one CTA per 128 table rows.  Lane = data row; each of the 16 warps owns p_pad / 16 consecutive
+// sorted columns and walks them for the four 32-row groups.  Consecutive sorted columns share their leading slots: the product P
+// of the first G-1 factors stays in a register per row group and is rebuilt only where sorted_level says a leading factor changed
+// (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
+//   DIG = false: out[c * ld + row]                                  (FP64 slab)
+//   DIG = true:  planes[s][c][row] (row stride ld bytes, plane stride p_pad * ld), scaled by 2^(8 sd - 2 - exps[c])
+// y != nullptr: the values are already in registers, so r_ws[block][c] = sum over the block's rows of y[row] * Phi[row][c] is formed
+// here (fixed order: lanes by butterfly, row groups in sequence) instead of rebuilding Phi a second time for Phi^T y.
+template <int G, bool DIG>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __restrict__ T, int stride,
                                                                const uint16_t* __restrict__ sorted_slot,
-                                                               const uint8_t* __restrict__ sorted_level, int p_pad, int n_blocks,
-                                                               double* __restrict__ out, int64_t ld, int* __restrict__ col_hi,
-                                                               const int* __restrict__ exps, int8_t* __restrict__ planes) {
+                                                               const uint8_t* __restrict__ sorted_level, int p_pad,
+                                                               double* __restrict__ out, int64_t ld, const int* __restrict__ exps,
+                                                               int8_t* __restrict__ planes, int sd, const double* __restrict__ y,
+                                                               int64_t y_rows, double* __restrict__ r_ws) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
-  int* s_hi = reinterpret_cast<int*>(smem_raw + 128 + (size_t)kBuildRows * stride * sizeof(double));   // OUT_EXP: p_pad column maxima
-  if constexpr (MODE == OUT_EXP)
-    for (int c = threadIdx.x; c < p_pad; c += kBuildThreads) s_hi[c] = 0;
   init_stage_barrier(bar);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = (warp & 3) * 32 + lane;
-  const double* trow = sT + (size_t)row * stride;
-  const int cpq = p_pad / 4;                           // four warps share a row group, a quarter of the columns each
-  const int c_begin = (warp >> 2) * cpq;
-  constexpr int NB = 8;
-  int use = 0;
-  for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x, ++use) {   // persistent over 128-row blocks
-    stage_table_rows(sT, bar, T, stride, rb, use);
-    const size_t grow = (size_t)rb * kBuildRows + row;
-    double P = 1.0;
-    for (int c0 = c_begin; c0 < c_begin + cpq; c0 += NB) {
-      double last[NB];
-      int lv[NB];
+  const int cpw = p_pad / (kBuildThreads / 32);        // columns per warp (p_pad is a multiple of 128)
+  const int c_begin = warp * cpw;
+  constexpr int NB = 8, RG = kBuildRows / 32;
+  const int64_t rb = blockIdx.x;
+  stage_table_rows(sT, bar, T, stride, rb, 0);
+  const size_t grow0 = (size_t)rb * kBuildRows + lane;
+  static_assert(RG == 4, "four row groups of 32 rows");
+  double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;       // y of this lane's row in each row group
+  if (y != nullptr) {
+    const int64_t row = (int64_t)grow0;
+    y0 = row < y_rows ? y[row] : 0.0;
+    y1 = row + 32 < y_rows ? y[row + 32] : 0.0;
+    y2 = row + 64 < y_rows ? y[row + 64] : 0.0;
+    y3 = row + 96 < y_rows ? y[row + 96] : 0.0;
+  }
+  double P0 = 1.0, P1 = 1.0, P2 = 1.0, P3 = 1.0;       // running prefix products, one per row group
+  for (int c0 = c_begin; c0 < c_begin + cpw; c0 += NB) {
+    int lv[NB], sl[NB];
+    double dot[NB];
 #pragma unroll
-      for (int e = 0; e < NB; ++e) {
-        lv[e] = (c0 + e == c_begin) ? 0 : (int)__ldg(sorted_level + c0 + e);
-        last[e] = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + (G - 1))];
-      }
+    for (int e = 0; e < NB; ++e) {
+      lv[e] = (c0 + e == c_begin) ? 0 : (int)__ldg(sorted_level + c0 + e);
+      sl[e] = __ldg(sorted_slot + (size_t)(c0 + e) * G + (G - 1));
+      dot[e] = 0.0;
+    }
+#pragma unroll 1
+    for (int rg = 0; rg < RG; ++rg) {                   // not unrolled: one copy of the body keeps the kernel below 128 registers
+      const double* trow = sT + (size_t)(rg * 32 + lane) * stride;
+      double P = rg == 0 ? P0 : (rg == 1 ? P1 : (rg == 2 ? P2 : P3));
+      const double yr = rg == 0 ? y0 : (rg == 1 ? y1 : (rg == 2 ? y2 : y3));
+      double last[NB];
+#pragma unroll
+      for (int e = 0; e < NB; ++e) last[e] = trow[sl[e]];
 #pragma unroll
       for (int e = 0; e < NB; ++e) {
         if constexpr (G > 1) {
@@ -120,51 +173,64 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
           last[e] *= P;
         }
       }
-      if constexpr (MODE == OUT_F64) {
+      if (rg == 0) P0 = P; else if (rg == 1) P1 = P; else if (rg == 2) P2 = P; else P3 = P;
+      const size_t grow = grow0 + rg * 32;
+      if constexpr (!DIG) {
 #pragma unroll
         for (int e = 0; e < NB; ++e) out[(size_t)(c0 + e) * ld + grow] = last[e];
-      } else if constexpr (MODE == OUT_EXP) {
-#pragma unroll
-        for (int e = 0; e < NB; ++e) {
-          const int m = __reduce_max_sync(0xffffffffu, abs_hi(last[e]));
-          if (lane == 0 && m > s_hi[c0 + e]) atomicMax(s_hi + c0 + e, m);     // shared-memory maximum over this CTA's rows
-        }
       } else {
 #pragma unroll
-        for (int e = 0; e < NB; ++e) {
-          const double scale = __hiloint2double((1023 + 54 - __ldg(exps + c0 + e)) << 20, 0);
-          store_digits(last[e], scale, planes + (size_t)(c0 + e) * ld + grow, (size_t)p_pad * ld);
-        }
+        for (int e = 0; e < NB; ++e)
+          store_digits(last[e], digit_scale(sd, __ldg(exps + c0 + e)), sd, planes + (size_t)(c0 + e) * ld + grow, (size_t)p_pad * ld);
+      }
+      if (y != nullptr) {                                // warp-uniform
+#pragma unroll
+        for (int e = 0; e < NB; ++e) dot[e] = fma(yr, last[e], dot[e]);
       }
     }
-  }
-  if constexpr (MODE == OUT_EXP) {                     // one global maximum per column and CTA
-    __syncthreads();
-    for (int c = threadIdx.x; c < p_pad; c += kBuildThreads)
-      if (s_hi[c] > 0) atomicMax(col_hi + c, s_hi[c]);
+    if (y != nullptr) {                                  // warp-uniform
+      double mine = 0.0;
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        const double t = warp_sum(dot[e]);
+        if (lane == e) mine = t;
+      }
+      if (lane < NB) r_ws[(size_t)rb * p_pad + c0 + lane] = mine;
+    }
   }
 }
 
-// exps[c] from the accumulated high words (and reset them for the next slab)
-__global__ void k_exps_from_hi(int* __restrict__ hi, int n, int n_pad, int* __restrict__ exps, int* __restrict__ err) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    if (hi[i] >= 0x7ff00000) atomicExch(err, 4);      // Inf / NaN in the column
-    exps[i] = exp_from_hi(hi[i]);
-    hi[i] = 0;
+// r_acc[c] (+)= sum_b r_ws[b][c] over the nblk row blocks of a slab (fixed order: warp w sums b = w, w + 16, ..., then warps in sequence)
+__global__ void __launch_bounds__(512) k_reduce_r(const double* __restrict__ r_ws, int nblk, int p_pad, int accumulate, double* __restrict__ r_acc) {
+  __shared__ double part[16][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double s = 0.0;
+  for (int b = warp; b < nblk; b += 16) s += r_ws[(size_t)b * p_pad + c];
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) t += part[w][lane];
+    r_acc[c] = accumulate ? r_acc[c] + t : t;
   }
-  else if (i < n_pad) exps[i] = 0;
+}
+// r[perm[c]] = r_acc[c]  (sorted column order -> the caller's column order)
+__global__ void k_unpermute_vec(const double* __restrict__ in, const int* __restrict__ perm, int p_pad, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < p_pad && perm[c] >= 0) out[perm[c]] = in[c];
 }
 
 // Phi slab, row-major, lane = sorted column (coalesced stores); the G slots of a column are loaded once and reused for the
 // warp's eight rows.
-//   OUT_F64:    out[row * ldo + c]
-//   OUT_DIGITS: exps[row] from the row maximum (first sweep, registers only), then planes[s][row][c] (second sweep)
-template <int G, int MODE>
+//   DIG = false: out[row * ldo + c]
+//   DIG = true:  exps[row] from the row maximum (first sweep, registers only), then planes[s][row][c] (second sweep)
+template <int G, bool DIG>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __restrict__ T, int stride,
                                                              const uint16_t* __restrict__ sorted_slot, int p_pad,
                                                              double* __restrict__ out, int64_t ldo, int* __restrict__ exps,
-                                                             int8_t* __restrict__ planes, size_t plane_stride, int* __restrict__ err) {
+                                                             int8_t* __restrict__ planes, size_t plane_stride, int sd, int* __restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
@@ -175,7 +241,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
   const double* tbase = sT + (size_t)warp * RW * stride;
   const size_t row0 = (size_t)blockIdx.x * kBuildRows + warp * RW;
   double scale[RW];
-  if constexpr (MODE == OUT_DIGITS) {
+  if constexpr (DIG) {
     int hi[RW];
 #pragma unroll
     for (int r = 0; r < RW; ++r) hi[r] = 0;
@@ -199,7 +265,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
         exps[row0 + r] = e;
         if (mh >= 0x7ff00000) atomicExch(err, 4);   // Inf / NaN in the row
       }
-      scale[r] = __hiloint2double((1023 + 54 - e) << 20, 0);
+      scale[r] = digit_scale(sd, e);
     }
   }
   for (int c = lane; c < p_pad; c += 32) {
@@ -213,53 +279,47 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
     for (int g = 1; g < G; ++g)
 #pragma unroll
       for (int r = 0; r < RW; ++r) v[r] *= tbase[r * stride + sl[g]];
-    if constexpr (MODE == OUT_F64) {
+    if constexpr (!DIG) {
 #pragma unroll
       for (int r = 0; r < RW; ++r) out[(row0 + r) * ldo + c] = v[r];
     } else {
 #pragma unroll
-      for (int r = 0; r < RW; ++r) store_digits(v[r], scale[r], planes + (row0 + r) * (size_t)p_pad + c, plane_stride);
+      for (int r = 0; r < RW; ++r) store_digits(v[r], scale[r], sd, planes + (row0 + r) * (size_t)p_pad + c, plane_stride);
     }
   }
 }
 
 struct BuildArgs {
   bool transposed = false;
-  int mode = OUT_F64;
-  double* out = nullptr; int64_t ld = 0;     // FP64 slab (OUT_F64); ld also = bytes per plane row of the transposed digits
-  int* col_hi = nullptr;                     // OUT_EXP (transposed)
-  int* exps = nullptr;                       // read (transposed OUT_DIGITS) or written (row-major OUT_DIGITS)
+  bool digits = false;
+  int sd = kOzMaxDigits;                     // digits per element (INT8 path)
+  double* out = nullptr; int64_t ld = 0;     // FP64 slab; ld also = bytes per plane row of the transposed digits
+  int* exps = nullptr;                       // read (transposed digits) or written (row-major digits)
   int8_t* planes = nullptr; size_t plane_stride = 0;
+  const double* y = nullptr; int64_t y_rows = 0; double* r_ws = nullptr;   // transposed only: fused Phi^T y partials
 };
 
 template <int G>
 static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
-  const size_t smem_rows = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
-  const int n_blocks = (int)(rows / kBuildRows);
-  const unsigned grid = (unsigned)n_blocks;
-#define GRIEF_BT(MODE_)                                                                                                             \
+  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
+  const unsigned grid = (unsigned)(rows / kBuildRows);
+  GRIEF_REQUIRE(smem <= 227 * 1024, "build_phi: %zu bytes of shared memory", smem);
+#define GRIEF_BT(DIG_)                                                                                                              \
   do {                                                                                                                              \
-    const size_t smem = smem_rows + (MODE_ == OUT_EXP ? (size_t)pl->p_pad * sizeof(int) : 0);                                       \
-    const unsigned g = MODE_ == OUT_EXP ? std::min<unsigned>(grid, 148u * 2u) : grid;                                                \
-    GRIEF_REQUIRE(smem <= 227 * 1024, "build_phi_t: %zu bytes of shared memory", smem);                                             \
-    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    k_build_phi_t<G, MODE_><<<g, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad,    \
-                                                               n_blocks, a.out, a.ld, a.col_hi, a.exps, a.planes);                  \
+    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G, DIG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    k_build_phi_t<G, DIG_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad,  \
+                                                                 a.out, a.ld, a.exps, a.planes, a.sd, a.y, a.y_rows, a.r_ws);       \
   } while (0)
-#define GRIEF_BN(MODE_)                                                                                                             \
+#define GRIEF_BN(DIG_)                                                                                                              \
   do {                                                                                                                              \
-    const size_t smem = smem_rows;                                                                                                  \
-    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    k_build_phi<G, MODE_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, a.out, a.ld, a.exps,  \
-                                                                a.planes, a.plane_stride, ozaki_err_flag());                        \
+    GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, DIG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    k_build_phi<G, DIG_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, a.out, a.ld, a.exps,   \
+                                                               a.planes, a.plane_stride, a.sd, pl->d_err);                          \
   } while (0)
   if (a.transposed) {
-    if (a.mode == OUT_F64) GRIEF_BT(OUT_F64);
-    else if (a.mode == OUT_EXP) GRIEF_BT(OUT_EXP);
-    else GRIEF_BT(OUT_DIGITS);
+    if (a.digits) GRIEF_BT(true); else GRIEF_BT(false);
   } else {
-    if (a.mode == OUT_F64) GRIEF_BN(OUT_F64);
-    else GRIEF_BN(OUT_DIGITS);
+    if (a.digits) GRIEF_BN(true); else GRIEF_BN(false);
   }
 #undef GRIEF_BT
 #undef GRIEF_BN
@@ -284,25 +344,26 @@ static int launch_build(const Plan* pl, const double* T, int64_t rows, const Bui
   }
 }
 
-// ---- pass 1: A = Phi^T Phi ----
+static OzOpts oz_opts(const Plan* pl, int digits) {
+  OzOpts o;
+  o.digits = digits; o.cluster = pl->opts.cluster; o.err = pl->d_err;
+  return o;
+}
+
+// ---- pass 1: A = Phi^T Phi (and r = Phi^T y from the same sweep) ----
 struct GramSchedule {
   int nb, n_tiles, splits;
   int64_t slab_rows;
 };
 
-static int g_gemm_mode = 1;            // INT8 tensor-core arithmetic by default; 0 = FP64 DMMA
-int gemm_mode() { return g_gemm_mode; }
-void set_gemm_mode(int mode) { g_gemm_mode = mode ? 1 : 0; }
 constexpr int kOzakiKRange = 16384;   // values of K per int32 accumulation in k_ozaki
 
-static size_t g_slab_budget_bytes = (size_t)4 << 30;      // bytes of Phi^T staged per pass-1 slab
-void set_slab_budget(size_t bytes) { g_slab_budget_bytes = bytes ? bytes : ((size_t)4 << 30); }
-
-GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
+GramSchedule gram_schedule(const Plan* pl, int64_t n_pad, int sms) {
   GramSchedule s;
+  const int p_pad = pl->p_pad;
   s.nb = p_pad / kTileN;
   s.n_tiles = s.nb * (s.nb + 1) / 2;
-  const int64_t budget_rows = (int64_t)(g_slab_budget_bytes / ((size_t)p_pad * 8)) / kBuildRows * kBuildRows;
+  const int64_t budget_rows = (int64_t)(pl->opts.slab_budget / ((size_t)p_pad * 8)) / kBuildRows * kBuildRows;
   s.slab_rows = std::max<int64_t>(kBuildRows, std::min<int64_t>(n_pad, std::max<int64_t>(kBuildRows, budget_rows)));
   // K splits: fill whole waves of `sms` CTAs, keep >= 256 data rows per split
   const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.slab_rows / 256, 64));
@@ -316,7 +377,7 @@ GramSchedule gram_schedule(int p_pad, int64_t n_pad, int sms) {
     if (eff >= 0.97) { best = (int)S; break; }
   }
   s.splits = best;
-  if (g_gemm_mode == 1)      // at most 16384 rows per int32 accumulation; more splits when that is needed to fill the SMs
+  if (pl->opts.gemm_mode == 1)      // at most 16384 rows per int32 accumulation; more splits when that is needed to fill the SMs
     s.splits = std::max(best, (int)((s.slab_rows + kOzakiKRange - 1) / kOzakiKRange));
   return s;
 }
@@ -325,12 +386,13 @@ static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
 static size_t gram_exps_len(const Plan* pl) { return (size_t)(pl->p_pad + 255) / 256 * 256; }
 
-// workspace: [Phi^T slab (FP64, DMMA path) | digit planes (INT8 path)] [split partials] [exps] [col_hi]
+// workspace: [Phi^T slab (FP64, DMMA path) | digit planes (INT8 path)] [split partials] [exps] [slot_hi] [r_ws] [r_acc]
 size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms) {
-  const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
-  const size_t slab = g_gemm_mode == 1 ? align256(ozaki_plane_bytes(pl->p_pad, (int)s.slab_rows))
-                                       : align256((size_t)pl->p_pad * s.slab_rows * sizeof(double));
-  return slab + align256((size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double)) + 2 * align256(gram_exps_len(pl) * sizeof(int));
+  const GramSchedule s = gram_schedule(pl, n_pad, sms);
+  const size_t slab = pl->opts.gemm_mode == 1 ? align256(ozaki_plane_bytes(pl->p_pad, (int)s.slab_rows))
+                                              : align256((size_t)pl->p_pad * s.slab_rows * sizeof(double));
+  return slab + align256((size_t)s.splits * pl->p_pad * pl->p_pad * sizeof(double)) + 2 * align256(gram_exps_len(pl) * sizeof(int)) +
+         align256((size_t)(s.slab_rows / kBuildRows) * pl->p_pad * sizeof(double)) + align256((size_t)pl->p_pad * sizeof(double));
 }
 
 // A[perm[i]][perm[j]] = sum_s part[s][i][j] over the lower tiles (fixed split order), mirrored bit-identically.
@@ -352,23 +414,30 @@ k_gram_reduce(const double* __restrict__ part, const int* __restrict__ perm, int
   }
 }
 
-int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, void* workspace, size_t ws_bytes,
-                int sms, cudaStream_t stream, int* launches) {
+// r != nullptr: r (p) = Phi^T y comes out of the builders' sweep (y: n valid rows).
+int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, const double* y, int64_t n, double* r,
+                void* workspace, size_t ws_bytes, int sms, cudaStream_t stream, int* launches) {
   GRIEF_REQUIRE(n_pad % kBuildRows == 0, "gram: n_pad=%lld must be a multiple of %d", (long long)n_pad, kBuildRows);
   GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
-  const GramSchedule s = gram_schedule(pl->p_pad, n_pad, sms);
+  const GramSchedule s = gram_schedule(pl, n_pad, sms);
   const int pp = pl->p_pad;
-  const bool i8 = g_gemm_mode == 1;
+  const bool i8 = pl->opts.gemm_mode == 1;
+  const int sd = pl->opts.digits_gram;
   char* wq = reinterpret_cast<char*>(workspace);
   double* PhiT = reinterpret_cast<double*>(wq);
   int8_t* planes = reinterpret_cast<int8_t*>(wq);
   wq += i8 ? align256(ozaki_plane_bytes(pp, (int)s.slab_rows)) : align256((size_t)pp * s.slab_rows * sizeof(double));
   double* part = reinterpret_cast<double*>(wq); wq += align256((size_t)s.splits * pp * pp * sizeof(double));
   int* exps = reinterpret_cast<int*>(wq); wq += align256(gram_exps_len(pl) * sizeof(int));
-  int* col_hi = reinterpret_cast<int*>(wq);
+  int* slot_hi = reinterpret_cast<int*>(wq); wq += align256(gram_exps_len(pl) * sizeof(int));
+  double* r_ws = reinterpret_cast<double*>(wq); wq += align256((size_t)(s.slab_rows / kBuildRows) * pp * sizeof(double));
+  double* r_acc = reinterpret_cast<double*>(wq);
+  GRIEF_REQUIRE((size_t)pl->stride <= gram_exps_len(pl), "gram: table stride %d exceeds the slot scratch", pl->stride);
   const size_t part_doubles = (size_t)s.splits * pp * pp;
-  if (n_pad == 0) GRIEF_CUDA(cudaMemsetAsync(part, 0, part_doubles * sizeof(double), stream));
-  if (i8) GRIEF_CUDA(cudaMemsetAsync(col_hi, 0, gram_exps_len(pl) * sizeof(int), stream));
+  if (n_pad == 0) {
+    GRIEF_CUDA(cudaMemsetAsync(part, 0, part_doubles * sizeof(double), stream));
+    if (r) GRIEF_CUDA(cudaMemsetAsync(r_acc, 0, (size_t)pp * sizeof(double), stream));
+  }
   GemmOpts o;
   o.lower_only = true;
   o.splits = s.splits;
@@ -378,35 +447,37 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
     const double* Ts = T + (size_t)r0 * pl->stride;
     BuildArgs ba;
     ba.transposed = true;
+    if (r) { ba.y = y + r0; ba.y_rows = std::max<int64_t>(0, n - r0); ba.r_ws = r_ws; }
     int rc;
     prof_begin(PROF_BUILD_T, stream);
-    if (i8) {      // exponents of the column maxima over the slab, then the digit planes [7][p_pad][R] (K = data rows)
-      ba.mode = OUT_EXP; ba.col_hi = col_hi;
+    if (i8) {      // exponents from the slot maxima of the slab's tables, then the digit planes [sd][p_pad][R] (K = data rows)
+      GRIEF_CUDA(cudaMemsetAsync(slot_hi, 0, gram_exps_len(pl) * sizeof(int), stream));
+      const int64_t total = R * (int64_t)pl->stride;
+      k_slot_hi<<<sms * 4, 256, (size_t)pl->stride * sizeof(int), stream>>>(Ts, pl->stride, total, slot_hi);
+      const int n_e = (int)gram_exps_len(pl);
+      k_col_exps<<<(n_e + 255) / 256, 256, 0, stream>>>(slot_hi, pl->d_sorted_slot, pl->n_groups, pp, n_e, exps, pl->d_err);
+      ba.digits = true; ba.sd = sd; ba.exps = exps; ba.planes = planes; ba.ld = R;
       rc = launch_build(pl, Ts, R, ba, stream);
-      if (rc == GRIEF_OK) {
-        const int n_e = (int)gram_exps_len(pl);
-        k_exps_from_hi<<<(n_e + 255) / 256, 256, 0, stream>>>(col_hi, pp, n_e, exps, ozaki_err_flag());
-        ba.mode = OUT_DIGITS; ba.exps = exps; ba.planes = planes; ba.ld = R;
-        rc = launch_build(pl, Ts, R, ba, stream);
-      }
     } else {
-      ba.mode = OUT_F64; ba.out = PhiT; ba.ld = s.slab_rows;
+      ba.out = PhiT; ba.ld = s.slab_rows;
       rc = launch_build(pl, Ts, R, ba, stream);
     }
+    if (rc == GRIEF_OK && r) k_reduce_r<<<pp / 32, 512, 0, stream>>>(r_ws, (int)(R / kBuildRows), pp, r0 > 0 ? 1 : 0, r_acc);
     prof_end(PROF_BUILD_T, stream);
     if (rc != GRIEF_OK) return rc;
     prof_begin(PROF_GRAM, stream);
     if (i8)
-      rc = ozaki_gemm(planes, pp, exps, pp, planes, pp, exps, pp, (int)R, part, pp, r0 > 0, true, s.splits, (int64_t)pp * pp, stream, launches);
+      rc = ozaki_gemm(planes, pp, exps, pp, planes, pp, exps, pp, (int)R, part, pp, r0 > 0, true, s.splits, (int64_t)pp * pp, oz_opts(pl, sd), stream, launches);
     else
       rc = gemm_nt_ex(PhiT, s.slab_rows, PhiT, s.slab_rows, part, pp, pp, pp, (int)R, 1.0, r0 > 0 ? 1.0 : 0.0, o, stream, launches);
     prof_end(PROF_GRAM, stream);
     if (rc != GRIEF_OK) return rc;
-    if (launches) *launches += i8 ? 3 : 1;
+    if (launches) *launches += (i8 ? 3 : 1) + (r ? 1 : 0);
   }
   k_gram_reduce<<<dim3(s.nb, s.nb), 256, 0, stream>>>(part, pl->d_perm, pp, s.splits, lda, A);
+  if (r) k_unpermute_vec<<<(pp + 255) / 256, 256, 0, stream>>>(r_acc, pl->d_perm, pp, r);
   GRIEF_CUDA(cudaGetLastError());
-  if (launches) *launches += 1;
+  if (launches) *launches += r ? 2 : 1;
   return GRIEF_OK;
 }
 
@@ -445,7 +516,7 @@ int launch_permute_vec(const Plan* pl, const double* in, double scale, double* o
 
 // Scratch of the Z = Phi B product (carved out of the callers' workspaces)
 size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows) {
-  if (g_gemm_mode != 1) return align256((size_t)slab_rows * pl->p_pad * sizeof(double));                       // Phi slab
+  if (pl->opts.gemm_mode != 1) return align256((size_t)slab_rows * pl->p_pad * sizeof(double));                // Phi slab
   return align256(ozaki_plane_bytes(slab_rows, pl->p_pad)) + align256((size_t)slab_rows * sizeof(int)) +       // digits of the slab
          align256(ozaki_plane_bytes(pl->p_pad, pl->p_pad)) + align256(((size_t)pl->p_pad + 256) * sizeof(int));  // digits of B
 }
@@ -458,7 +529,7 @@ struct ZScratch {
 static ZScratch carve_zscratch(const Plan* pl, int64_t slab_rows, void* scratch) {
   ZScratch z{};
   char* q = reinterpret_cast<char*>(scratch);
-  if (g_gemm_mode != 1) {
+  if (pl->opts.gemm_mode != 1) {
     z.Phi = reinterpret_cast<double*>(q);
   } else {
     z.pa = reinterpret_cast<int8_t*>(q); q += align256(ozaki_plane_bytes(slab_rows, pl->p_pad));
@@ -471,9 +542,9 @@ static ZScratch carve_zscratch(const Plan* pl, int64_t slab_rows, void* scratch)
 
 // Once per evaluation, after launch_permute_b: digit planes of B' for the INT8 path (no-op on the DMMA path).
 int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream) {
-  if (g_gemm_mode != 1) return GRIEF_OK;
+  if (pl->opts.gemm_mode != 1) return GRIEF_OK;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
-  return ozaki_slice(Bperm, pl->p_pad, pl->p_pad, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, stream);
+  return ozaki_slice(Bperm, pl->p_pad, pl->p_pad, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, pl->opts.digits_z, pl->d_err, stream);
 }
 
 // Z (slab_rows x ldz, columns in SORTED order) = Phi(slab) * B, B symmetric given as Bperm (p_pad x p_pad, launch_permute_b).
@@ -483,21 +554,23 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   GRIEF_REQUIRE(slab_rows % kBuildRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kBuildRows);
   GRIEF_REQUIRE(ldz >= pl->p_pad, "zgemm: ldz=%lld must be >= p_pad=%d", (long long)ldz, pl->p_pad);
   if (slab_rows == 0) return GRIEF_OK;
+  const bool i8 = pl->opts.gemm_mode == 1;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
   BuildArgs ba;
-  if (g_gemm_mode == 1) {      // row exponents + digit planes [7][slab_rows][p_pad] straight from the tables
-    ba.mode = OUT_DIGITS; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
+  if (i8) {      // row exponents + digit planes [sd][slab_rows][p_pad] straight from the tables
+    ba.digits = true; ba.sd = pl->opts.digits_z; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
   } else {
-    ba.mode = OUT_F64; ba.out = z.Phi; ba.ld = pl->p_pad;
+    ba.out = z.Phi; ba.ld = pl->p_pad;
   }
   prof_begin(PROF_BUILD, stream);
   int rc = launch_build(pl, T_slab, slab_rows, ba, stream);
   prof_end(PROF_BUILD, stream);
   if (rc != GRIEF_OK) return rc;
   prof_begin(PROF_ZGEMM, stream);
-  if (g_gemm_mode == 1) {
+  if (i8) {
     GRIEF_REQUIRE(pl->p_pad <= kOzakiKRange, "zgemm: p_pad=%d exceeds the INT8 path's K range of %d", pl->p_pad, kOzakiKRange);
-    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p_pad, z.eb, pl->p_pad, pl->p_pad, Z, ldz, false, false, 1, 0, stream, launches);
+    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p_pad, z.eb, pl->p_pad, pl->p_pad, Z, ldz, false, false, 1, 0,
+                    oz_opts(pl, pl->opts.digits_z), stream, launches);
   } else {
     GemmOpts o;
     rc = gemm_nt_ex(z.Phi, pl->p_pad, Bperm, pl->p_pad, Z, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);

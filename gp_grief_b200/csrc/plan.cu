@@ -24,6 +24,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+PlanOpts& default_plan_opts() {
+  static thread_local PlanOpts opts;
+  return opts;
+}
+
 // ---- per-kernel timing ----
 struct ProfRec { int slot; cudaEvent_t e0, e1; };
 static thread_local bool g_prof_on = false;
@@ -72,6 +77,7 @@ Plan::~Plan() {
   cudaFree(d_sorted_level);
   cudaFree(d_sorted_gslot);
   cudaFree(d_perm);
+  cudaFree(d_err);
 }
 
 static inline uint64_t mix64(uint64_t h, uint64_t v) {
@@ -101,6 +107,7 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   pl->p = p;
   pl->p_pad = (p + kTileN - 1) / kTileN * kTileN;
   cudaGetDevice(&pl->device);
+  pl->opts = default_plan_opts();
   pl->dims.resize(d);
   int goff = 0, qoff = 0, foff = 0;
   for (int i = 0; i < d; ++i) {
@@ -279,6 +286,7 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_level, sorted_level);
   if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_gslot, sorted_gslot);
   if (rc == GRIEF_OK) rc = upload(&pl->d_perm, pl->perm_h);
+  if (rc == GRIEF_OK) rc = upload(&pl->d_err, std::vector<int>(1, 0));
   if (rc != GRIEF_OK) {
     delete pl;
     return rc;

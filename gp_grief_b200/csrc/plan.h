@@ -32,6 +32,17 @@ struct DimDesc {          // one input dimension, device-visible POD
 struct GradDesc;
 void grad_desc_destroy(GradDesc* gd);
 
+// Arithmetic / staging options of the two O(n p^2) products.  Every plan carries its own copy (taken from the calling thread's
+// defaults when the plan is created, changed with grief_plan_set_option): nothing here is process-global.
+struct PlanOpts {
+  int gemm_mode = 1;                       // 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki)
+  int cluster = 0;                         // INT8 mode: CTA pairs (cta_group::2)
+  int digits_gram = 7;                     // INT8 digits per operand of A = Phi^T Phi
+  int digits_z = 7;                        // INT8 digits per operand of Z = Phi B
+  size_t slab_budget = (size_t)4 << 30;    // bytes of Phi^T staged per pass-1 slab
+};
+PlanOpts& default_plan_opts();             // thread-local defaults for plans created on this thread
+
 struct Plan {
   // ---- host copies ----
   int d = 0, p = 0, p_pad = 0;          // p_pad = p rounded up to kTileN
@@ -61,6 +72,8 @@ struct Plan {
   int* d_perm = nullptr;                // p_pad: external column of sorted column c (-1 for padding columns)
   std::vector<int> perm_h;
   int device = 0;
+  PlanOpts opts;
+  int* d_err = nullptr;                 // device error flag of this plan's INT8 launches (see OzOpts::err)
   GradDesc* grad = nullptr;             // set by grief_grad_setup
   ~Plan();
 };
@@ -83,17 +96,19 @@ struct GemmOpts {
 int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K, double alpha,
                double beta, const GemmOpts& opts, cudaStream_t stream, int* launches);
 
-// FP64 GEMM on the INT8 tensor cores (ozaki.cu).  Digit planes: [7][rows_alloc][K rounded up to 32] int8.
+// FP64 GEMM on the INT8 tensor cores (ozaki.cu).  Digit planes: [digits][rows_alloc][K rounded up to 32] int8; buffers are always
+// sized for kOzMaxDigits planes, `digits` of them are written and read.
+constexpr int kOzMinDigits = 4, kOzMaxDigits = 7;
+struct OzOpts {
+  int digits = kOzMaxDigits;   // balanced 8-bit digits per operand: 8 * digits - 2 bits + sign below the row maximum
+  int cluster = 0;             // 1: CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles
+  int* err = nullptr;          // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value
+};
 size_t ozaki_plane_bytes(int64_t rows, int K);
-int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exps_len, int8_t* planes, cudaStream_t stream);
+int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exps_len, int8_t* planes, int digits, int* err, cudaStream_t stream);
 int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, const int8_t* pb, int64_t rows_b_alloc, const int* eb, int N,
-               int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, cudaStream_t stream,
-               int* launches);
-int ozaki_check(cudaStream_t stream);
-int* ozaki_err_flag();               // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value
-void ozaki_set_cluster(int on);     // 1: CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles (off by default)
-// 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki) for the two O(n p^2) products
-int gemm_mode();
-void set_gemm_mode(int mode);
+               int K, double* C, int64_t ldc, bool accumulate, bool lower_only, int splits, int64_t c_split_stride, const OzOpts& opt,
+               cudaStream_t stream, int* launches);
+int ozaki_check(int* err, cudaStream_t stream);
 
 }  // namespace grief

@@ -234,8 +234,15 @@ int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const dou
   const size_t bytes_int = ((size_t)(2 * d + 1) * sizeof(int) + 15) / 16 * 16;
   // grow-only scratch kept between calls (one evaluation = one call; a stream-ordered alloc/free pair per call showed
   // erratic 10-800 ms host stalls after long GPU phases)
-  static thread_local char* scratch = nullptr;
-  static thread_local size_t scratch_bytes = 0;
+  // (per thread AND per device: a scratch pointer is only valid on the device it was allocated on)
+  constexpr int kMaxDev = 64;
+  static thread_local char* scratch_dev[kMaxDev] = {};
+  static thread_local size_t scratch_bytes_dev[kMaxDev] = {};
+  int dev = 0;
+  GRIEF_CUDA(cudaGetDevice(&dev));
+  GRIEF_REQUIRE(dev >= 0 && dev < kMaxDev, "topk: device ordinal %d", dev);
+  char*& scratch = scratch_dev[dev];
+  size_t& scratch_bytes = scratch_bytes_dev[dev];
   const size_t need = bytes_vals + bytes_par + bytes_cho + bytes_eig + bytes_int;
   if (need > scratch_bytes) {
     if (scratch) cudaFree(scratch);

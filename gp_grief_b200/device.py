@@ -109,15 +109,27 @@ class DevicePlan(object):
         nat.check(nat.lib().grief_phi_rows(self._h, nat.dev_ptr(T), n, nat.dev_ptr(Phi), nat.stream_ptr()))
         return Phi
 
-    def gram(self, T, n, out=None, workspace=None):
-        """A = Phi^T Phi (p, p) from the tables of n rows."""
+    def set_option(self, what, value):
+        """Per-plan option (nat.OPT_GEMM_MODE / OPT_DIGITS_GRAM / OPT_DIGITS_Z / OPT_SLAB_BUDGET, include/grief_b200.h)."""
+        nat.check(nat.lib().grief_plan_set_option(self._h, int(what), int(value)))
+
+    def get_option(self, what):
+        return int(nat.lib().grief_plan_get_option(self._h, int(what)))
+
+    def gram(self, T, n, out=None, workspace=None, y=None, r_out=None):
+        """A = Phi^T Phi (p, p) from the tables of n rows; with y (n,) also r = Phi^T y from the same sweep (returned in r_out)."""
         torch = _torch()
         A = out if out is not None else torch.empty((self.p, self.p), dtype=torch.float64, device=T.device)
         need = nat.lib().grief_gram_workspace_bytes(self._h, n)
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty((need,), dtype=torch.uint8, device=T.device)
-        nat.check(nat.lib().grief_gram(self._h, nat.dev_ptr(T), n, nat.dev_ptr(A), A.stride(0), nat.dev_ptr(workspace),
-                                       workspace.numel(), nat.stream_ptr()))
+        if y is None:
+            nat.check(nat.lib().grief_gram(self._h, nat.dev_ptr(T), n, nat.dev_ptr(A), A.stride(0), nat.dev_ptr(workspace),
+                                           workspace.numel(), nat.stream_ptr()))
+            return A
+        assert r_out is not None and r_out.numel() == self.p and y.numel() == n
+        nat.check(nat.lib().grief_gram_ry(self._h, nat.dev_ptr(T), n, nat.dev_ptr(y), nat.dev_ptr(A), A.stride(0),
+                                          nat.dev_ptr(r_out), nat.dev_ptr(workspace), workspace.numel(), nat.stream_ptr()))
         return A
 
     def gram_workspace_bytes(self, n):

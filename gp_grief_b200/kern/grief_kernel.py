@@ -19,6 +19,10 @@ from .grid_kernel import GridKernel
 logger = logging.getLogger(__name__)
 
 
+class DegenerateEigenpairError(ArithmeticError):
+    """A selected grid eigenpair has a (numerically) repeated eigenvalue: its eigenvector derivative does not exist."""
+
+
 class GriefKernel(GridKernel):
     """Kernel  k(x, z) = Phi(x) diag(w) Phi(z)^T  with Phi the p leading grid eigenfunctions.
 
@@ -168,6 +172,10 @@ class GriefKernel(GridKernel):
         qs_i[:, k] = q_k / sqrt(lambda_k) are the scaled Schur vectors handed to the device plan.  First-order
         perturbation of the symmetric m_i x m_i eigenproblem K_uu,i = Q diag(lambda) Q^T:
             d lambda_k = q_k^T dK q_k,     d q_k = sum_{l != k} q_l (q_l^T dK q_k) / (lambda_k - lambda_l).
+        The expansion needs simple eigenvalues.  Grid eigenvalues saturate at dim_noise_var after a few modes, so a selected
+        index can sit in a cluster whose gaps are below the rounding noise of the eigen-solver (eps * max lambda); there the
+        eigenvectors are an arbitrary rotation and the derivative is meaningless: DegenerateEigenpairError is raised (the model
+        then falls back to finite differences) instead of returning inf / NaN.
         """
         plan = self.device_plan()
         d = self.grid_dim
@@ -181,9 +189,15 @@ class GriefKernel(GridKernel):
             M = Q.T.dot(dK).dot(Q)
             uniq = plan.unique[i]
             dqs = np.zeros((Q.shape[0], uniq.size))
+            gap_floor = 64.0 * np.finfo(float).eps * float(np.max(np.abs(lam)))
             for c, k in enumerate(uniq):
                 gap = lam[k] - lam
                 gap[k] = 1.0
+                close = np.nonzero(np.abs(gap) < gap_floor)[0]
+                if close.size:
+                    raise DegenerateEigenpairError(
+                        "input dimension %d: selected grid eigenvalue %d (%.3e) is within %.1e of eigenvalue %d; the analytic "
+                        "kernel-parameter gradient needs simple eigenvalues" % (i, int(k), lam[k], gap_floor, int(close[0])))
                 coef = M[:, k] / gap
                 coef[k] = 0.0
                 dq = Q.dot(coef)

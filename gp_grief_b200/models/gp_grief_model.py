@@ -155,13 +155,26 @@ class GPGriefModel(BaseModel):
         self.parameters
         self._cov_setup()
 
+    #: (digits of A = Phi^T Phi, digits of Z = Phi B) for the INT8 tensor-core arithmetic, or None for the library defaults
+    #: (include/grief_b200.h, GRIEF_OPT_DIGITS_*).  8 D - 2 bits per operand below its row maximum.
+    gemm_digits = None
+
+    def _plan(self):
+        """The kernel's device plan with this model's arithmetic options applied."""
+        from .. import _native as nat
+        plan = self.kern.device_plan()
+        if self.gemm_digits is not None:
+            plan.set_option(nat.OPT_DIGITS_GRAM, self.gemm_digits[0])
+            plan.set_option(nat.OPT_DIGITS_Z, self.gemm_digits[1])
+        return plan
+
     def _stats(self):
         """A = Phi^T Phi, r = Phi^T y, s = y^T y on the device (all-reduced over ranks), cached like `_A`."""
         dev = self._dev
         if 'stats' in dev:
             return dev['stats']
         t = self._torch
-        plan = self.kern.device_plan()
+        plan = self._plan()
         p = plan.p
         T = plan.build_tables(self._X_dev)
         from ..sharding import stats_layout
@@ -175,8 +188,7 @@ class GPGriefModel(BaseModel):
         if ws is None or ws.numel() < need:
             ws = t.empty((need,), dtype=t.uint8, device="cuda")
             dev['gram_ws'] = ws
-        plan.gram(T, self.num_local, out=A, workspace=ws)
-        plan.phi_t_vec(T, self.num_local, self._y_dev, out=r)
+        plan.gram(T, self.num_local, out=A, workspace=ws, y=self._y_dev, r_out=r)      # A and r = Phi^T y from one sweep
         s.copy_(self._device_mod.sumsq(self._y_dev))
         if self._dist is not None:
             self._dist.all_reduce(buf)
@@ -237,14 +249,22 @@ class GPGriefModel(BaseModel):
                                           "use grad_method='finite_difference'")
             pmap = self.kern.base_parameter_map()
             active = [pmap[i] for i in theta_free]
-            gradient[1 + theta_free] = self._theta_gradient(active, out)
+            from ..kern.grief_kernel import DegenerateEigenpairError
+            try:
+                gradient[1 + theta_free] = self._theta_gradient(active, out)
+            except DegenerateEigenpairError as e:      # repeated grid eigenvalue among the selected ones: no analytic derivative
+                logger.warning("analytic kernel-parameter gradient unavailable (%s); using finite differences for this evaluation", e)
+                return self._finite_diff_gradient(parameters)
         assert not np.any(np.isnan(gradient[free])), "gradient missed!"
+        if not np.all(np.isfinite(gradient[free])):
+            raise FloatingPointError("non-finite entries in the log-likelihood gradient at free parameters %s"
+                                     % np.nonzero(free & ~np.isfinite(gradient))[0].tolist())
         return log_like, gradient
 
     def _theta_gradient(self, active, solve_out):
         """d LML / d theta for the active base-kernel parameters [(dim, kind)] (pass 2 on the device)."""
         t = self._torch
-        plan = self.kern.device_plan()
+        plan = self._plan()
         dqs = self.kern.scaled_eigvec_derivatives(active)
         plan.grad_setup([a[0] for a in active], [0 if a[1] == 'variance' else 1 for a in active], dqs)
         g = plan.grad_theta(self._dev['tables'], self._X_dev, self._y_dev, self.num_local, solve_out['G2'],
@@ -269,7 +289,7 @@ class GPGriefModel(BaseModel):
         """
         self.predict_precompute(Xnew)
         t = self._torch
-        plan = self.kern.device_plan()
+        plan = self._plan()
         out = self._cov_setup(want_grad=compute_var is not None)
         M = Xnew.shape[0]
         Xd = t.as_tensor(np.ascontiguousarray(Xnew, dtype=np.float64)).cuda()

@@ -61,8 +61,9 @@ void grief_launch_count_reset(void);
 
 /*
  * Optional per-kernel timing for benchmarks: CUDA events are recorded on the launch stream around the kernels
- * of each slot.  Slots: 0 fused Gram (k_gram), 1 fused Phi*B GEMM (k_zgemm), 2 table prepass, 3 gradient
- * contraction, 4 top-p select, 5 p x p stage, 6 Phi^T y, 7 derivative tables.  grief_profile_read synchronises,
+ * of each slot.  Slots (grief_profile_slots() = 10): 0 Gram GEMM (pass 1), 1 Phi*B GEMM (pass 2), 2 table prepass, 3 gradient
+ * contraction, 4 top-p select, 5 p x p stage, 6 stand-alone Phi^T v, 7 derivative tables, 8 Phi^T slab builder (pass 1, incl. the
+ * fused Phi^T y), 9 Phi slab builder (pass 2).  grief_profile_read synchronises,
  * writes the accumulated milliseconds and launch counts of every slot (arrays of grief_profile_slots()) and resets.
  */
 void grief_profile_enable(int on);
@@ -133,23 +134,33 @@ int grief_build_tables_dx(const grief_plan* plan, const double* X_dev, int64_t l
 int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, double* Phi_dev, void* stream);
 
 /*
- * HBM budget (bytes) for the Phi^T slab that pass 1 stages per GEMM launch (default 4 GiB; 0 restores the default).
- * Smaller budgets mean more, shorter launches; results are identical up to the order of the fixed-order accumulation.
- * Query grief_gram_workspace_bytes again after changing it.
+ * Options of the two O(n p^2) products (A = Phi^T Phi and Z = Phi B).  Every plan carries its own values; a new plan copies the
+ * CALLING THREAD's defaults (grief_set_default_option), and grief_plan_set_option changes one plan.  Nothing is process-global.
+ * Workspace sizes depend on the options: query them after changing one.
+ *   GRIEF_OPT_GEMM_MODE    arithmetic:
+ *       0  FP64 DMMA GEMM (k_gemm_nt), 36 TFLOP/s
+ *       1  (default) FP64 emulated on the INT8 tensor cores (tcgen05 kind::i8): every operand row is scaled by a power of two and cut
+ *          into D balanced 8-bit digits (8 D - 2 bits + sign, round to nearest); D (D + 1) / 2 exact int8 x int8 -> int32 digit
+ *          products; element errors are bounded by ~2^(1 - 8 D) of the product of the operands' row maxima times K
+ *          (D = 7: the accuracy class of DGEMM)
+ *       3  as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2; correct and
+ *          tested, not faster on a power-capped B200
+ *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (4..7).  A feeds a Cholesky factorisation: keep it at DGEMM class unless the caller's
+ *                          tolerance allows less
+ *   GRIEF_OPT_DIGITS_Z     D of Z = Phi B (pass 2 and the predictive variance), 4..7
+ *   GRIEF_OPT_SLAB_BUDGET  bytes of HBM for the Phi^T slab that pass 1 stages per GEMM launch (default 4 GiB; 0 restores it).  Smaller
+ *                          budgets mean more, shorter launches; results are identical up to the order of the fixed-order accumulation
+ * grief_set_slab_budget / grief_set_gemm_mode / grief_get_gemm_mode are the round-1 spellings of the default setters.
  */
+#define GRIEF_OPT_GEMM_MODE 0
+#define GRIEF_OPT_DIGITS_GRAM 1
+#define GRIEF_OPT_DIGITS_Z 2
+#define GRIEF_OPT_SLAB_BUDGET 3
+int grief_set_default_option(int what, int64_t value);
+int64_t grief_get_default_option(int what);
+int grief_plan_set_option(grief_plan* plan, int what, int64_t value);
+int64_t grief_plan_get_option(const grief_plan* plan, int what);
 void grief_set_slab_budget(size_t bytes);
-
-/*
- * Arithmetic of the two O(n p^2) products (A = Phi^T Phi and Z = Phi B):
- *   0  FP64 DMMA GEMM (k_gemm_nt), 36 TFLOP/s
- *   1  FP64 emulated on the INT8 tensor cores (tcgen05 kind::i8, 7 balanced 8-bit digits per operand = 54 bits + sign,
- *      28 exact int8 x int8 -> int32 digit products), ~75 TFLOP/s FP64-equivalent; element errors are bounded by 2^-53 of
- *      the product of the operands' row maxima times K, i.e. the accuracy class of DGEMM
- *   3  as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2 (each CTA stages
- *      its A rows and half of the B rows; multicast tcgen05.commit; leader-side barriers); correct and tested, not faster on a
- *      power-capped B200, off by default
- * Workspace sizes depend on the mode: query them after changing it.  Process-wide.
- */
 void grief_set_gemm_mode(int mode);
 int grief_get_gemm_mode(void);
 
@@ -162,6 +173,13 @@ int grief_get_gemm_mode(void);
 size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n);
 int grief_gram(const grief_plan* plan, const double* T_dev, int64_t n, double* A_dev, int64_t lda,
                void* workspace_dev, size_t workspace_bytes, void* stream);
+/*
+ * A = Phi^T Phi and r = Phi^T y (models/gp_grief_model.py:148-149 and :234) from ONE sweep over the rows: the builder that stages a
+ * slab of Phi has every element in a register, so y^T Phi is accumulated there (fixed order) instead of a second pass over Phi.
+ *   y_dev (n), r_dev (p) out.  r_dev == NULL: same as grief_gram.
+ */
+int grief_gram_ry(const grief_plan* plan, const double* T_dev, int64_t n, const double* y_dev, double* A_dev, int64_t lda,
+                  double* r_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* out[j] = sum_n v[n] Phi[n,j]  (r = Phi^T y, models/gp_grief_model.py:234).  ws: grief_phi_t_vec_workspace_bytes */
 size_t grief_phi_t_vec_workspace_bytes(const grief_plan* plan, int64_t n);

@@ -233,11 +233,9 @@ def test_gram_and_quadform_over_several_slabs():
     Phi = plan.phi_rows(T, n)
     A_ref = (Phi.T @ Phi).cpu().numpy()
     A_one = plan.gram(T, n).cpu().numpy()
-    try:
-        nat.lib().grief_set_slab_budget(256 * 8 * 3000)          # 3000-row slabs (rounded down to 2944) -> 14 slabs
-        A_many = plan.gram(T, n).cpu().numpy()
-    finally:
-        nat.lib().grief_set_slab_budget(0)
+    plan.set_option(nat.OPT_SLAB_BUDGET, 256 * 8 * 3000)        # 3000-row slabs (rounded down to 2944) -> 14 slabs
+    A_many = plan.gram(T, n).cpu().numpy()
+    plan.set_option(nat.OPT_SLAB_BUDGET, 0)
     tol = 1e-12 * np.abs(A_ref).max()
     assert_allclose(A_one, A_ref, rtol=0, atol=tol)
     assert_allclose(A_many, A_ref, rtol=0, atol=tol)

@@ -1,0 +1,191 @@
+"""Round-2 GPU tests: digit count of the INT8 arithmetic, the Phi^T y fused into the pass-1 builder, per-plan options,
+the eigen-gap guard of the analytic gradient, empty row shards."""
+import logging
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from conftest import load_golden, model_cases, case_inputs
+from oracle import grief_oracle as orc
+from gp_grief_b200 import _native as nat
+import test_native_gpu as tn
+import test_api_gpu as ta
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_plan(d=4, m=6, p=200, seed=5, kernel="RBF"):
+    xg = [np.linspace(0, 1, m) for _ in range(d)]
+    names, var, ls = [kernel] * d, [1.0] * d, [0.3 + 0.07 * i for i in range(d)]
+    basis = orc.setup_inducing_cov(names, var, ls, xg, p)
+    c = dict(d=d, names=names, variances=var, lengthscales=ls, xg=xg)
+    return tn._plan_from_basis(c, basis), basis, c
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["int8", "fp64"])
+@pytest.mark.parametrize("name", model_cases())
+def test_fused_phi_t_y_matches_reference(name, mode):
+    """r = Phi^T y out of the Gram builder's sweep (grief_gram_ry) equals the stand-alone kernel and the reference's Phi.T.dot(y)
+    (models/gp_grief_model.py:234)."""
+    import torch
+    g = load_golden(name)
+    c = case_inputs(g)
+    basis = orc.setup_inducing_cov(c["names"], c["variances"], c["lengthscales"], c["xg"], c["n_eigs"])
+    plan = tn._plan_from_basis(c, basis)
+    plan.set_option(nat.OPT_GEMM_MODE, mode)
+    Phi_o = orc.grief_phi(basis, c["names"], c["variances"], c["lengthscales"], c["xg"], c["x"])
+    n = c["x"].shape[0]
+    T = plan.build_tables(torch.from_numpy(np.ascontiguousarray(c["x"])).cuda())
+    y = torch.from_numpy(np.ascontiguousarray(c["y"].reshape(-1))).cuda()
+    r = torch.full((plan.p,), np.nan, dtype=torch.float64, device="cuda")
+    A = plan.gram(T, n, y=y, r_out=r)
+    r_scale = float(np.abs(Phi_o).T.dot(np.abs(c["y"])).max())
+    assert_allclose(r.cpu().numpy(), Phi_o.T.dot(c["y"]).reshape(-1), rtol=0, atol=1e-13 * r_scale)
+    assert_allclose(r.cpu().numpy(), plan.phi_t_vec(T, n, y).cpu().numpy(), rtol=0, atol=1e-13 * r_scale)
+    A_o = Phi_o.T.dot(Phi_o)
+    assert_allclose(A.cpu().numpy(), A_o, rtol=0, atol=1e-12 * np.abs(A_o).max())
+
+
+def test_fused_phi_t_y_over_several_slabs_and_ragged_rows():
+    import torch
+    rng = np.random.default_rng(21)
+    plan, basis, c = _random_plan(p=300)
+    n = 20011
+    X = torch.from_numpy(rng.random((n, c["d"]))).cuda()
+    y = torch.from_numpy(rng.standard_normal(n)).cuda()
+    T = plan.build_tables(X)
+    Phi = plan.phi_rows(T, n)
+    r_ref = (Phi.T @ y).cpu().numpy()
+    scale = float((Phi.abs().T @ y.abs()).max())
+    for budget in (0, 384 * 8 * 3000):                      # one slab / seven slabs of 2944 rows
+        plan.set_option(nat.OPT_SLAB_BUDGET, budget)
+        r = torch.empty((plan.p,), dtype=torch.float64, device="cuda")
+        plan.gram(T, n, y=y, r_out=r)
+        assert_allclose(r.cpu().numpy(), r_ref, rtol=0, atol=1e-13 * scale)
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern32"])
+def test_digit_count_controls_the_error_of_both_products(kernel):
+    """8 D - 2 bits per operand below its row maximum: the error of A = Phi^T Phi and of q = diag(Phi B Phi^T) must shrink by
+    ~2^8 per digit and stay under the documented bound; D = 7 is the DGEMM-class default."""
+    import torch
+    rng = np.random.default_rng(8)
+    plan, basis, c = _random_plan(d=4, m=7, p=260, kernel=kernel)
+    n = 30011
+    X = torch.from_numpy(rng.random((n, c["d"]))).cuda()
+    T = plan.build_tables(X)
+    Phi = plan.phi_rows(T, n)
+    A_ref = (Phi.T @ Phi).cpu().numpy()
+    B = rng.standard_normal((plan.p, plan.p))
+    B = torch.from_numpy(B + B.T).cuda()
+    q_ref = ((Phi @ B) * Phi).sum(1).cpu().numpy()
+    assert plan.get_option(nat.OPT_DIGITS_GRAM) == 7 and plan.get_option(nat.OPT_DIGITS_Z) == 7
+    errs_a, errs_q = [], []
+    for D in (4, 5, 6, 7):
+        plan.set_option(nat.OPT_DIGITS_GRAM, D)
+        plan.set_option(nat.OPT_DIGITS_Z, D)
+        A = plan.gram(T, n).cpu().numpy()
+        assert_array_equal(A, A.T)
+        q = plan.quadform_rows(T, n, B).cpu().numpy()
+        ea = np.abs(A - A_ref).max() / np.abs(A_ref).max()
+        eq = np.abs(q - q_ref).max() / np.abs(q_ref).max()
+        errs_a.append(ea)
+        errs_q.append(eq)
+        bound = max(2.0 ** -(8 * D - 10), 2e-13)            # fp64 reference itself is ~1e-14 here
+        assert ea < bound and eq < 64 * bound, (D, ea, eq, bound)
+    assert errs_a[0] > 30 * errs_a[1] and errs_a[1] > 10 * errs_a[2], errs_a
+    with pytest.raises(ValueError):
+        plan.set_option(nat.OPT_DIGITS_Z, 8)
+    with pytest.raises(ValueError):
+        plan.set_option(nat.OPT_DIGITS_GRAM, 3)
+
+
+@pytest.mark.parametrize("digits", [(6, 6), (6, 5), (7, 5)])
+@pytest.mark.parametrize("name", ["syn_t2_n2000_d4_m8_p64", "syn_t2_matern52_n1500_d3_m10_p48", "syn_t1_n3000_d6_m10_p256_w",
+                                  "c1_automobile"])
+def test_reduced_digit_models_stay_within_the_north_star_tolerance(name, digits):
+    """The reference goldens (LML, gradients) at <= 1e-9 relative with fewer int8 digit products (21 / 15 instead of 28)."""
+    g = load_golden(name)
+    m = ta.build_model(g)
+    m.gemm_digits = digits
+    ll, grad = m.log_likelihood(return_gradient=True)
+    assert_allclose(float(np.asarray(ll).squeeze()), float(g["lml"]), rtol=1e-9)
+    if "grad_adjoint" in g and not bool(g["type2"]):
+        ref = g["grad_adjoint"]
+        ok = ~np.isnan(ref) & ~np.isnan(grad)
+        assert_allclose(grad[ok], ref[ok], rtol=1e-9, atol=1e-9 * np.abs(ref[ok]).max())
+    if bool(g["type2"]):
+        m7 = ta.build_model(g)
+        m7.gemm_digits = (7, 7)
+        _, g7 = m7.log_likelihood(return_gradient=True)
+        ok = ~np.isnan(g7)
+        assert_allclose(grad[ok], g7[ok], rtol=0, atol=1e-9 * np.abs(g7[ok]).max())
+
+
+def test_options_are_per_plan_not_process_wide():
+    import torch
+    rng = np.random.default_rng(2)
+    plan_a, _, c = _random_plan(p=150, seed=1)
+    plan_b, _, _ = _random_plan(p=150, seed=1)
+    before = nat.lib().grief_get_default_option(nat.OPT_GEMM_MODE)
+    plan_a.set_option(nat.OPT_GEMM_MODE, 0)
+    plan_a.set_option(nat.OPT_DIGITS_GRAM, 5)
+    assert plan_b.get_option(nat.OPT_GEMM_MODE) == before == 1          # neither the other plan nor the defaults moved
+    assert plan_b.get_option(nat.OPT_DIGITS_GRAM) == 7
+    assert nat.lib().grief_get_default_option(nat.OPT_DIGITS_GRAM) == 7
+    n = 5000
+    X = torch.from_numpy(rng.random((n, c["d"]))).cuda()
+    Ta, Tb = plan_a.build_tables(X), plan_b.build_tables(X)
+    Aa, Ab = plan_a.gram(Ta, n).cpu().numpy(), plan_b.gram(Tb, n).cpu().numpy()
+    assert_allclose(Aa, Ab, rtol=0, atol=1e-12 * np.abs(Ab).max())
+    # defaults are copied when a plan is created
+    try:
+        nat.check(nat.lib().grief_set_default_option(nat.OPT_DIGITS_Z, 6))
+        plan_c, _, _ = _random_plan(p=150, seed=1)
+        assert plan_c.get_option(nat.OPT_DIGITS_Z) == 6 and plan_b.get_option(nat.OPT_DIGITS_Z) == 7
+    finally:
+        nat.check(nat.lib().grief_set_default_option(nat.OPT_DIGITS_Z, 7))
+    with pytest.raises(ValueError):
+        nat.check(nat.lib().grief_set_default_option(99, 1))
+
+
+def test_repeated_grid_eigenvalue_falls_back_to_finite_differences(caplog):
+    """d = 2 with n_eigs = m^d selects every grid eigenpair, including the cluster at dim_noise_var where the eigenvector
+    derivative does not exist: the model must say so and return the finite-difference gradient, not inf / NaN."""
+    import gp_grief_b200 as gp
+    from gp_grief_b200.kern.grief_kernel import DegenerateEigenpairError
+    rng = np.random.default_rng(0)
+    d, m, n = 2, 12, 400
+    x = rng.random((n, d))
+    y = np.sin(3 * x.sum(1, keepdims=True)) + 0.1 * rng.standard_normal((n, 1))
+    grid = gp.grid.InducingGrid(xg=[np.linspace(0, 1, m).reshape(-1, 1)] * d)
+    kern = gp.kern.GriefKernel([gp.kern.RBF(1, lengthscale=0.6 + 0.1 * i) for i in range(d)], grid, n_eigs=m ** d,
+                               reweight_eig_funs=False, opt_kernel_params=True, dim_noise_var=1e-12)
+    model = gp.models.GPGriefModel(x, y, kern, noise_var=0.1)
+    assert model.grad_method == 'adjoint'
+    pmap = kern.base_parameter_map()
+    with pytest.raises(DegenerateEigenpairError):
+        kern.scaled_eigvec_derivatives([pmap[1]])
+    with caplog.at_level(logging.WARNING):
+        ll, grad = model.log_likelihood(return_gradient=True)
+    assert "finite differences" in caplog.text
+    free = np.logical_not(model._fixed_indicies)
+    assert np.all(np.isfinite(grad[free]))
+    ll_fd, grad_fd = model._finite_diff_gradient(model.parameters)
+    assert_allclose(grad[free], grad_fd[free], rtol=1e-12, atol=0)
+
+
+def test_empty_row_shard_evaluates_to_the_prior_terms():
+    """A rank whose shard is empty (sharding.row_shard tail) must contribute zeros, not raise before the all-reduce."""
+    import gp_grief_b200 as gp
+    d, m, p = 3, 6, 40
+    grid = gp.grid.InducingGrid(xg=[np.linspace(0, 1, m).reshape(-1, 1)] * d)
+    kern = gp.kern.GriefKernel([gp.kern.RBF(1, lengthscale=0.3 + 0.1 * i) for i in range(d)], grid, n_eigs=p,
+                               reweight_eig_funs=False, opt_kernel_params=True)
+    model = gp.models.GPGriefModel(np.zeros((0, d)), np.zeros((0, 1)), kern, noise_var=0.1)
+    st = model._stats()
+    assert float(st['A'].abs().max()) == 0.0 and float(st['r'].abs().max()) == 0.0 and float(st['s']) == 0.0
+    out = model._cov_setup(want_grad=True, want_G2=True)
+    g = model._theta_gradient([(0, 'lengthscale'), (1, 'variance')], out)
+    assert_array_equal(g, np.zeros(2))
