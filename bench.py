@@ -7,7 +7,7 @@
 
 One "step" = one complete evaluation at NEW kernel hyper-parameters:
   Type-II (C3: n = 10M, d = 10, m = 20, p = 4096): host Schur of the d grid matrices -> GPU top-p selection -> table prepass ->
-      Gram + Phi^T y (pass 1) -> [all-reduce] -> Cholesky / LML / d/dnoise -> Phi*G2 GEMM + contraction (pass 2) -> [all-reduce]
+      Gram + Phi^T y (pass 1) -> [all-reduce] -> Cholesky / LML / d/dnoise -> Phi*P^-1 GEMM + contraction (pass 2) -> [all-reduce]
   Type-I (C2, C4, C5): the same without pass 2 (gradient w.r.t. the p weights and the noise from the p x p stage);
       `type1_reevals_per_s` is the O(p^3) re-evaluation on cached statistics that a Type-I optimiser actually iterates.
 Rows are sharded over ranks (strong scaling: the total n is fixed).  Prints ONE JSON line on rank 0.
@@ -301,7 +301,7 @@ def run_ours(args):
         nat.check(lib.grief_set_default_option(nat.OPT_DIGITS_GRAM, dg))
         nat.check(lib.grief_set_default_option(nat.OPT_DIGITS_Z, dz))
     dg, dz = int(lib.grief_get_default_option(nat.OPT_DIGITS_GRAM)), int(lib.grief_get_default_option(nat.OPT_DIGITS_Z))
-    pairs = lambda D: D * (D + 1) // 2
+    pairs = lambda D, sym=False: D * (D + 1) // 2 + (1 if (sym and D % 2 == 0) else 0)     # int8 digit GEMMs per FP64 GEMM
 
     r0, r1 = row_shard(n_total, world, rank)
     n_local = r1 - r0
@@ -535,7 +535,7 @@ def run_ours(args):
     flops = {"k_zgemm": 2.0 * rows128 * p_pad * p_pad, "k_gram": float(rows128) * p_pad * (p_pad + 128)}
     digits_of = {"k_zgemm": dz, "k_gram": dg}
     gk = {"int8": "k_ozaki<1,D>", "int8x2": "k_ozaki<2,D> (cta_group::2 pairs)", "fp64": "k_gemm_nt"}[args.gemm]
-    label = {"k_zgemm": gk + " [Z = Phi*G2, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
+    label = {"k_zgemm": gk + " [Z = Phi*P^-1, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
              "k_build_phi": "k_build_phi [Phi slab, pass 2]", "k_build_phi_t": "k_build_phi_t (+ slot maxima, fused Phi^T y) [Phi^T slab, pass 1]",
              "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)"}
     non_gemm = 0.0
@@ -546,8 +546,8 @@ def run_ours(args):
             if name in flops:
                 row["issued_fp64_equiv_tflops"] = flops[name] * args.steps / (t_ms * 1e-3) * 1e-12
                 if i8:
-                    row["int8_digit_products"] = pairs(digits_of[name])
-                    row["issued_int8_tops"] = pairs(digits_of[name]) * row["issued_fp64_equiv_tflops"]
+                    row["int8_digit_products"] = pairs(digits_of[name], name == "k_gram")
+                    row["issued_int8_tops"] = row["int8_digit_products"] * row["issued_fp64_equiv_tflops"]
             elif name not in ("solve", "k_topk"):
                 non_gemm += t_ms
             kern_rows.append(row)
@@ -587,8 +587,8 @@ def run_ours(args):
             roofline = dict(common, bound="tensor",
                             kernel="k_ozaki (tcgen05 kind::i8, TMEM accumulators, TMA digit planes): %s as %d exact int8 x int8 -> int32 digit "
                                    "GEMMs (%d digits per operand); digit planes written straight from the tables by the slab builders"
-                                   % ("Z = Phi*G2 for pass 2, one launch per slab of 37888 rows" if dom["slot"] == "k_zgemm" else
-                                      "A = Phi^T Phi for pass 1, one launch per slab", pairs(digits_of[dom["slot"]]), digits_of[dom["slot"]]),
+                                   % ("Z = Phi*P^-1 for pass 2, one launch per slab of 37888 rows" if dom["slot"] == "k_zgemm" else
+                                      "A = Phi^T Phi for pass 1, one launch per slab", dom["int8_digit_products"], digits_of[dom["slot"]]),
                             achieved=tops, peak=peak_i8, unit="TOP/s (int8)", frac=tops / peak_i8, peak_source=src,
                             int8_peak_measured=pk)
         else:
@@ -601,7 +601,7 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(cfg, n_total, args.cpu_rows or (1 << 14), max(2, args.cpu_chunks))
     dtype = "f64" if not i8 else ("f64 (O(n p^2) products as exact int8 digit GEMMs on the tensor cores: %d-bit operands for A = Phi^T Phi, %d-bit for "
-                                  "Z = Phi G2, relative to the operand row maximum)" % (8 * dg - 2, 8 * dz - 2))
+                                  "Z = Phi P^-1, relative to the operand row maximum)" % (8 * dg - 2, 8 * dz - 2))
     line = {"metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic",

@@ -26,13 +26,13 @@ int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const dou
 
 int grad_desc_create(GradDesc** out, const Plan* pl, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat);
 int grad_desc_n_active(const GradDesc* gd);
-int grad_desc_dt_width(const GradDesc* gd);
-int launch_dtables(const Plan* pl, const GradDesc* gd, const double* X, int64_t ldx, int64_t n_valid, int64_t rows_total, double* DT, cudaStream_t stream);
-int contract_blocks(int sms);
-int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t ldz, const double* T, const double* DT, const double* y,
-                    const double* gvec, int64_t rows, double* partial, int sms, cudaStream_t stream);
-int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream);
-int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream);
+int contract_acc_len(const Plan* pl);
+int contract_total_warps(const Plan* pl, int sms);
+int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* y,
+                    const double* bvec, double noise_var, int64_t rows_blk, int64_t rows_valid, double* acc, int sms, cudaStream_t stream);
+int launch_grad_finish(const Plan* pl, const GradDesc* gd, const double* acc, int sms, double* out, cudaStream_t stream);
+int launch_rowdot(const Plan* pl, const double* Zt, int64_t ldz, const double* T, int64_t rows_blk, int64_t rows_valid, double* out,
+                  cudaStream_t stream);
 int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream);
 int launch_permute_vec(const Plan* pl, const double* in, double scale, double* out, cudaStream_t stream);
 size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows);
@@ -264,42 +264,43 @@ int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const 
   return grad_desc_create(&pl->grad, pl, n_active, dims, kinds, dqs_concat);
 }
 
+// workspace of grief_grad_theta: [Zp^T slab] [GEMM scratch] [per-warp accumulators] [b in sorted order] [permuted P^-1]
 size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
   if (!pl->grad) return 0;
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) +
-         align256((size_t)slab * std::max(1, grad_desc_dt_width(pl->grad)) * sizeof(double)) +
-         align256((size_t)contract_blocks(sms) * std::max(1, grad_desc_n_active(pl->grad)) * sizeof(double)) + align256((size_t)pl->p_pad * sizeof(double)) +
+         align256((size_t)contract_total_warps(pl, sms) * contract_acc_len(pl) * sizeof(double)) + align256((size_t)pl->p_pad * sizeof(double)) +
          align256((size_t)pl->p_pad * pl->p_pad * sizeof(double));
 }
 
 int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev, int64_t n,
-                     const double* G2_dev, int64_t ldg, const double* b_dev, double noise_var, double* grad_dev, void* workspace_dev,
+                     const double* Pinv_dev, int64_t ldp, const double* b_dev, double noise_var, double* grad_dev, void* workspace_dev,
                      size_t workspace_bytes, void* stream_) {
   GRIEF_REQUIRE(plan && plan->impl->grad, "grief_grad_theta: call grief_grad_setup first");
-  GRIEF_REQUIRE(G2_dev && b_dev && grad_dev && workspace_dev && (n == 0 || (T_dev && X_dev && y_dev)), "grief_grad_theta: null pointer");
+  GRIEF_REQUIRE(Pinv_dev && b_dev && grad_dev && workspace_dev && (n == 0 || (T_dev && X_dev && y_dev)), "grief_grad_theta: null pointer");
   GRIEF_REQUIRE(workspace_bytes >= grief_grad_workspace_bytes(plan, n), "grief_grad_theta: workspace too small");
+  GRIEF_REQUIRE(noise_var > 0.0, "grief_grad_theta: noise_var=%g", noise_var);
   GRIEF_PLAN_DEVICE(plan->impl);
   const Plan* pl = plan->impl;
   const GradDesc* gd = pl->grad;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int sms = sm_count();
-  const int na = grad_desc_n_active(gd), dtw = grad_desc_dt_width(gd);
+  const int na = grad_desc_n_active(gd);
   const int64_t slab = slab_rows_for(n, sms);
+  const size_t acc_doubles = (size_t)contract_total_warps(pl, sms) * contract_acc_len(pl);
   char* q = reinterpret_cast<char*>(workspace_dev);
-  double* Z = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
+  double* Zt = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
   void* zscr = q; q += align256(zgemm_scratch_bytes(pl, slab));
-  double* DT = reinterpret_cast<double*>(q); q += align256((size_t)slab * std::max(1, dtw) * sizeof(double));
-  double* partial = reinterpret_cast<double*>(q); q += align256((size_t)contract_blocks(sms) * std::max(1, na) * sizeof(double));
-  double* gvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p_pad * sizeof(double));
+  double* acc = reinterpret_cast<double*>(q); q += align256(acc_doubles * sizeof(double));
+  double* bvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p_pad * sizeof(double));
   double* Bperm = reinterpret_cast<double*>(q);
   if (na == 0) return GRIEF_OK;
-  GRIEF_CUDA(cudaMemsetAsync(partial, 0, (size_t)contract_blocks(sms) * na * sizeof(double), stream));
-  int rc = launch_permute_vec(pl, b_dev, 1.0 / noise_var, gvec, stream);      // g = b / sigma^2 in sorted column order
+  GRIEF_CUDA(cudaMemsetAsync(acc, 0, acc_doubles * sizeof(double), stream));
+  int rc = launch_permute_vec(pl, b_dev, 1.0, bvec, stream);                  // b in sorted column order
   if (rc != GRIEF_OK) return rc;
-  rc = launch_permute_b(pl, G2_dev, ldg, Bperm, stream);
+  rc = launch_permute_b(pl, Pinv_dev, ldp, Bperm, stream);
   if (rc == GRIEF_OK) rc = launch_zgemm_prepare(pl, Bperm, slab, zscr, stream);
   if (rc != GRIEF_OK) return rc;
   g_launches += 2;
@@ -307,15 +308,14 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, pl->p_pad, stream, &g_launches);
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Zt, slab, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
-    rc = launch_dtables(pl, gd, X_dev + (size_t)r0 * ldx, ldx, rows_valid, rows_valid, DT, stream);
+    rc = launch_contract(pl, Zt, slab, T_dev + (size_t)r0 * pl->stride, X_dev + (size_t)r0 * ldx, ldx, y_dev + r0, bvec, noise_var, rows_blk,
+                         rows_valid, acc, sms, stream);
     if (rc != GRIEF_OK) return rc;
-    rc = launch_contract(pl, gd, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, DT, y_dev + r0, gvec, rows_valid, partial, sms, stream);
-    if (rc != GRIEF_OK) return rc;
-    g_launches += 2;
+    g_launches += 1;
   }
-  rc = launch_reduce_partials(partial, contract_blocks(sms), na, grad_dev, stream);
+  rc = launch_grad_finish(pl, gd, acc, sms, grad_dev, stream);
   if (rc == GRIEF_OK) g_launches += 1;
   if (rc == GRIEF_OK && pl->opts.gemm_mode == 1) rc = ozaki_check(pl->d_err, stream);
   return rc;
@@ -349,9 +349,9 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, pl->p_pad, stream, &g_launches);
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, slab, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
-    rc = launch_rowdot(pl, Z, pl->p_pad, T_dev + (size_t)r0 * pl->stride, rows_valid, q_dev + r0, stream);
+    rc = launch_rowdot(pl, Z, slab, T_dev + (size_t)r0 * pl->stride, rows_blk, rows_valid, q_dev + r0, stream);
     if (rc != GRIEF_OK) return rc;
     g_launches += 1;
   }

@@ -1,17 +1,25 @@
 // G4: analytic hyper-parameter gradient (replaces the reference's finite-difference loop,
 // models/basemodel.py:328-361, which costs (#free + 1) full Phi / Gram rebuilds).
 //
-//   dLML/dtheta = sum_n sum_j Zt[n,j] * dPhi[n,j]/dtheta,    Zt = Phi * G2 + y g^T,
-//   G2 = -(P^-1 + b b^T/sigma^2),  g = b/sigma^2                                
+//   dLML/dtheta = sum_n sum_j Zt[n,j] * dPhi[n,j]/dtheta,
+//   Zt = Phi * G2 + y g^T,  G2 = -(P^-1 + b b^T/sigma^2),  g = b/sigma^2                              
+//      = -Phi P^-1 + a b^T,  a = (y - Phi b) / sigma^2   (the residual scaled by the noise: alpha of models/gp_grief_model.py:234)
+// Only Zp = Phi P^-1 goes through the O(n p^2) GEMM (launch_zgemm, phi_stage.cu, one slab of rows at a time, stored TRANSPOSED with
+// its columns in the plan's SORTED order); the rank-one part is added here in FP64 from f = Phi b.  (Round 1 multiplied by G2: its
+// rows are dominated by b b^T/sigma^2, ~n times larger than P^-1, so the digit GEMM spent ~20 of its bits on a term that costs two
+// multiplies per element to form exactly.)
 //
-// Z = Phi*G2 comes from launch_zgemm (phi_stage.cu: slab builder + GEMM), one slab of rows at a time, with its columns in the
-// plan's SORTED order (so do gvec and the slot table handed to k_contract / k_rowdot).  For a parameter theta of
-// input dimension i (group g of the table layout) only the factor of dimension i changes:
-//   dPhi[n,j]/dtheta = DT_theta[n, t_g(j)] * prod_{g' != g} H_g'[n, t_g'(j)]
-//   DT_theta[n,t]    = dF_i[n,k_i(t)]/dtheta * prod_{i' in g, i' != i} F_i'[n,k_i'(t)]
-//   dF_i[n,k]/dtheta = sum_u dK_i(x_n,u)/dtheta * Qs_i[u,k] + K_i(x_n,u) * dQs_i[u,k]/dtheta
+// Reverse mode instead of a derivative table per parameter.  With Phi[n,j] = prod_g T[n, s_g(j)] (group tables, plan.h):
+//   W[n,s]   = dL/dT[n,s]   = sum_{j: s_g(j) = s} Zt[n,j] * prod_{g' != g} T[n, s_g'(j)]
+//   V_i[n,k] = dL/dF_i[n,k] = sum_{s in group(i): k_i(s) = k} W[n,s] * prod_{i' in group, i' != i} F_i'[n, k_i'(s)]
+//   F_i[n,k] = sum_u K_i(x_n,u) Qs_i[u,k]   =>   dL/dtheta = sum_n sum_u dK_i(x_n,u)/dtheta * (sum_k V_i[n,k] Qs_i[u,k])
+//                                                          + sum_{u,k} dQs_i[u,k]/dtheta * M_i[u,k],   M_i[u,k] = sum_n K_i(x_n,u) V_i[n,k]
 // with dQs/dtheta (eigenvector / eigenvalue perturbation of the m_i x m_i grid problem) supplied by the host.
-// k_dtables evaluates DT for a slab of rows; k_contract folds Z, H and DT into per-parameter sums.
+// k_contract_rows: one warp per 32 data rows, LANE = ROW.  The sorted columns form a trie over the key positions (consecutive
+// columns share their leading slots); every lane walks it in the same order, so there is no divergence and no cross-lane traffic:
+// prefix products and per-level partial sums live in registers, W lives in shared memory as [slot][lane] (conflict-free).  ~15
+// instructions per (row, column) instead of the ~110 of the round-1 kernel (warp per row, lane = column, one FMA per parameter),
+// and the 4 KB/row derivative table of k_dtables is gone.
 #include <vector>
 
 #include "plan.h"
@@ -20,26 +28,11 @@ namespace grief {
 
 struct GradDesc {            // device-resident description of the active parameters
   int n_active = 0;
-  int dt_width = 0;          // doubles per DT row
-  int sum_du = 0;            // sum over active params of u_dim
-  int max_np = 0;
-  int* d_a_dim = nullptr;    // [n_active]
+  int* d_a_dim = nullptr;    // [n_active] input dimension
   int* d_a_kind = nullptr;   // 0 = variance, 1 = lengthscale
-  int* d_a_group = nullptr;
-  int* d_a_kk = nullptr;     // index among the active params of its group
-  int* d_a_qoff = nullptr;   // offset into d_dqs
-  int* d_a_foff = nullptr;   // offset into the per-row dF scratch
-  int* d_g_np = nullptr;     // [G] active params per group
-  int* d_g_dtoff = nullptr;  // [G+1] offset of the group's block inside a DT row
-  int* d_g_slot0 = nullptr;  // [G]
-  int* d_g_size = nullptr;   // [G]
-  int* d_ga = nullptr;       // [G][max_np] -> active index
-  double* d_dqs = nullptr;
-  std::vector<int> g_np_h, g_dtoff_h;
-  ~GradDesc() {
-    cudaFree(d_a_dim); cudaFree(d_a_kind); cudaFree(d_a_group); cudaFree(d_a_kk); cudaFree(d_a_qoff); cudaFree(d_a_foff);
-    cudaFree(d_g_np); cudaFree(d_g_dtoff); cudaFree(d_g_slot0); cudaFree(d_g_size); cudaFree(d_ga); cudaFree(d_dqs);
-  }
+  int* d_a_qoff = nullptr;   // offset of the parameter's (m_i x u_i) block inside d_dqs
+  double* d_dqs = nullptr;   // d(scaled eigenvectors) / d(theta), per active parameter
+  ~GradDesc() { cudaFree(d_a_dim); cudaFree(d_a_kind); cudaFree(d_a_qoff); cudaFree(d_dqs); }
 };
 
 template <typename T>
@@ -56,47 +49,21 @@ int grad_desc_create(GradDesc** out, const Plan* pl, int n_active, const int32_t
   GRIEF_REQUIRE(n_active >= 0 && n_active <= 2 * kMaxDims, "grad_desc: n_active=%d", n_active);
   GradDesc* gd = new GradDesc();
   gd->n_active = n_active;
-  const int G = pl->n_groups;
-  std::vector<int> a_dim(n_active), a_kind(n_active), a_group(n_active), a_kk(n_active), a_qoff(n_active), a_foff(n_active);
-  std::vector<int> g_np(G, 0);
-  int qoff = 0, foff = 0;
+  std::vector<int> a_dim(n_active), a_kind(n_active), a_qoff(n_active);
+  int qoff = 0;
   for (int a = 0; a < n_active; ++a) {
     const int i = dims[a];
     if (i < 0 || i >= pl->d || kinds[a] < 0 || kinds[a] > 1) {
       delete gd;
       return fail(GRIEF_ERR_BAD_ARG, "grad_desc: parameter %d has dim=%d kind=%d", a, i, kinds[a]);
     }
-    int g = 0;
-    while (!(pl->group_begin[g] <= i && i < pl->group_begin[g + 1])) ++g;
-    a_dim[a] = i; a_kind[a] = kinds[a]; a_group[a] = g; a_kk[a] = g_np[g]++;
+    a_dim[a] = i; a_kind[a] = kinds[a];
     a_qoff[a] = qoff; qoff += pl->dims[i].m * pl->dims[i].u;
-    a_foff[a] = foff; foff += pl->dims[i].u;
   }
-  gd->sum_du = foff;
-  std::vector<int> g_dtoff(G + 1, 0);
-  int max_np = 1;
-  for (int g = 0; g < G; ++g) {
-    g_dtoff[g + 1] = g_dtoff[g] + pl->group_size[g] * g_np[g];
-    max_np = std::max(max_np, g_np[g]);
-  }
-  gd->dt_width = g_dtoff[G];
-  gd->max_np = max_np;
-  std::vector<int> ga((size_t)G * max_np, -1);
-  for (int a = 0; a < n_active; ++a) ga[(size_t)a_group[a] * max_np + a_kk[a]] = a;
-  gd->g_np_h = g_np;
-  gd->g_dtoff_h = g_dtoff;
   std::vector<double> dqs(dqs_concat, dqs_concat + qoff);
   int rc = upload_vec(&gd->d_a_dim, a_dim);
   if (rc == GRIEF_OK) rc = upload_vec(&gd->d_a_kind, a_kind);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_a_group, a_group);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_a_kk, a_kk);
   if (rc == GRIEF_OK) rc = upload_vec(&gd->d_a_qoff, a_qoff);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_a_foff, a_foff);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_g_np, g_np);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_g_dtoff, g_dtoff);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_g_slot0, pl->group_slot0);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_g_size, pl->group_size);
-  if (rc == GRIEF_OK) rc = upload_vec(&gd->d_ga, ga);
   if (rc == GRIEF_OK) rc = upload_vec(&gd->d_dqs, dqs);
   if (rc != GRIEF_OK) { delete gd; return rc; }
   *out = gd;
@@ -104,7 +71,6 @@ int grad_desc_create(GradDesc** out, const Plan* pl, int n_active, const int32_t
 }
 void grad_desc_destroy(GradDesc* gd) { delete gd; }
 int grad_desc_n_active(const GradDesc* gd) { return gd->n_active; }
-int grad_desc_dt_width(const GradDesc* gd) { return gd->dt_width; }
 
 __global__ void k_scale_vec(const double* __restrict__ in, double scale, int n, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,277 +120,362 @@ __device__ __forceinline__ void kern_eval_d(int kernel, double x, double u, doub
   }
 }
 
-struct DtParams {
-  const DimDesc* dims; const double* grid; const double* qs; const uint8_t* slot_k; const int* group_begin;
-  int d, sum_m, sum_u, max_group_dims, G;
-  // gradient description
-  int n_active, dt_width, sum_du, max_np;
-  const int *a_dim, *a_kind, *a_qoff, *a_foff, *g_np, *g_dtoff, *g_slot0, *ga;
-  const double* dqs;
-  const double* X; int64_t ldx; int64_t n_valid;   // rows >= n_valid produce zeros
-  double* DT; int RB;
+// ---- column sweep helpers (lane = row; all control flow is warp-uniform) ----
+// Key position k of sorted column c: slot ss[c * G + k]; level[c] = first key position where column c differs from c - 1 (G if equal).
+template <int G>
+struct Trie {
+  double pfx[G > 1 ? G - 1 : 1];     // pfx[k] = h_0 * ... * h_k of the open path (levels 0 .. G-2)
+  double hk[G > 1 ? G - 1 : 1];      // h_k of the open node at level k
+  int sk[G > 1 ? G - 1 : 1];         // its slot
 };
-
-// One block = RB rows.  smem: sK[RB][sum_m], sKl[RB][sum_m], sF[RB][sum_u], sdF[RB][sum_du].
-__global__ void __launch_bounds__(256) k_dtables(const DtParams P, int64_t rows_total) {
-  extern __shared__ double sm[];
-  double* sK = sm;
-  double* sKl = sK + (size_t)P.RB * P.sum_m;
-  double* sF = sKl + (size_t)P.RB * P.sum_m;
-  double* sdF = sF + (size_t)P.RB * P.sum_u;
-  const int64_t row0 = (int64_t)blockIdx.x * P.RB;
-  const int rows = (int)min((int64_t)P.RB, rows_total - row0);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int task = tid; task < rows * P.sum_m; task += nt) {
-    const int r = task / P.sum_m, c = task - r * P.sum_m;
-    int i = 0;
-    while (i + 1 < P.d && P.dims[i + 1].grid_off <= c) ++i;
-    const DimDesc dd = P.dims[i];
-    const int64_t row = row0 + r;
-    double k = 0.0, dk = 0.0;
-    if (row < P.n_valid) kern_eval_d(dd.kernel, P.X[row * P.ldx + i], P.grid[c], dd.variance, dd.lengthscale, k, dk);
-    sK[(size_t)r * P.sum_m + c] = k;
-    sKl[(size_t)r * P.sum_m + c] = dk;
-  }
-  __syncthreads();
-  for (int task = tid; task < rows * P.sum_u; task += nt) {
-    const int r = task / P.sum_u, c = task - r * P.sum_u;
-    int i = 0;
-    while (i + 1 < P.d && P.dims[i + 1].f_off <= c) ++i;
-    const DimDesc dd = P.dims[i];
-    const int k = c - dd.f_off;
-    const double* kv = sK + (size_t)r * P.sum_m + dd.grid_off;
-    const double* q = P.qs + dd.q_off + k;
-    double acc = 0.0;
-    for (int g = 0; g < dd.m; ++g) acc = fma(kv[g], q[(size_t)g * dd.u], acc);
-    sF[(size_t)r * P.sum_u + c] = acc;
-  }
-  for (int task = tid; task < rows * P.sum_du; task += nt) {
-    const int r = task / P.sum_du, c = task - r * P.sum_du;
-    int a = 0;
-    while (a + 1 < P.n_active && P.a_foff[a + 1] <= c) ++a;
-    const DimDesc dd = P.dims[P.a_dim[a]];
-    const int k = c - P.a_foff[a];
-    const double* kv = sK + (size_t)r * P.sum_m + dd.grid_off;
-    const double* kl = sKl + (size_t)r * P.sum_m + dd.grid_off;
-    const double* q = P.qs + dd.q_off + k;
-    const double* dq = P.dqs + P.a_qoff[a] + k;
-    const bool is_ls = P.a_kind[a] == 1;
-    const double inv_var = 1.0 / dd.variance;
-    double acc = 0.0;
-    for (int g = 0; g < dd.m; ++g) {
-      const double dk = is_ls ? kl[g] : kv[g] * inv_var;
-      acc = fma(dk, q[(size_t)g * dd.u], acc);
-      acc = fma(kv[g], dq[(size_t)g * dd.u], acc);
-    }
-    sdF[(size_t)r * P.sum_du + c] = acc;
-  }
-  __syncthreads();
-  for (int task = tid; task < rows * P.dt_width; task += nt) {
-    const int r = task / P.dt_width, c = task - r * P.dt_width;
-    int g = 0;
-    while (g + 1 < P.G && P.g_dtoff[g + 1] <= c) ++g;
-    const int np = P.g_np[g];
-    const int local = c - P.g_dtoff[g];
-    const int tl = local / np, kk = local - tl * np;
-    const int a = P.ga[(size_t)g * P.max_np + kk];
-    const int ia = P.a_dim[a];
-    const int s = P.g_slot0[g] + tl;
-    const uint8_t* ks = P.slot_k + (size_t)s * P.max_group_dims;
-    const int b0 = P.group_begin[g], b1 = P.group_begin[g + 1];
-    double v = sdF[(size_t)r * P.sum_du + P.a_foff[a] + ks[ia - b0]];
-    for (int i = b0; i < b1; ++i)
-      if (i != ia) v *= sF[(size_t)r * P.sum_u + P.dims[i].f_off + ks[i - b0]];
-    P.DT[(row0 + r) * (int64_t)P.dt_width + c] = v;
-  }
-}
 
 struct ContractParams {
-  const double* Z; int64_t ldz;      // slab rows x ldz
+  const double* Zt; int64_t ldz;     // Zp^T slab: [p_pad][ldz], rows of the slab contiguous
   const double* T; int stride;       // slab rows x stride
-  const double* DT; int dt_width;    // slab rows x dt_width
+  const double* X; int64_t ldx;      // slab rows x ldx
   const double* y;                   // slab rows
-  const double* gvec;                // p: b / sigma^2
-  const uint16_t* col_slot;          // p_pad x G
-  const int *g_np, *g_dtoff, *g_slot0;
-  int p, max_np;
-  int64_t rows;                      // valid rows in this slab
-  double* partial;                   // [gridDim.x][n_active], accumulated (+=) across slabs
-  const int* ga; int n_active;
+  const double* bvec;                // p_pad: b in sorted column order (0 for padding columns)
+  const uint16_t* ss; const uint8_t* level;      // sorted slots (key order), level
+  const DimDesc* dims; const double* grid; const double* qs; const uint8_t* slot_k; const int* slot_group; const int* group_begin;
+  int d, p_pad, width, sum_u, max_group_dims, m_max;
+  int64_t rows_valid;                // rows of the slab that exist (the rest are zero-padded tables)
+  int n_rg;                          // 32-row groups in the slab
+  double inv_noise;
+  double* acc; int acc_len;          // [total warps][acc_len]: M_i (sum m_i u_i doubles, layout of qs) then (gl_i, gv_i) per dimension
+  int regionA;                       // doubles of the per-warp scratch that starts as the table rows
 };
 
-constexpr int kContractK = 4;   // parameters per group accumulated in registers per sweep (measured at C3: 4 -> 36.2, 6 -> 38.4, 8 -> 41.5 ms per 1M rows)
-
-// One warp per data row, ONE sweep over the columns for all groups (a second sweep only if a group has more than
-// kContractK active parameters): per column the leave-one-group-out products L_g = Zt * prod_{g' != g} H_g' come from
-// prefix / suffix products, and L_g * DT[g][t_g(j)][kk] is accumulated per (group, parameter) in registers.
 template <int G>
-__global__ void __launch_bounds__(256) k_contract(const ContractParams P) {
+__global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  double* sRow = sm + (size_t)warp * (P.stride + P.dt_width);          // [stride] table row, [dt_width] DT row
-  double* sAcc = sm + (size_t)nw * (P.stride + P.dt_width) + (size_t)warp * P.n_active;
-  for (int a = lane; a < P.n_active; a += 32) sAcc[a] = 0.0;
-  int np[G], slot0[G], dtoff[G];
-#pragma unroll
-  for (int g = 0; g < G; ++g) { np[g] = P.g_np[g]; slot0[g] = P.g_slot0[g]; dtoff[g] = P.g_dtoff[g]; }
-  for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < P.rows; row += (int64_t)gridDim.x * nw) {
+  double* sA = sm + (size_t)warp * (P.regionA + P.stride * 32);      // table rows [32][stride]; later F, V, K scratch
+  double* sW = sA + P.regionA;                                        // [stride][32]
+  const int wg = blockIdx.x * nw + warp, wtot = gridDim.x * nw;
+  double* acc_out = P.acc + (size_t)wg * P.acc_len;
+  const int stride = P.stride;
+  constexpr int NB = 8;
+  for (int rg = wg; rg < P.n_rg; rg += wtot) {
     __syncwarp();
-    for (int e = lane; e < P.stride; e += 32) sRow[e] = P.T[row * P.stride + e];
-    for (int e = lane; e < P.dt_width; e += 32) sRow[P.stride + e] = P.DT[row * (int64_t)P.dt_width + e];
+    const int64_t row = (int64_t)rg * 32 + lane;
+    const bool valid = row < P.rows_valid;
+    {
+      const double* src = P.T + (size_t)rg * 32 * stride;
+      for (int e = lane; e < 32 * stride; e += 32) sA[e] = src[e];
+      for (int e = lane; e < 32 * stride; e += 32) sW[e] = 0.0;
+    }
     __syncwarp();
-    const double yr = P.y[row];
-    const double* zrow = P.Z + row * P.ldz;
-    const double* sDT = sRow + P.stride;
-    for (int k0 = 0; k0 < P.max_np; k0 += kContractK) {
-      double acc[G][kContractK];
+    const double* trow = sA + (size_t)lane * stride;
+    Trie<G> tr;
+    // ---- forward sweep: f = Phi[row, :] . b ----
+    double f = 0.0;
+    for (int c0 = 0; c0 < P.p_pad; c0 += NB) {
+      int lv[NB], sl[NB];
+      double bv[NB];
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int kk = 0; kk < kContractK; ++kk) acc[g][kk] = 0.0;
-      for (int j = lane; j < P.p; j += 32) {
-        const double zt = fma(yr, P.gvec[j], zrow[j]);
-        const uint16_t* cs = P.col_slot + (size_t)j * G;
-        int sl[G];
-        double h[G], L[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { sl[g] = cs[g]; h[g] = sRow[sl[g]]; }
-        double run = zt;                       // prefix pass: L[g] = zt * prod_{g' < g} h
-#pragma unroll
-        for (int g = 0; g < G; ++g) { L[g] = run; run *= h[g]; }
-        run = 1.0;                             // suffix pass: L[g] *= prod_{g' > g} h
-#pragma unroll
-        for (int g = G - 1; g >= 0; --g) { L[g] *= run; run *= h[g]; }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const double* dt = sDT + dtoff[g] + (size_t)(sl[g] - slot0[g]) * np[g] + k0;
-#pragma unroll
-          for (int kk = 0; kk < kContractK; ++kk)
-            if (k0 + kk < np[g]) acc[g][kk] = fma(L[g], dt[kk], acc[g][kk]);
-        }
+      for (int e = 0; e < NB; ++e) {
+        lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(P.level + c0 + e);
+        sl[e] = __ldg(P.ss + (size_t)(c0 + e) * G + (G - 1));
+        bv[e] = __ldg(P.bvec + c0 + e);
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g)
+      for (int e = 0; e < NB; ++e) {
+        if constexpr (G > 1) {
+          if (lv[e] < G - 1) {
 #pragma unroll
-        for (int kk = 0; kk < kContractK; ++kk)
-          if (k0 + kk < np[g]) {               // warp-uniform
-            const double v = warp_sum(acc[g][kk]);
-            if (lane == 0) sAcc[P.ga[(size_t)g * P.max_np + k0 + kk]] += v;
+            for (int k = 0; k < G - 1; ++k)
+              if (k >= lv[e]) {
+                const double h = trow[__ldg(P.ss + (size_t)(c0 + e) * G + k)];
+                tr.pfx[k] = k > 0 ? tr.pfx[k - 1] * h : h;
+              }
           }
+          f = fma(tr.pfx[G - 2] * trow[sl[e]], bv[e], f);
+        } else {
+          f = fma(trow[sl[e]], bv[e], f);
+        }
+      }
     }
-  }
-  __syncthreads();
-  // block partial = sum over warps (fixed order)
-  for (int a = threadIdx.x; a < P.n_active; a += blockDim.x) {
-    double s = 0.0;
-    for (int w = 0; w < nw; ++w) s += sm[(size_t)nw * (P.stride + P.dt_width) + (size_t)w * P.n_active + a];
-    P.partial[(size_t)blockIdx.x * P.n_active + a] += s;
-  }
-}
-
-__global__ void k_reduce_partials(const double* __restrict__ partial, int nblk, int n_active, double* __restrict__ out) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_active) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n_active + a];
-  out[a] = s;
-}
-
-// out[n] = sum_j Z[n,j] * Phi[n,j]   (diag of Phi* P^-1 Phi*^T for the predictive variance)
-template <int G>
-__global__ void __launch_bounds__(256) k_rowdot(const double* __restrict__ Z, int64_t ldz, const double* __restrict__ T, int stride,
-                                                const uint16_t* __restrict__ col_slot, int p, int64_t rows, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp; row < rows; row += nwarps) {
-    const double* t = T + row * stride;
-    const double* z = Z + row * ldz;
-    double acc = 0.0;
-    for (int j = lane; j < p; j += 32) {
-      double ph = t[col_slot[(size_t)j * G]];
+    const double a_n = valid ? (P.y[row] - f) * P.inv_noise : 0.0;
+    // ---- backward sweep: W[slot] += dL/dT ----
+    double S[G > 1 ? G - 1 : 1];
 #pragma unroll
-      for (int g = 1; g < G; ++g) ph *= t[col_slot[(size_t)j * G + g]];
-      acc = fma(ph, z[j], acc);
+    for (int k = 0; k < (G > 1 ? G - 1 : 1); ++k) S[k] = 0.0;
+    const double* zcol = P.Zt + row;
+    for (int c0 = 0; c0 < P.p_pad; c0 += NB) {
+      int lv[NB], sl[NB];
+      double zt[NB];
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(P.level + c0 + e);
+        sl[e] = __ldg(P.ss + (size_t)(c0 + e) * G + (G - 1));
+        zt[e] = fma(a_n, __ldg(P.bvec + c0 + e), -__ldcs(zcol + (size_t)(c0 + e) * P.ldz));
+      }
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        if constexpr (G > 1) {
+          if (lv[e] < G - 1) {
+            if (c0 + e > 0) {                  // close the open nodes of levels G-2 .. lv
+#pragma unroll
+              for (int k = G - 2; k >= 0; --k)
+                if (k >= lv[e]) {
+                  const double up = k > 0 ? tr.pfx[k - 1] : 1.0;
+                  sW[tr.sk[k] * 32 + lane] += up * S[k];
+                  if (k > 0) S[k - 1] = fma(tr.hk[k], S[k], S[k - 1]);
+                  S[k] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < G - 1; ++k)      // open levels lv .. G-2 for this column
+              if (k >= lv[e]) {
+                tr.sk[k] = __ldg(P.ss + (size_t)(c0 + e) * G + k);
+                tr.hk[k] = trow[tr.sk[k]];
+                tr.pfx[k] = k > 0 ? tr.pfx[k - 1] * tr.hk[k] : tr.hk[k];
+              }
+          }
+          sW[sl[e] * 32 + lane] += tr.pfx[G - 2] * zt[e];
+          S[G - 2] = fma(trow[sl[e]], zt[e], S[G - 2]);
+        } else {
+          sW[sl[e] * 32 + lane] += zt[e];
+        }
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[row] = acc;
+    if constexpr (G > 1) {                       // close what is still open
+#pragma unroll
+      for (int k = G - 2; k >= 0; --k) {
+        const double up = k > 0 ? tr.pfx[k - 1] : 1.0;
+        sW[tr.sk[k] * 32 + lane] += up * S[k];
+        if (k > 0) S[k - 1] = fma(tr.hk[k], S[k], S[k - 1]);
+      }
+    }
+    __syncwarp();
+    // ---- tail: W -> V (per-dimension factors) -> parameter sums; the table rows are dead, their space is scratch ----
+    double* sF = sA;                               // [sum_u][32]
+    double* sV = sF + (size_t)P.sum_u * 32;        // [sum_u][32]
+    double* sK = sV + (size_t)P.sum_u * 32;        // [m_max][33]
+    for (int i = 0; i < P.d; ++i) {                // F_i[k] = sum_g K_i(x, u_g) Qs_i[g, k]
+      const DimDesc dd = P.dims[i];
+      const double x = valid ? P.X[row * P.ldx + i] : 0.0;
+      for (int k = 0; k < dd.u; ++k) sF[(dd.f_off + k) * 32 + lane] = 0.0;
+      for (int g = 0; g < dd.m; ++g) {
+        double kv, dk;
+        kern_eval_d(dd.kernel, x, __ldg(P.grid + dd.grid_off + g), dd.variance, dd.lengthscale, kv, dk);
+        const double* q = P.qs + dd.q_off + (size_t)g * dd.u;
+        for (int k = 0; k < dd.u; ++k) sF[(dd.f_off + k) * 32 + lane] = fma(kv, __ldg(q + k), sF[(dd.f_off + k) * 32 + lane]);
+      }
+    }
+    for (int e = 0; e < P.sum_u; ++e) sV[e * 32 + lane] = 0.0;
+    for (int s = 2; s < P.width; ++s) {            // V_i[k_i(s)] += W[s] * prod_{i' != i} F_i'[k_i'(s)]
+      const int g = __ldg(P.slot_group + s);
+      const int b0 = __ldg(P.group_begin + g), b1 = __ldg(P.group_begin + g + 1);
+      const uint8_t* ks = P.slot_k + (size_t)s * P.max_group_dims;
+      const double w = sW[s * 32 + lane];
+      for (int i = b0; i < b1; ++i) {
+        double prod = w;
+        for (int i2 = b0; i2 < b1; ++i2)
+          if (i2 != i) prod *= sF[(P.dims[i2].f_off + (int)__ldg(ks + i2 - b0)) * 32 + lane];
+        sV[(P.dims[i].f_off + (int)__ldg(ks + i - b0)) * 32 + lane] += prod;
+      }
+    }
+    for (int i = 0; i < P.d; ++i) {                // parameter sums of dimension i and its M matrix
+      const DimDesc dd = P.dims[i];
+      const double x = valid ? P.X[row * P.ldx + i] : 0.0;
+      double gl = 0.0, gv = 0.0;
+      for (int g = 0; g < dd.m; ++g) {
+        double kv, dk;
+        kern_eval_d(dd.kernel, x, __ldg(P.grid + dd.grid_off + g), dd.variance, dd.lengthscale, kv, dk);
+        if (!valid) { kv = 0.0; dk = 0.0; }
+        sK[g * 33 + lane] = kv;
+        const double* q = P.qs + dd.q_off + (size_t)g * dd.u;
+        double U = 0.0;
+        for (int k = 0; k < dd.u; ++k) U = fma(sV[(dd.f_off + k) * 32 + lane], __ldg(q + k), U);
+        gl = fma(dk, U, gl);
+        gv = fma(kv, U, gv);
+      }
+      gl = warp_sum(gl);
+      gv = warp_sum(gv) / dd.variance;
+      const int ag = P.acc_len - 2 * P.d + 2 * i;
+      if (lane == 0) { acc_out[ag] += gl; acc_out[ag + 1] += gv; }
+      __syncwarp();
+      for (int q = lane; q < dd.m * dd.u; q += 32) {      // M_i[g, k] += sum_rows K[g][row] V[k][row]
+        const int g = q / dd.u, k = q - g * dd.u;
+        const double* kr = sK + g * 33;
+        const double* vr = sV + (size_t)(dd.f_off + k) * 32;
+        double s = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) s = fma(kr[r], vr[r], s);
+        acc_out[dd.q_off + q] += s;
+      }
+      __syncwarp();
+    }
   }
 }
 
-int launch_dtables(const Plan* pl, const GradDesc* gd, const double* X, int64_t ldx, int64_t n_valid, int64_t rows_total,
-                   double* DT, cudaStream_t stream) {
-  if (rows_total == 0 || gd->dt_width == 0) return GRIEF_OK;
-  const size_t per_row = (size_t)(2 * pl->sum_m + pl->sum_u + gd->sum_du) * sizeof(double);
-  int RB = (int)std::min<size_t>(32, (160 * 1024) / per_row);
-  if (RB < 1) return fail(GRIEF_ERR_UNSUPPORTED, "dtables: per-row scratch of %zu bytes exceeds shared memory", per_row);
-  DtParams P;
-  P.dims = pl->d_dims; P.grid = pl->d_grid; P.qs = pl->d_qs; P.slot_k = pl->d_slot_k; P.group_begin = pl->d_group_begin;
-  P.d = pl->d; P.sum_m = pl->sum_m; P.sum_u = pl->sum_u; P.max_group_dims = pl->max_group_dims; P.G = pl->n_groups;
-  P.n_active = gd->n_active; P.dt_width = gd->dt_width; P.sum_du = gd->sum_du; P.max_np = gd->max_np;
-  P.a_dim = gd->d_a_dim; P.a_kind = gd->d_a_kind; P.a_qoff = gd->d_a_qoff; P.a_foff = gd->d_a_foff;
-  P.g_np = gd->d_g_np; P.g_dtoff = gd->d_g_dtoff; P.g_slot0 = gd->d_g_slot0; P.ga = gd->d_ga; P.dqs = gd->d_dqs;
-  P.X = X; P.ldx = ldx; P.n_valid = n_valid; P.DT = DT; P.RB = RB;
-  const size_t smem = per_row * RB;
-  GRIEF_CUDA(cudaFuncSetAttribute(k_dtables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = (rows_total + RB - 1) / RB;
-  prof_begin(PROF_DTABLES, stream);
-  k_dtables<<<(unsigned)blocks, 256, smem, stream>>>(P, rows_total);
-  prof_end(PROF_DTABLES, stream);
-  GRIEF_CUDA(cudaGetLastError());
-  return GRIEF_OK;
+// grad[a] = sum over warps of (gl or gv of the parameter's dimension) + <dQs_a, sum over warps of M_dim>   (fixed order)
+__global__ void __launch_bounds__(256) k_grad_finish(const double* __restrict__ acc, int n_warps, int acc_len, int d, int n_active,
+                                                     const int* __restrict__ a_dim, const int* __restrict__ a_kind,
+                                                     const int* __restrict__ a_qoff, const DimDesc* __restrict__ dims,
+                                                     const double* __restrict__ dqs, double* __restrict__ grad) {
+  __shared__ double red[256];
+  const int a = blockIdx.x;
+  if (a >= n_active) return;
+  const DimDesc dd = dims[a_dim[a]];
+  double part = 0.0;
+  for (int q = threadIdx.x; q < dd.m * dd.u; q += blockDim.x) {
+    double m = 0.0;
+    for (int w = 0; w < n_warps; ++w) m += acc[(size_t)w * acc_len + dd.q_off + q];
+    part = fma(dqs[a_qoff[a] + q], m, part);
+  }
+  if (threadIdx.x == 0) {
+    const int ag = acc_len - 2 * d + 2 * a_dim[a] + (a_kind[a] == 1 ? 0 : 1);
+    double g = 0.0;
+    for (int w = 0; w < n_warps; ++w) g += acc[(size_t)w * acc_len + ag];
+    part += g;
+  }
+  red[threadIdx.x] = part;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) grad[a] = red[0];
 }
 
-int contract_blocks(int sms) { return sms * 2; }
+// out[row] = sum_c Zt[c][row] * Phi[row][c]   (diag of Phi* P^-1 Phi*^T for the predictive variance), lane = row, trie prefix products
+template <int G>
+__global__ void __launch_bounds__(128) k_rowdot_t(const double* __restrict__ Zt, int64_t ldz, const double* __restrict__ T, int stride,
+                                                  const uint16_t* __restrict__ ss, const uint8_t* __restrict__ level, int p_pad,
+                                                  int n_rg, int64_t rows_valid, double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double* sA = sm + (size_t)warp * stride * 32;
+  constexpr int NB = 8;
+  for (int rg = blockIdx.x * nw + warp; rg < n_rg; rg += gridDim.x * nw) {
+    __syncwarp();
+    const double* src = T + (size_t)rg * 32 * stride;
+    for (int e = lane; e < 32 * stride; e += 32) sA[e] = src[e];
+    __syncwarp();
+    const int64_t row = (int64_t)rg * 32 + lane;
+    const double* trow = sA + (size_t)lane * stride;
+    const double* zcol = Zt + row;
+    double pfx[G > 1 ? G - 1 : 1];
+    double acc = 0.0;
+    for (int c0 = 0; c0 < p_pad; c0 += NB) {
+      int lv[NB], sl[NB];
+      double z[NB];
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(level + c0 + e);
+        sl[e] = __ldg(ss + (size_t)(c0 + e) * G + (G - 1));
+        z[e] = __ldcs(zcol + (size_t)(c0 + e) * ldz);
+      }
+#pragma unroll
+      for (int e = 0; e < NB; ++e) {
+        if constexpr (G > 1) {
+          if (lv[e] < G - 1) {
+#pragma unroll
+            for (int k = 0; k < G - 1; ++k)
+              if (k >= lv[e]) {
+                const double h = trow[__ldg(ss + (size_t)(c0 + e) * G + k)];
+                pfx[k] = k > 0 ? pfx[k - 1] * h : h;
+              }
+          }
+          acc = fma(pfx[G - 2] * trow[sl[e]], z[e], acc);
+        } else {
+          acc = fma(trow[sl[e]], z[e], acc);
+        }
+      }
+    }
+    if (row < rows_valid) out[row] = acc;
+  }
+}
+
+// ---- launchers ----
+static int plan_m_max(const Plan* pl) {
+  int mm = 1;
+  for (auto& dd : pl->dims) mm = std::max(mm, dd.m);
+  return mm;
+}
+// warps per CTA that fit shared memory; per warp: region A (table rows [32][stride], later F [sum_u][32], V [sum_u][32], K [m_max][33])
+// and W [stride][32]
+static int contract_warps(const Plan* pl, size_t* smem_out, int* regionA_out) {
+  const int regionA = std::max(pl->stride * 32, 64 * pl->sum_u + 33 * plan_m_max(pl));
+  const size_t per_warp = ((size_t)regionA + (size_t)pl->stride * 32) * sizeof(double);
+  int nw = (int)std::min<size_t>(4, (220 * 1024) / per_warp);
+  if (smem_out) *smem_out = per_warp * std::max(nw, 1);
+  if (regionA_out) *regionA_out = regionA;
+  return nw;
+}
+int contract_acc_len(const Plan* pl) {
+  int qtot = 0;
+  for (auto& dd : pl->dims) qtot += dd.m * dd.u;
+  return qtot + 2 * pl->d;
+}
+int contract_total_warps(const Plan* pl, int sms) { return sms * std::max(1, contract_warps(pl, nullptr, nullptr)); }
 
 template <int G>
-static int launch_contract_g(const ContractParams& P, int blocks, size_t smem, cudaStream_t stream) {
-  GRIEF_CUDA(cudaFuncSetAttribute(k_contract<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_contract<G><<<blocks, 256, smem, stream>>>(P);
+static int launch_contract_g(const ContractParams& P, int blocks, int threads, size_t smem, cudaStream_t stream) {
+  GRIEF_CUDA(cudaFuncSetAttribute(k_contract_rows<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_contract_rows<G><<<blocks, threads, smem, stream>>>(P);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
 
-int launch_contract(const Plan* pl, const GradDesc* gd, const double* Z, int64_t ldz, const double* T, const double* DT,
-                    const double* y, const double* gvec, int64_t rows, double* partial, int sms, cudaStream_t stream) {
-  if (rows == 0 || gd->n_active == 0) return GRIEF_OK;
+// Zt: Zp^T slab (p_pad x ldz).  acc: contract_total_warps x contract_acc_len doubles, zeroed by the caller before the first slab.
+int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* y,
+                    const double* bvec, double noise_var, int64_t rows_blk, int64_t rows_valid, double* acc, int sms, cudaStream_t stream) {
+  if (rows_blk == 0) return GRIEF_OK;
+  size_t smem = 0;
+  int regionA = 0;
+  const int nw = contract_warps(pl, &smem, &regionA);
+  if (nw < 1) return fail(GRIEF_ERR_UNSUPPORTED, "contract: a table row of %d entries does not fit shared memory", pl->stride);
   ContractParams P;
-  P.Z = Z; P.ldz = ldz; P.T = T; P.stride = pl->stride; P.DT = DT; P.dt_width = gd->dt_width; P.y = y; P.gvec = gvec;
-  P.col_slot = pl->d_sorted_gslot; P.g_np = gd->d_g_np; P.g_dtoff = gd->d_g_dtoff; P.g_slot0 = gd->d_g_slot0;
-  // Z, gvec and the slot table are in the sorted column order (padding columns contribute 0)
-  P.p = pl->p_pad; P.max_np = gd->max_np; P.rows = rows; P.partial = partial; P.ga = gd->d_ga; P.n_active = gd->n_active;
-  const int nw = 8;
-  const size_t smem = ((size_t)nw * (pl->stride + gd->dt_width) + (size_t)nw * gd->n_active) * sizeof(double);
-  if (smem > 200 * 1024) return fail(GRIEF_ERR_UNSUPPORTED, "contract: %zu bytes of shared memory per block", smem);
-  const int blocks = contract_blocks(sms);
+  P.Zt = Zt; P.ldz = ldz; P.T = T; P.stride = pl->stride; P.X = X; P.ldx = ldx; P.y = y; P.bvec = bvec;
+  P.ss = pl->d_sorted_slot; P.level = pl->d_sorted_level;
+  P.dims = pl->d_dims; P.grid = pl->d_grid; P.qs = pl->d_qs; P.slot_k = pl->d_slot_k; P.slot_group = pl->d_slot_group; P.group_begin = pl->d_group_begin;
+  P.d = pl->d; P.p_pad = pl->p_pad; P.width = pl->width; P.sum_u = pl->sum_u; P.max_group_dims = pl->max_group_dims;
+  P.m_max = plan_m_max(pl);
+  P.rows_valid = rows_valid; P.n_rg = (int)(rows_blk / 32); P.inv_noise = 1.0 / noise_var;
+  P.acc = acc; P.acc_len = contract_acc_len(pl); P.regionA = regionA;
   int rc;
   prof_begin(PROF_CONTRACT, stream);
   switch (pl->n_groups) {
-    case 1: rc = launch_contract_g<1>(P, blocks, smem, stream); break;
-    case 2: rc = launch_contract_g<2>(P, blocks, smem, stream); break;
-    case 3: rc = launch_contract_g<3>(P, blocks, smem, stream); break;
-    case 4: rc = launch_contract_g<4>(P, blocks, smem, stream); break;
-    case 5: rc = launch_contract_g<5>(P, blocks, smem, stream); break;
-    case 6: rc = launch_contract_g<6>(P, blocks, smem, stream); break;
-    case 7: rc = launch_contract_g<7>(P, blocks, smem, stream); break;
-    case 8: rc = launch_contract_g<8>(P, blocks, smem, stream); break;
+    case 1: rc = launch_contract_g<1>(P, sms, nw * 32, smem, stream); break;
+    case 2: rc = launch_contract_g<2>(P, sms, nw * 32, smem, stream); break;
+    case 3: rc = launch_contract_g<3>(P, sms, nw * 32, smem, stream); break;
+    case 4: rc = launch_contract_g<4>(P, sms, nw * 32, smem, stream); break;
+    case 5: rc = launch_contract_g<5>(P, sms, nw * 32, smem, stream); break;
+    case 6: rc = launch_contract_g<6>(P, sms, nw * 32, smem, stream); break;
+    case 7: rc = launch_contract_g<7>(P, sms, nw * 32, smem, stream); break;
+    case 8: rc = launch_contract_g<8>(P, sms, nw * 32, smem, stream); break;
     default: return fail(GRIEF_ERR_UNSUPPORTED, "contract: %d groups", pl->n_groups);
   }
   prof_end(PROF_CONTRACT, stream);
   return rc;
 }
 
-int launch_reduce_partials(const double* partial, int nblk, int n_active, double* out, cudaStream_t stream) {
-  if (n_active == 0) return GRIEF_OK;
-  k_reduce_partials<<<(n_active + 127) / 128, 128, 0, stream>>>(partial, nblk, n_active, out);
+int launch_grad_finish(const Plan* pl, const GradDesc* gd, const double* acc, int sms, double* out, cudaStream_t stream) {
+  if (gd->n_active == 0) return GRIEF_OK;
+  k_grad_finish<<<gd->n_active, 256, 0, stream>>>(acc, contract_total_warps(pl, sms), contract_acc_len(pl), pl->d, gd->n_active,
+                                                  gd->d_a_dim, gd->d_a_kind, gd->d_a_qoff, pl->d_dims, gd->d_dqs, out);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
 
-int launch_rowdot(const Plan* pl, const double* Z, int64_t ldz, const double* T, int64_t rows, double* out, cudaStream_t stream) {
-  if (rows == 0) return GRIEF_OK;
-  const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, 148 * 8);
-#define RD(Gv) k_rowdot<Gv><<<blocks, 256, 0, stream>>>(Z, ldz, T, pl->stride, pl->d_sorted_gslot, pl->p_pad, rows, out)
+int launch_rowdot(const Plan* pl, const double* Zt, int64_t ldz, const double* T, int64_t rows_blk, int64_t rows_valid, double* out,
+                  cudaStream_t stream) {
+  if (rows_blk == 0 || rows_valid == 0) return GRIEF_OK;
+  const size_t per_warp = (size_t)pl->stride * 32 * sizeof(double);
+  const int nw = (int)std::min<size_t>(4, (220 * 1024) / per_warp);
+  if (nw < 1) return fail(GRIEF_ERR_UNSUPPORTED, "rowdot: a table row of %d entries does not fit shared memory", pl->stride);
+  const size_t smem = per_warp * nw;
+  const int n_rg = (int)(rows_blk / 32);
+  const unsigned blocks = (unsigned)std::min<int>((n_rg + nw - 1) / nw, 148 * 2);
+#define RD(Gv)                                                                                                          \
+  do {                                                                                                                  \
+    GRIEF_CUDA(cudaFuncSetAttribute(k_rowdot_t<Gv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    k_rowdot_t<Gv><<<blocks, nw * 32, smem, stream>>>(Zt, ldz, T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level,    \
+                                                      pl->p_pad, n_rg, rows_valid, out);                                \
+  } while (0)
   switch (pl->n_groups) {
     case 1: RD(1); break; case 2: RD(2); break; case 3: RD(3); break; case 4: RD(4); break;
     case 5: RD(5); break; case 6: RD(6); break; case 7: RD(7); break; case 8: RD(8); break;

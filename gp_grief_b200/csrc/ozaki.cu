@@ -1,10 +1,11 @@
 // FP64 GEMM on the INT8 tensor cores (Ozaki splitting, tcgen05 kind::i8) -- the fast path of both O(n p^2) products.
 //
 //   C (M x N, f64) (+)= A (M x K, f64) * B (N x K, f64)^T
-// Every operand row is scaled by a power of two so that |x| < 1 and cut into SD balanced 8-bit digits (SD = 4..7; 8 SD - 2 bits
+// Every operand row is scaled by a power of two so that |x| < 1 and cut into SD balanced 8-bit digits (SD = 3..7; 8 SD - 2 bits
 // + sign, rounded to nearest):
 //   x 2^-e = sum_s d_s 2^(-6 - 8 s),   A B^T = sum_{a,b} 2^(-12 - 8 (a + b)) D_a(A) D_b(B)^T,   pairs with a + b <= SD - 1 kept
-//   (SD (SD + 1) / 2 products: 28 / 21 / 15 / 10; what is dropped is below ~2^(2 - 8 SD) of the row-scale product).  Each digit
+//   (SD (SD + 1) / 2 products: 28 / 21 / 15 / 10; what is dropped is below ~2^(2 - 8 SD) of the row-scale product; for the
+//   symmetric product A = X X^T with SD even the pair a = b = SD / 2 of the first dropped group is kept as well).  Each digit
 //   product is an exact int8 x int8 -> int32 GEMM; one accumulation covers at most 16384 values of K (7 pairs x 2^14 x 2^14 < 2^31),
 //   longer K is split over blockIdx.z.
 // Kernel: one CTA per 128 x 128 tile.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b;
@@ -36,14 +37,15 @@ constexpr int A_SLICE = TM * KC, B_SLICE = TN * KC;            // one digit plan
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 constexpr int kStageBudget = 196 * 1024;                       // bytes of shared memory for the operand ring
 
-// Work items.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b:
-//   item 0: g = SD-1 .. SD-4   all SD + SD digit planes   (SD = 7: 22 MMAs per K chunk, 56 KB per stage)
-//   item 1: g = SD-5 .. 0      digits 0 .. SD-5 of both   (SD = 7:  6 MMAs per K chunk, 24 KB per stage); absent at SD = 4
+// Work items.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b (larger g = less significant).
+// With g_top the last group kept (g_top = SD - 1, or SD when the diagonal pair is added, see OzOpts::diag_pair):
+//   item 0: g = g_top .. g_top-3   all SD + SD digit planes   (SD = 7: g = 6..3, 22 MMAs per K chunk, 56 KB per stage)
+//   item 1: g = g_top-4 .. 0       digits 0 .. g_top-4 of both (SD = 7: g = 2..0, 6 MMAs per K chunk, 24 KB per stage)
+// Group g = SD (only with diag_pair, SD even) holds the single pair a = b = SD / 2.
 // Two sweeps over K per tile, two drains.
-template <int SD> __device__ __forceinline__ constexpr int num_items() { return SD > 4 ? 2 : 1; }
-template <int SD> __device__ __forceinline__ int item_g_hi(int it) { return it == 0 ? SD - 1 : SD - 5; }
-template <int SD> __device__ __forceinline__ int item_g_lo(int it) { return it == 0 ? (SD > 4 ? SD - 4 : 0) : 0; }
-template <int SD> __device__ __forceinline__ int item_digits(int it) { return it == 0 ? SD : SD - 4; }
+__host__ __device__ constexpr int item_g_hi(int g_top, int it) { return it == 0 ? g_top : g_top - 4; }
+__host__ __device__ constexpr int item_g_lo(int g_top, int it) { return it == 0 ? (g_top - 3 > 0 ? g_top - 3 : 0) : 0; }
+__host__ __device__ constexpr int item_digits(int sd, int g_top, int it) { return it == 0 ? sd : g_top - 3; }
 
 constexpr int oz_stage_bytes(int cl, int sd) { return sd * (A_SLICE + B_SLICE / cl); }
 constexpr int oz_stages(int cl, int sd) { return kStageBudget / oz_stage_bytes(cl, sd) > 6 ? 6 : kStageBudget / oz_stage_bytes(cl, sd); }
@@ -104,6 +106,7 @@ struct OzParams {
   int m_valid, n_valid;              // elements of C that exist
   int lower_only;                    // skip tiles entirely above the diagonal
   int accumulate;                    // 1: C += result, 0: C = result
+  int store_t;                       // 1: C is stored transposed, element (m, n) at C[n * ldc + m]
   int group_n;                       // column tiles per rasterisation group (CL = 1; 0: plain row-major tile order)
   int* err;
 };
@@ -113,8 +116,37 @@ struct OzParams {
 // (M = 256, N = 128, K = 32), each CTA's TMEM receives its 128 rows of the four accumulators and each CTA drains its own rows.
 // Both CTAs' TMA loads complete on the LEADER's full barrier (peer bit of the barrier address cleared), the leader's commits are
 // multicast to both CTAs' empty / tfull barriers, the drain threads of both CTAs arrive on the leader's tfree barrier.
-// SD = digits per operand.
-template <int CL, int SD>
+// SD = digits per operand, GT = last significance group kept (SD - 1, or SD with the diagonal pair).  Both are template
+// parameters: the MMA sequence of a K chunk must be straight-line code -- one thread issues it, and with run-time group bounds
+// that thread spent more cycles deciding than the tensor pipe spent multiplying (measured: 1650 instead of 2400 TOP/s).
+template <int CL, int SD, int GT, int IT>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint64_t da0, uint64_t db0, uint32_t idesc, bool first) {
+  constexpr int nd = item_digits(SD, GT, IT), g_hi = item_g_hi(GT, IT), g_lo = item_g_lo(GT, IT);
+  constexpr int kBSlice = B_SLICE / CL;
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {            // accumulator gi <-> group g_hi - gi, TMEM columns gi*128 ..
+    const int g = g_hi - gi;
+    if (g < g_lo) continue;
+    bool fresh = first;
+#pragma unroll
+    for (int a = 0; a < SD; ++a) {
+      const int b = g - a;
+      if (a >= nd || b < 0 || b >= nd) continue;
+      if (g == SD && a != b) continue;          // group SD: the diagonal pair only
+      const uint64_t da = da0 + (uint64_t)(a * (A_SLICE >> 4)), db = db0 + (uint64_t)(b * (kBSlice >> 4));
+      const uint32_t accf = fresh ? 0u : 1u;
+      if (CL == 1)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+                         tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+      else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
+                         tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
+      fresh = false;
+    }
+  }
+}
+
+template <int CL, int SD, int GT>
 __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps maps, const OzParams prm) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -125,7 +157,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
   constexpr int kBSlice = B_SLICE / CL;              // this CTA's share of a B digit plane: 128 or 64 rows of 32 bytes
   constexpr int kStageBytes = oz_stage_bytes(CL, SD);
   constexpr int kStages = oz_stages(CL, SD);
-  constexpr int kNumItems = num_items<SD>();
+  constexpr int kNumItems = GT > 3 ? 2 : 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int bn = CL == 2 ? blockIdx.y : blockIdx.x, bm = CL == 2 ? blockIdx.x : blockIdx.y;   // CTA pairs are adjacent in x
   if (CL == 1 && prm.group_n > 0) {                  // grouped rasterisation: all row tiles pass over group_n column tiles at a time
@@ -150,7 +182,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
     if (!prm.accumulate)
       for (int e = tid; e < TM * TN; e += 192) {
         const int r = bm * TM + e / TN, c = bn * TN + e % TN;
-        if (r < prm.m_valid && c < prm.n_valid) Cz[(size_t)r * prm.ldc + c] = 0.0;
+        if (r < prm.m_valid && c < prm.n_valid) Cz[prm.store_t ? (size_t)c * prm.ldc + r : (size_t)r * prm.ldc + c] = 0.0;
       }
     return;
   }
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
   if (tid == 128) {                                 // ---- TMA producer (warp 4) ----
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
-      const int nd = item_digits<SD>(it);
+      const int nd = item_digits(SD, GT, it);
       const uint32_t bytes = (uint32_t)(nd * (A_SLICE + kBSlice));
       const CUtensorMap* mA = &maps.m[it == 0 ? 0 : 1];
       const CUtensorMap* mB = &maps.m[CL == 2 ? (it == 0 ? 4 : 5) : (it == 0 ? 2 : 3)];
@@ -221,7 +253,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
     const uint64_t dhi = (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);   // K-major SWIZZLE_32B: LBO 1, SBO 256 B, v1
     int q = 0;
     for (int it = 0; it < kNumItems && ok; ++it) {
-      const int nd = item_digits<SD>(it), g_hi = item_g_hi<SD>(it), g_lo = item_g_lo<SD>(it);
+      const int nd = item_digits(SD, GT, it);
       if (it > 0) ok = wait_bounded(tfree, (uint32_t)((it - 1) & 1));     // accumulators drained
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -232,25 +264,8 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = ring + s * kStageBytes, sb = sa + nd * A_SLICE;
         const uint64_t da0 = dhi | (uint64_t)((sa >> 4) & 0x3FFF), db0 = dhi | (uint64_t)((sb >> 4) & 0x3FFF);
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {            // accumulator gi <-> group g_hi - gi, TMEM columns gi*128 ..
-          const int g = g_hi - gi;
-          if (g < g_lo) break;
-          uint32_t accf = c > 0 ? 1u : 0u;
-#pragma unroll
-          for (int a = 0; a < SD; ++a) {
-            const int b = g - a;
-            if (a >= nd || b < 0 || b >= nd) continue;
-            const uint64_t da = da0 + (uint64_t)(a * (A_SLICE >> 4)), db = db0 + (uint64_t)(b * (kBSlice >> 4));
-            if (CL == 1)
-              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
-                               tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
-            else
-              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(
-                               tmem + (uint32_t)(gi * TN)), "l"(da), "l"(db), "r"(idesc), "r"(accf) : "memory");
-            accf = 1u;
-          }
-        }
+        if (it == 0) issue_chunk<CL, SD, GT, 0>(tmem, da0, db0, idesc, c == 0);
+        else issue_chunk<CL, SD, GT, 1>(tmem, da0, db0, idesc, c == 0);
         if (CL == 1)
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
         else
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
       live = wait_bounded(tfull, (uint32_t)(it & 1));
       if (!live) { if (lane == 0) atomicExch(prm.err, 3); break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int g_hi = item_g_hi<SD>(it), ng = g_hi - item_g_lo<SD>(it) + 1;
+      const int g_hi = item_g_hi(GT, it), ng = g_hi - item_g_lo(GT, it) + 1;
       double wgt[4];
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) wgt[gi] = gi < ng ? ldexp(1.0, -12 - 8 * (g_hi - gi)) * rs : 0.0;
@@ -297,6 +312,26 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] = fma(wgt[gi], (double)(int)v[j], acc[j]);
         }
+        const bool keep = (it > 0) || prm.accumulate;
+        if (prm.store_t) {                           // C^T: for a fixed column the 32 lanes (= 32 consecutive rows) are contiguous
+          const int row = row0 + lane;
+          if (row < prm.m_valid) {
+            double old[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = bn * TN + c0 + j;
+              old[j] = (keep && col < prm.n_valid) ? __ldcg(Cz + (size_t)col * prm.ldc + row) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = bn * TN + c0 + j;
+              double cs;
+              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cs) : "r"(cscale + (uint32_t)(c0 + j) * 8));
+              if (col < prm.n_valid) __stcg(Cz + (size_t)col * prm.ldc + row, old[j] + acc[j] * cs);
+            }
+          }
+          continue;
+        }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 16; ++j)                // own row, 16 columns -> staging [row][17]
@@ -309,7 +344,6 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
         const int col = bn * TN + c0 + j, rbase = row0 + (lane >> 4);
         const bool col_ok = col < prm.n_valid;
         double* dst0 = Cz + (size_t)rbase * prm.ldc + col;
-        const bool keep = (it > 0) || prm.accumulate;
         double old[16], val[16];
 #pragma unroll
         for (int h = 0; h < 16; ++h) old[h] = (keep && col_ok && rbase + 2 * h < prm.m_valid) ? __ldcg(dst0 + (size_t)(2 * h) * prm.ldc) : 0.0;
@@ -388,12 +422,12 @@ int ozaki_slice(const double* X, int64_t ld, int rows, int K, int* exps, int exp
   return GRIEF_OK;
 }
 
-template <int CL, int SD>
+template <int CL, int SD, int GT>
 static int launch_ozaki(const OzMaps& maps, const OzParams& prm, dim3 grid, cudaStream_t stream) {
   constexpr size_t smem = oz_smem_bytes(CL, SD);
   static_assert(smem <= 227 * 1024, "k_ozaki: shared memory");
   // function attributes are per device: set on every launch (a host-side table lookup in the runtime)
-  GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<CL, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GRIEF_CUDA(cudaFuncSetAttribute(k_ozaki<CL, SD, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (CL == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -401,9 +435,9 @@ static int launch_ozaki(const OzMaps& maps, const OzParams& prm, dim3 grid, cuda
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    GRIEF_CUDA(cudaLaunchKernelEx(&cfg, k_ozaki<CL, SD>, maps, prm));
+    GRIEF_CUDA(cudaLaunchKernelEx(&cfg, k_ozaki<CL, SD, GT>, maps, prm));
   } else {
-    k_ozaki<CL, SD><<<grid, 192, smem, stream>>>(maps, prm);
+    k_ozaki<CL, SD, GT><<<grid, 192, smem, stream>>>(maps, prm);
   }
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
@@ -425,7 +459,12 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   GRIEF_REQUIRE(split_chunks * KC <= 16384, "ozaki_gemm: %d values of K per accumulation exceed the int32 budget of 16384", split_chunks * KC);
   alignas(64) OzMaps maps;
   memset(&maps, 0, sizeof(maps));
-  const int light = SD - 4;                          // digit planes of the second sweep (none at SD = 4)
+  // Symmetric product (A = Phi^T Phi: both operands are the same matrix) with an even digit count: the first dropped group g = SD
+  // contains the pair a = b = SD / 2, whose product d_a(x) d_a(x') is a SQUARE on the diagonal (and positively correlated for
+  // correlated columns): a bias of ~2^(2 - 8 SD) that does not average out over K, measured as 10x the random truncation error.
+  // That one pair is kept (one more MMA per K chunk); for independent operands (Z = Phi B) it is zero-mean like the others.
+  const int g_top = (opt.diag_pair && SD % 2 == 0) ? SD : SD - 1;
+  const int light = g_top - 3;                       // digit planes of the second sweep
   {
     int rc = make_plane_map(&maps.m[0], pa, M, rows_a_alloc, kp, TM, SD, SD);
     if (rc == GRIEF_OK) rc = make_plane_map(&maps.m[2], pb, N, rows_b_alloc, kp, TN, SD, SD);
@@ -440,7 +479,7 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   OzParams prm;
   prm.C = C; prm.ldc = ldc; prm.ea = ea; prm.eb = eb;
   prm.chunks = chunks; prm.split_chunks = split_chunks; prm.c_split_stride = c_split_stride;
-  prm.m_valid = M; prm.n_valid = N; prm.lower_only = lower_only ? 1 : 0; prm.accumulate = accumulate ? 1 : 0; prm.err = opt.err;
+  prm.m_valid = M; prm.n_valid = N; prm.lower_only = lower_only ? 1 : 0; prm.accumulate = accumulate ? 1 : 0; prm.store_t = opt.store_t; prm.err = opt.err;
   const int tiles_m = (M + TM - 1) / TM, tiles_n = (N + TN - 1) / TN;
   // rasterisation: the B digit panels of one group of column tiles (128 rows x K of a CTA x SD bytes each) take <= ~60 MB of the 126 MB L2
   prm.group_n = 0;
@@ -454,12 +493,11 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   const bool pairs = opt.cluster && tiles_m >= 2;     // CTA pairs adjacent in x (cluster (2,1,1)); an odd last pair runs one CTA on zero rows
   const dim3 grid = pairs ? dim3((tiles_m + 1) / 2 * 2, tiles_n, splits) : dim3(tiles_n, tiles_m, splits);
   int rc;
-#define GRIEF_OZ(SD_)                                                                                              \
-  case SD_: rc = pairs ? launch_ozaki<2, SD_>(maps, prm, grid, stream) : launch_ozaki<1, SD_>(maps, prm, grid, stream); break
-  switch (SD) {
-    GRIEF_OZ(4); GRIEF_OZ(5); GRIEF_OZ(6); GRIEF_OZ(7);
-    default: return fail(GRIEF_ERR_BAD_ARG, "ozaki_gemm: %d digits", SD);
-  }
+#define GRIEF_OZ(SD_, GT_)                                                                                         \
+  if (SD == SD_ && g_top == GT_)                                                                                   \
+    rc = pairs ? launch_ozaki<2, SD_, GT_>(maps, prm, grid, stream) : launch_ozaki<1, SD_, GT_>(maps, prm, grid, stream)
+  rc = fail(GRIEF_ERR_BAD_ARG, "ozaki_gemm: %d digits with last group %d", SD, g_top);
+  GRIEF_OZ(3, 2); GRIEF_OZ(4, 3); GRIEF_OZ(4, 4); GRIEF_OZ(5, 4); GRIEF_OZ(6, 5); GRIEF_OZ(6, 6); GRIEF_OZ(7, 6);
 #undef GRIEF_OZ
   if (rc != GRIEF_OK) return rc;
   if (launches) *launches += 1;

@@ -67,7 +67,7 @@ __device__ __forceinline__ void store_digits(double v, double scale, int sd, int
   base[0 * plane_stride] = (int8_t)(hi >> 16);       // digit 0 = byte 6 (most significant)
   base[1 * plane_stride] = (int8_t)(hi >> 8);
   base[2 * plane_stride] = (int8_t)hi;
-  base[3 * plane_stride] = (int8_t)(lo >> 24);
+  if (sd > 3) base[3 * plane_stride] = (int8_t)(lo >> 24);
   if (sd > 4) base[4 * plane_stride] = (int8_t)(lo >> 16);
   if (sd > 5) base[5 * plane_stride] = (int8_t)(lo >> 8);
   if (sd > 6) base[6 * plane_stride] = (int8_t)lo;
@@ -438,6 +438,8 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
     GRIEF_CUDA(cudaMemsetAsync(part, 0, part_doubles * sizeof(double), stream));
     if (r) GRIEF_CUDA(cudaMemsetAsync(r_acc, 0, (size_t)pp * sizeof(double), stream));
   }
+  OzOpts oz_gram = oz_opts(pl, sd);
+  oz_gram.diag_pair = 1;
   GemmOpts o;
   o.lower_only = true;
   o.splits = s.splits;
@@ -467,7 +469,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
     if (rc != GRIEF_OK) return rc;
     prof_begin(PROF_GRAM, stream);
     if (i8)
-      rc = ozaki_gemm(planes, pp, exps, pp, planes, pp, exps, pp, (int)R, part, pp, r0 > 0, true, s.splits, (int64_t)pp * pp, oz_opts(pl, sd), stream, launches);
+      rc = ozaki_gemm(planes, pp, exps, pp, planes, pp, exps, pp, (int)R, part, pp, r0 > 0, true, s.splits, (int64_t)pp * pp, oz_gram, stream, launches);
     else
       rc = gemm_nt_ex(PhiT, s.slab_rows, PhiT, s.slab_rows, part, pp, pp, pp, (int)R, 1.0, r0 > 0 ? 1.0 : 0.0, o, stream, launches);
     prof_end(PROF_GRAM, stream);
@@ -547,12 +549,13 @@ int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_
   return ozaki_slice(Bperm, pl->p_pad, pl->p_pad, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, pl->opts.digits_z, pl->d_err, stream);
 }
 
-// Z (slab_rows x ldz, columns in SORTED order) = Phi(slab) * B, B symmetric given as Bperm (p_pad x p_pad, launch_permute_b).
-// scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
-int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
+// Zt (p_pad x ldz, TRANSPOSED: sorted column c of Z = Phi(slab) * B is row c of Zt, the slab's data rows are contiguous) -- the
+// layout its consumers (k_contract_rows, k_rowdot_t: lane = data row) read with full coalescing.  B symmetric, given as Bperm
+// (p_pad x p_pad, launch_permute_b).  scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
+int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Zt,
                  int64_t ldz, cudaStream_t stream, int* launches) {
   GRIEF_REQUIRE(slab_rows % kBuildRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kBuildRows);
-  GRIEF_REQUIRE(ldz >= pl->p_pad, "zgemm: ldz=%lld must be >= p_pad=%d", (long long)ldz, pl->p_pad);
+  GRIEF_REQUIRE(ldz >= slab_rows, "zgemm: ldz=%lld must be >= slab_rows=%lld", (long long)ldz, (long long)slab_rows);
   if (slab_rows == 0) return GRIEF_OK;
   const bool i8 = pl->opts.gemm_mode == 1;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
@@ -569,11 +572,13 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   prof_begin(PROF_ZGEMM, stream);
   if (i8) {
     GRIEF_REQUIRE(pl->p_pad <= kOzakiKRange, "zgemm: p_pad=%d exceeds the INT8 path's K range of %d", pl->p_pad, kOzakiKRange);
-    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p_pad, z.eb, pl->p_pad, pl->p_pad, Z, ldz, false, false, 1, 0,
-                    oz_opts(pl, pl->opts.digits_z), stream, launches);
+    OzOpts oo = oz_opts(pl, pl->opts.digits_z);
+    oo.store_t = 1;
+    rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p_pad, z.eb, pl->p_pad, pl->p_pad, Zt, ldz, false, false, 1, 0, oo, stream, launches);
   } else {
     GemmOpts o;
-    rc = gemm_nt_ex(z.Phi, pl->p_pad, Bperm, pl->p_pad, Z, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);
+    o.store_t = true;
+    rc = gemm_nt_ex(z.Phi, pl->p_pad, Bperm, pl->p_pad, Zt, ldz, (int)slab_rows, pl->p_pad, pl->p_pad, 1.0, 0.0, o, stream, launches);
   }
   prof_end(PROF_ZGEMM, stream);
   if (rc == GRIEF_OK && launches) *launches += 1;

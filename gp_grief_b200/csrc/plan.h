@@ -98,10 +98,12 @@ int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, doubl
 
 // FP64 GEMM on the INT8 tensor cores (ozaki.cu).  Digit planes: [digits][rows_alloc][K rounded up to 32] int8; buffers are always
 // sized for kOzMaxDigits planes, `digits` of them are written and read.
-constexpr int kOzMinDigits = 4, kOzMaxDigits = 7;
+constexpr int kOzMinDigits = 3, kOzMaxDigits = 7;
 struct OzOpts {
   int digits = kOzMaxDigits;   // balanced 8-bit digits per operand: 8 * digits - 2 bits + sign below the row maximum
   int cluster = 0;             // 1: CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles
+  int store_t = 0;             // 1: C is written transposed (element (m, n) at C[n * ldc + m])
+  int diag_pair = 0;           // 1: both operands are the same matrix (Gram): keep the pair a = b = digits / 2 of group g = digits
   int* err = nullptr;          // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value
 };
 size_t ozaki_plane_bytes(int64_t rows, int K);

@@ -161,15 +161,16 @@ class DevicePlan(object):
         nat.check(nat.lib().grief_grad_setup(self._h, na, nat.host_ptr(dims_a), nat.host_ptr(kinds_a), nat.host_ptr(dqs)))
         self.n_active = na
 
-    def grad_theta(self, T, X_dev, y_dev, n, G2, b, noise_var):
+    def grad_theta(self, T, X_dev, y_dev, n, Pinv, b, noise_var):
+        """d LML / d theta of the active parameters from P^-1 (p, p) and b = P^-1 r (device tensors)."""
         torch = _torch()
         g = torch.zeros((max(self.n_active, 1),), dtype=torch.float64, device=T.device)
         need = nat.lib().grief_grad_workspace_bytes(self._h, n)
         ws = torch.empty((max(need, 256),), dtype=torch.uint8, device=T.device)
         ldx = X_dev.stride(0) if n > 1 else self.d
-        G2 = _even_ld(G2)
+        Pinv = _even_ld(Pinv)
         nat.check(nat.lib().grief_grad_theta(self._h, nat.dev_ptr(T), nat.dev_ptr(X_dev), ldx, nat.dev_ptr(y_dev), n,
-                                             nat.dev_ptr(G2), G2.stride(0), nat.dev_ptr(b), float(noise_var),
+                                             nat.dev_ptr(Pinv), Pinv.stride(0), nat.dev_ptr(b), float(noise_var),
                                              nat.dev_ptr(g), nat.dev_ptr(ws), ws.numel(), nat.stream_ptr()))
         return g[:self.n_active]
 

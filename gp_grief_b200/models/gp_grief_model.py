@@ -237,7 +237,7 @@ class GPGriefModel(BaseModel):
         n_base = parameters.size - 1 - self.kern.n_eigs
         theta_free = np.nonzero(free[1:1 + n_base])[0]
         need_theta = self.kern.opt_kernel_params and theta_free.size > 0
-        out = self._cov_setup(want_grad=True, want_G2=need_theta)
+        out = self._cov_setup(want_grad=True)
         log_like = np.array([[out['lml']]])
         if self.kern.reweight_eig_funs:
             gradient[-self.kern.n_eigs:] = out['grad_w'].cpu().numpy()
@@ -267,7 +267,7 @@ class GPGriefModel(BaseModel):
         plan = self._plan()
         dqs = self.kern.scaled_eigvec_derivatives(active)
         plan.grad_setup([a[0] for a in active], [0 if a[1] == 'variance' else 1 for a in active], dqs)
-        g = plan.grad_theta(self._dev['tables'], self._X_dev, self._y_dev, self.num_local, solve_out['G2'],
+        g = plan.grad_theta(self._dev['tables'], self._X_dev, self._y_dev, self.num_local, solve_out['Pinv'],
                             solve_out['b'], float(self.noise_var))
         if self._dist is not None:
             self._dist.all_reduce(g)

@@ -145,9 +145,9 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
  *          (D = 7: the accuracy class of DGEMM)
  *       3  as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2; correct and
  *          tested, not faster on a power-capped B200
- *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (4..7).  A feeds a Cholesky factorisation: keep it at DGEMM class unless the caller's
+ *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (3..7).  A feeds a Cholesky factorisation: keep it at DGEMM class unless the caller's
  *                          tolerance allows less
- *   GRIEF_OPT_DIGITS_Z     D of Z = Phi B (pass 2 and the predictive variance), 4..7
+ *   GRIEF_OPT_DIGITS_Z     D of Z = Phi B (pass 2: B = P^-1, and the predictive variance), 3..7
  *   GRIEF_OPT_SLAB_BUDGET  bytes of HBM for the Phi^T slab that pass 1 stages per GEMM launch (default 4 GiB; 0 restores it).  Smaller
  *                          budgets mean more, shorter launches; results are identical up to the order of the fixed-order accumulation
  * grief_set_slab_budget / grief_set_gemm_mode / grief_get_gemm_mode are the round-1 spellings of the default setters.
@@ -199,7 +199,7 @@ int grief_sumsq(const double* y_dev, int64_t n, double* out_dev, void* ws_dev, v
  *   b_dev           out (p): P^-1 r  (== alpha_p of models/gp_grief_model.py:97)
  *   Pinv_dev        out (p,p) or NULL: P^-1 (needed for the gradients)
  *   grad_w_dev      out (p) or NULL
- *   G2_dev          out (p,p) or NULL: -(P^-1 + b b^T / noise_var), operand of grief_grad_pass
+ *   G2_dev          out (p,p) or NULL: -(P^-1 + b b^T / noise_var) (the round-1 operand of pass 2; grief_grad_theta takes P^-1 now)
  *   scalars_host    out double[GRIEF_SC_COUNT]
  *   info_host       out: 0, or the order of the leading minor that is not positive definite
  */
@@ -219,14 +219,16 @@ int grief_solve_lml(grief_ctx* ctx, int p, const double* A_dev, int64_t lda, con
  *                       the scaled eigenvectors passed to grief_plan_create (host-side eigen-perturbation)
  * grief_grad_theta: grad_dev[a] = d LML / d theta_a for the rows given (a row shard when multi-GPU: sum over
  *   ranks), holding the selected eigen-index set fixed (as finite differences implicitly do).
+ *   d LML / d theta = sum_n sum_j Zt[n,j] dPhi[n,j]/dtheta with Zt = -Phi P^-1 + a b^T, a = (y - Phi b) / noise_var: only Phi P^-1
+ *   goes through the O(n p^2) GEMM (arithmetic and digits per the plan's options), the rank-one part is formed in FP64.
  *   T_dev          tables of the n rows (grief_build_tables)
- *   G2_dev, ldg    -(P^-1 + b b^T/noise_var) from grief_solve_lml, symmetric, ldg even
+ *   Pinv_dev, ldp  P^-1 from grief_solve_lml, symmetric
  *   b_dev          P^-1 r from grief_solve_lml
  */
 int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat);
 size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n);
 int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev,
-                     int64_t n, const double* G2_dev, int64_t ldg, const double* b_dev, double noise_var,
+                     int64_t n, const double* Pinv_dev, int64_t ldp, const double* b_dev, double noise_var,
                      double* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /*

@@ -82,7 +82,7 @@ def test_digit_count_controls_the_error_of_both_products(kernel):
     q_ref = ((Phi @ B) * Phi).sum(1).cpu().numpy()
     assert plan.get_option(nat.OPT_DIGITS_GRAM) == 7 and plan.get_option(nat.OPT_DIGITS_Z) == 7
     errs_a, errs_q = [], []
-    for D in (4, 5, 6, 7):
+    for D in (3, 4, 5, 6, 7):
         plan.set_option(nat.OPT_DIGITS_GRAM, D)
         plan.set_option(nat.OPT_DIGITS_Z, D)
         A = plan.gram(T, n).cpu().numpy()
@@ -94,11 +94,12 @@ def test_digit_count_controls_the_error_of_both_products(kernel):
         errs_q.append(eq)
         bound = max(2.0 ** -(8 * D - 10), 2e-13)            # fp64 reference itself is ~1e-14 here
         assert ea < bound and eq < 64 * bound, (D, ea, eq, bound)
-    assert errs_a[0] > 30 * errs_a[1] and errs_a[1] > 10 * errs_a[2], errs_a
+    assert all(errs_a[i] > 10 * errs_a[i + 1] for i in range(3)) and errs_a[3] >= errs_a[4], errs_a
+    assert all(errs_q[i] > 10 * errs_q[i + 1] for i in range(3)), errs_q
     with pytest.raises(ValueError):
         plan.set_option(nat.OPT_DIGITS_Z, 8)
     with pytest.raises(ValueError):
-        plan.set_option(nat.OPT_DIGITS_GRAM, 3)
+        plan.set_option(nat.OPT_DIGITS_GRAM, 2)
 
 
 @pytest.mark.parametrize("digits", [(6, 6), (6, 5), (7, 5)])
@@ -186,6 +187,6 @@ def test_empty_row_shard_evaluates_to_the_prior_terms():
     model = gp.models.GPGriefModel(np.zeros((0, d)), np.zeros((0, 1)), kern, noise_var=0.1)
     st = model._stats()
     assert float(st['A'].abs().max()) == 0.0 and float(st['r'].abs().max()) == 0.0 and float(st['s']) == 0.0
-    out = model._cov_setup(want_grad=True, want_G2=True)
+    out = model._cov_setup(want_grad=True)
     g = model._theta_gradient([(0, 'lengthscale'), (1, 'variance')], out)
     assert_array_equal(g, np.zeros(2))

@@ -37,6 +37,6 @@ for rep in range(2):
     active = [pmap[i] for i in theta_free]
     t0 = tic(); dqs = kern.scaled_eigvec_derivatives(active); t["eigvec_derivatives(host)"] = tic() - t0
     t0 = tic(); plan.grad_setup([a[0] for a in active], [0 if a[1] == 'variance' else 1 for a in active], dqs); t["grad_setup"] = tic() - t0
-    t0 = tic(); g = plan.grad_theta(model._dev['tables'], model._X_dev, model._y_dev, n, out['G2'], out['b'], 0.1); t["grad_theta"] = tic() - t0
+    t0 = tic(); g = plan.grad_theta(model._dev['tables'], model._X_dev, model._y_dev, n, out['Pinv'], out['b'], 0.1); t["grad_theta"] = tic() - t0
     t0 = tic(); ll, gr = model.log_likelihood(return_gradient=True); t["log_likelihood(cached parts + repeat grad)"] = tic() - t0
     print(json.dumps({k: round(v * 1e3, 2) for k, v in t.items()}))
