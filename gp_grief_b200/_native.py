@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libgrief_b200.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_NOT_PD, ERR_UNSUPPORTED, ERR_LIBRARY = 0, 1, 2, 3, 4, 5
 SC_LML, SC_YT_ALPHA, SC_LOGDET, SC_GRAD_NOISE, SC_RTB, SC_ALPHA_SQ, SC_TRACE, SC_COUNT = range(8)
-KERNEL_IDS = {"RBF": 0, "Exponential": 1, "Matern32": 2, "Matern52": 3}
-OPT_GEMM_MODE, OPT_DIGITS_GRAM, OPT_DIGITS_Z, OPT_SLAB_BUDGET = 0, 1, 2, 3
+KERNEL_IDS = {"RBF": 0, "Exponential": 1, "Matern32": 2, "Matern52": 3, "host": 4}
+OPT_GEMM_MODE, OPT_DIGITS_GRAM, OPT_DIGITS_Z, OPT_SLAB_BUDGET, OPT_DIGITS_VAR = 0, 1, 2, 3, 4
 
 c_int, c_i64, c_size, c_void, c_dbl = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_double
 _P = ctypes.POINTER
@@ -38,6 +38,7 @@ SIGNATURES = {
     "grief_table_rows": (c_i64, [c_i64]),
     "grief_build_tables": (c_int, [c_void, c_void, c_i64, c_i64, c_void, c_void]),
     "grief_build_tables_dx": (c_int, [c_void, c_void, c_i64, c_i64, c_int, c_void, c_void]),
+    "grief_build_tables_kxu": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_i64, c_int, c_void, c_void]),
     "grief_phi_rows": (c_int, [c_void, c_void, c_i64, c_void, c_void]),
     "grief_gram_workspace_bytes": (c_size, [c_void, c_i64]),
     "grief_gram": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_size, c_void]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "grief_set_slab_budget": (None, [c_size]),
     "grief_set_gemm_mode": (None, [c_int]),
     "grief_get_gemm_mode": (c_int, []),
+    "grief_rowcol_kr_matvec": (c_int, [c_int, c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
     "grief_gemm_nt": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
     "grief_solve_lml": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void, c_void, c_dbl, c_i64, c_void, c_void,
                                 c_void, c_void, c_void, c_void, _P(c_int), c_void]),

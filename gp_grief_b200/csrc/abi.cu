@@ -11,8 +11,8 @@ void solve_ctx_destroy(SolveCtx* c);
 int solve_lml(SolveCtx* ctx, int p, const double* A, int64_t lda, const double* r, const double* yty, const double* w,
               double noise, int64_t n_rows, double* L, double* b, double* Pinv, double* grad_w, double* G2,
               double* scalars_host, int* info_out, cudaStream_t stream, int* launches);
-int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64_t n_pad, double* T, cudaStream_t stream,
-                  int deriv_dim);
+int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64_t n_pad, double* T, cudaStream_t stream, int deriv_dim,
+                  const double* Kxu, int64_t ldk);
 int launch_phi_rows(const Plan* pl, const double* T, int64_t n, double* Phi, cudaStream_t stream);
 int phi_t_vec_blocks(int64_t n);
 int launch_phi_t_vec(const Plan* pl, const double* T, int64_t n, const double* v, double* out, double* ws, cudaStream_t stream);
@@ -36,10 +36,12 @@ int launch_rowdot(const Plan* pl, const double* Zt, int64_t ldz, const double* T
 int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm, cudaStream_t stream);
 int launch_permute_vec(const Plan* pl, const double* in, double scale, double* out, cudaStream_t stream);
 size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows);
-int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream);
+int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, int digits, cudaStream_t stream);
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
-                 int64_t ldz, cudaStream_t stream, int* launches);
+                 int64_t ldz, int digits, cudaStream_t stream, int* launches);
 int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
+int launch_rowcol_kr_matvec(int d, const int32_t* m, const double* const* R, const int32_t* const* ridx, const double* const* C, int64_t rows,
+                            int64_t cols, const double* x, double* y, cudaStream_t stream);
 
 static thread_local int g_launches = 0;
 
@@ -137,6 +139,8 @@ int grief_plan_info(const grief_plan* plan, int what) {
     case 3: return pl->p;
     case 4: return pl->p_pad;
     case 5: return pl->d;
+    case 6: return pl->sum_m;
+    case 7: return pl->n_host_dims;
     default: return -1;
   }
 }
@@ -146,7 +150,19 @@ int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx,
   GRIEF_REQUIRE(plan && (n == 0 || (T_dev && X_dev)), "grief_build_tables: null pointer");
   GRIEF_PLAN_DEVICE(plan->impl);
   GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d, "grief_build_tables: n=%lld ldx=%lld d=%d", (long long)n, (long long)ldx, plan->impl->d);
-  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, -1);
+  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, -1, nullptr, 0);
+  if (rc == GRIEF_OK && n > 0) g_launches += 1;
+  return rc;
+}
+
+int grief_build_tables_kxu(const grief_plan* plan, const double* X_dev, int64_t ldx, const double* Kxu_dev, int64_t ldk, int64_t n,
+                           int deriv_dim, double* T_dev, void* stream) {
+  GRIEF_REQUIRE(plan && (n == 0 || (T_dev && X_dev && Kxu_dev)), "grief_build_tables_kxu: null pointer");
+  GRIEF_PLAN_DEVICE(plan->impl);
+  GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d && ldk >= plan->impl->sum_m, "grief_build_tables_kxu: n=%lld ldx=%lld ldk=%lld (d=%d, sum of grid sizes=%d)",
+                (long long)n, (long long)ldx, (long long)ldk, plan->impl->d, plan->impl->sum_m);
+  GRIEF_REQUIRE(deriv_dim >= -1 && deriv_dim < plan->impl->d, "grief_build_tables_kxu: deriv_dim=%d outside [-1,%d)", deriv_dim, plan->impl->d);
+  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, deriv_dim, Kxu_dev, ldk);
   if (rc == GRIEF_OK && n > 0) g_launches += 1;
   return rc;
 }
@@ -156,7 +172,7 @@ int grief_build_tables_dx(const grief_plan* plan, const double* X_dev, int64_t l
   GRIEF_PLAN_DEVICE(plan->impl);
   GRIEF_REQUIRE(n >= 0 && ldx >= plan->impl->d, "grief_build_tables_dx: n=%lld ldx=%lld d=%d", (long long)n, (long long)ldx, plan->impl->d);
   GRIEF_REQUIRE(dim >= 0 && dim < plan->impl->d, "grief_build_tables_dx: dim=%d outside [0,%d)", dim, plan->impl->d);
-  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, dim);
+  int rc = launch_tables(plan->impl, X_dev, ldx, n, grief_table_rows(n), T_dev, (cudaStream_t)stream, dim, nullptr, 0);
   if (rc == GRIEF_OK && n > 0) g_launches += 1;
   return rc;
 }
@@ -177,8 +193,9 @@ static int set_opt(PlanOpts& o, int what, int64_t value) {
       return GRIEF_OK;
     case GRIEF_OPT_DIGITS_GRAM:
     case GRIEF_OPT_DIGITS_Z:
+    case GRIEF_OPT_DIGITS_VAR:
       GRIEF_REQUIRE(value >= kOzMinDigits && value <= kOzMaxDigits, "option digits: %lld outside [%d,%d]", (long long)value, kOzMinDigits, kOzMaxDigits);
-      (what == GRIEF_OPT_DIGITS_GRAM ? o.digits_gram : o.digits_z) = (int)value;
+      (what == GRIEF_OPT_DIGITS_GRAM ? o.digits_gram : (what == GRIEF_OPT_DIGITS_Z ? o.digits_z : o.digits_var)) = (int)value;
       return GRIEF_OK;
     case GRIEF_OPT_SLAB_BUDGET:
       GRIEF_REQUIRE(value >= 0, "option slab_budget: %lld", (long long)value);
@@ -192,6 +209,7 @@ static int64_t get_opt(const PlanOpts& o, int what) {
     case GRIEF_OPT_GEMM_MODE: return o.gemm_mode | (o.cluster << 1);
     case GRIEF_OPT_DIGITS_GRAM: return o.digits_gram;
     case GRIEF_OPT_DIGITS_Z: return o.digits_z;
+    case GRIEF_OPT_DIGITS_VAR: return o.digits_var;
     case GRIEF_OPT_SLAB_BUDGET: return (int64_t)o.slab_budget;
     default: return -1;
   }
@@ -260,6 +278,8 @@ int grief_solve_lml(grief_ctx* ctx, int p, const double* A_dev, int64_t lda, con
 int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat) {
   GRIEF_REQUIRE(plan && (n_active == 0 || (dims && kinds && dqs_concat)), "grief_grad_setup: null pointer");
   Plan* pl = plan->impl;
+  GRIEF_REQUIRE(pl->n_host_dims == 0 || n_active == 0, "grief_grad_setup: the analytic kernel-parameter gradient needs device kernels in every "
+                "dimension (%d dimension(s) are host-evaluated): use finite differences", pl->n_host_dims);
   if (pl->grad) { grad_desc_destroy(pl->grad); pl->grad = nullptr; }
   return grad_desc_create(&pl->grad, pl, n_active, dims, kinds, dqs_concat);
 }
@@ -301,14 +321,14 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   int rc = launch_permute_vec(pl, b_dev, 1.0, bvec, stream);                  // b in sorted column order
   if (rc != GRIEF_OK) return rc;
   rc = launch_permute_b(pl, Pinv_dev, ldp, Bperm, stream);
-  if (rc == GRIEF_OK) rc = launch_zgemm_prepare(pl, Bperm, slab, zscr, stream);
+  if (rc == GRIEF_OK) rc = launch_zgemm_prepare(pl, Bperm, slab, zscr, pl->opts.digits_z, stream);
   if (rc != GRIEF_OK) return rc;
   g_launches += 2;
   const int64_t n128 = grief_table_rows(n);
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Zt, slab, stream, &g_launches);
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Zt, slab, pl->opts.digits_z, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_contract(pl, Zt, slab, T_dev + (size_t)r0 * pl->stride, X_dev + (size_t)r0 * ldx, ldx, y_dev + r0, bvec, noise_var, rows_blk,
                          rows_valid, acc, sms, stream);
@@ -341,7 +361,7 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   double* Bperm = reinterpret_cast<double*>(reinterpret_cast<char*>(zscr) + align256(zgemm_scratch_bytes(pl, slab)));
   {
     int rc0 = launch_permute_b(pl, B_dev, ldb, Bperm, stream);
-    if (rc0 == GRIEF_OK) rc0 = launch_zgemm_prepare(pl, Bperm, slab, zscr, stream);
+    if (rc0 == GRIEF_OK) rc0 = launch_zgemm_prepare(pl, Bperm, slab, zscr, pl->opts.digits_var, stream);
     if (rc0 != GRIEF_OK) return rc0;
     g_launches += 1;
   }
@@ -349,13 +369,21 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, slab, stream, &g_launches);
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, slab, pl->opts.digits_var, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_rowdot(pl, Z, slab, T_dev + (size_t)r0 * pl->stride, rows_blk, rows_valid, q_dev + r0, stream);
     if (rc != GRIEF_OK) return rc;
     g_launches += 1;
   }
   return pl->opts.gemm_mode == 1 ? ozaki_check(pl->d_err, stream) : GRIEF_OK;
+}
+
+int grief_rowcol_kr_matvec(int d, const int32_t* m, const double* const* R_dev, const int32_t* const* ridx_dev, const double* const* C_dev,
+                           int64_t rows, int64_t cols, const double* x_dev, double* y_dev, void* stream) {
+  GRIEF_REQUIRE(m && C_dev && (R_dev || ridx_dev) && (rows == 0 || cols == 0 || (x_dev && y_dev)), "grief_rowcol_kr_matvec: null pointer");
+  int rc = launch_rowcol_kr_matvec(d, m, R_dev, ridx_dev, C_dev, rows, cols, x_dev, y_dev, (cudaStream_t)stream);
+  if (rc == GRIEF_OK && rows > 0) g_launches += 1;
+  return rc;
 }
 
 int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M, int N, int K,

@@ -7,7 +7,7 @@ mkdir -p "${OUT}" "${HERE}/build"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
        --expt-relaxed-constexpr -I"${HERE}/../../include")
-SRCS=(plan rows phi_stage solve dense ozaki topk grad abi)
+SRCS=(plan rows phi_stage solve dense ozaki topk grad krmatvec abi)
 OBJS=()
 pids=()
 for s in "${SRCS[@]}"; do

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
   const int wg = blockIdx.x * nw + warp, wtot = gridDim.x * nw;
   double* acc_out = P.acc + (size_t)wg * P.acc_len;
   const int stride = P.stride;
-  constexpr int NB = 8;
+  constexpr int NB = 16;
   for (int rg = wg; rg < P.n_rg; rg += wtot) {
     __syncwarp();
     const int64_t row = (int64_t)rg * 32 + lane;
@@ -200,15 +200,26 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
     double S[G > 1 ? G - 1 : 1];
 #pragma unroll
     for (int k = 0; k < (G > 1 ? G - 1 : 1); ++k) S[k] = 0.0;
+    // Zp^T is streamed from HBM: the loads of batch c0 + NB are issued before batch c0 is consumed (two batches of NB columns in
+    // flight per warp).  With four warps per SM (shared memory holds their tables and W) nothing else hides the DRAM latency.
     const double* zcol = P.Zt + row;
+    double znext[NB];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)e * P.ldz);
     for (int c0 = 0; c0 < P.p_pad; c0 += NB) {
       int lv[NB], sl[NB];
       double zt[NB];
 #pragma unroll
+      for (int e = 0; e < NB; ++e) zt[e] = znext[e];
+      if (c0 + NB < P.p_pad) {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)(c0 + NB + e) * P.ldz);
+      }
+#pragma unroll
       for (int e = 0; e < NB; ++e) {
         lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(P.level + c0 + e);
         sl[e] = __ldg(P.ss + (size_t)(c0 + e) * G + (G - 1));
-        zt[e] = fma(a_n, __ldg(P.bvec + c0 + e), -__ldcs(zcol + (size_t)(c0 + e) * P.ldz));
+        zt[e] = fma(a_n, __ldg(P.bvec + c0 + e), -zt[e]);
       }
 #pragma unroll
       for (int e = 0; e < NB; ++e) {
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(128) k_rowdot_t(const double* __restrict__ Zt,
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   double* sA = sm + (size_t)warp * stride * 32;
-  constexpr int NB = 8;
+  constexpr int NB = 16;
   for (int rg = blockIdx.x * nw + warp; rg < n_rg; rg += gridDim.x * nw) {
     __syncwarp();
     const double* src = T + (size_t)rg * 32 * stride;
@@ -359,14 +370,22 @@ __global__ void __launch_bounds__(128) k_rowdot_t(const double* __restrict__ Zt,
     const double* zcol = Zt + row;
     double pfx[G > 1 ? G - 1 : 1];
     double acc = 0.0;
+    double znext[NB];                                  // Z^T streams from HBM: the next batch is in flight while this one is consumed
+#pragma unroll
+    for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)e * ldz);
     for (int c0 = 0; c0 < p_pad; c0 += NB) {
       int lv[NB], sl[NB];
       double z[NB];
 #pragma unroll
+      for (int e = 0; e < NB; ++e) z[e] = znext[e];
+      if (c0 + NB < p_pad) {
+#pragma unroll
+        for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)(c0 + NB + e) * ldz);
+      }
+#pragma unroll
       for (int e = 0; e < NB; ++e) {
         lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(level + c0 + e);
         sl[e] = __ldg(ss + (size_t)(c0 + e) * G + (G - 1));
-        z[e] = __ldcs(zcol + (size_t)(c0 + e) * ldz);
       }
 #pragma unroll
       for (int e = 0; e < NB; ++e) {

@@ -543,17 +543,18 @@ static ZScratch carve_zscratch(const Plan* pl, int64_t slab_rows, void* scratch)
 }
 
 // Once per evaluation, after launch_permute_b: digit planes of B' for the INT8 path (no-op on the DMMA path).
-int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, cudaStream_t stream) {
+// `digits`: int8 digits per operand of this product (PlanOpts::digits_z for the gradient pass, digits_var for the predictive variance).
+int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, int digits, cudaStream_t stream) {
   if (pl->opts.gemm_mode != 1) return GRIEF_OK;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
-  return ozaki_slice(Bperm, pl->p_pad, pl->p_pad, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, pl->opts.digits_z, pl->d_err, stream);
+  return ozaki_slice(Bperm, pl->p_pad, pl->p_pad, pl->p_pad, z.eb, (pl->p_pad + 255) / 256 * 256, z.pb, digits, pl->d_err, stream);
 }
 
 // Zt (p_pad x ldz, TRANSPOSED: sorted column c of Z = Phi(slab) * B is row c of Zt, the slab's data rows are contiguous) -- the
 // layout its consumers (k_contract_rows, k_rowdot_t: lane = data row) read with full coalescing.  B symmetric, given as Bperm
 // (p_pad x p_pad, launch_permute_b).  scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Zt,
-                 int64_t ldz, cudaStream_t stream, int* launches) {
+                 int64_t ldz, int digits, cudaStream_t stream, int* launches) {
   GRIEF_REQUIRE(slab_rows % kBuildRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kBuildRows);
   GRIEF_REQUIRE(ldz >= slab_rows, "zgemm: ldz=%lld must be >= slab_rows=%lld", (long long)ldz, (long long)slab_rows);
   if (slab_rows == 0) return GRIEF_OK;
@@ -561,7 +562,7 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
   BuildArgs ba;
   if (i8) {      // row exponents + digit planes [sd][slab_rows][p_pad] straight from the tables
-    ba.digits = true; ba.sd = pl->opts.digits_z; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
+    ba.digits = true; ba.sd = digits; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
   } else {
     ba.out = z.Phi; ba.ld = pl->p_pad;
   }
@@ -572,7 +573,7 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   prof_begin(PROF_ZGEMM, stream);
   if (i8) {
     GRIEF_REQUIRE(pl->p_pad <= kOzakiKRange, "zgemm: p_pad=%d exceeds the INT8 path's K range of %d", pl->p_pad, kOzakiKRange);
-    OzOpts oo = oz_opts(pl, pl->opts.digits_z);
+    OzOpts oo = oz_opts(pl, digits);
     oo.store_t = 1;
     rc = ozaki_gemm(z.pa, slab_rows, z.ea, (int)slab_rows, z.pb, pl->p_pad, z.eb, pl->p_pad, pl->p_pad, Zt, ldz, false, false, 1, 0, oo, stream, launches);
   } else {

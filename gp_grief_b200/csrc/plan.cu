@@ -112,7 +112,7 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   int goff = 0, qoff = 0, foff = 0;
   for (int i = 0; i < d; ++i) {
     DimDesc& dd = pl->dims[i];
-    if (m[i] < 1 || m[i] > kMaxGrid || u[i] < 1 || u[i] > m[i] || kernel_id[i] < 0 || kernel_id[i] > KERN_MATERN52) {
+    if (m[i] < 1 || m[i] > kMaxGrid || u[i] < 1 || u[i] > m[i] || kernel_id[i] < 0 || kernel_id[i] > KERN_HOST) {
       delete pl;
       return fail(GRIEF_ERR_BAD_ARG, "plan_create: dimension %d has m=%d u=%d kernel=%d (need 1<=u<=m<=%d)", i, m[i],
                   u[i], kernel_id[i], kMaxGrid);
@@ -120,6 +120,7 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
     dd.m = m[i];
     dd.u = u[i];
     dd.kernel = kernel_id[i];
+    if (kernel_id[i] == KERN_HOST) pl->n_host_dims += 1;
     dd.grid_off = goff;
     dd.q_off = qoff;
     dd.f_off = foff;

@@ -16,7 +16,8 @@
 
 namespace grief {
 
-enum KernelId : int { KERN_RBF = 0, KERN_EXPONENTIAL = 1, KERN_MATERN32 = 2, KERN_MATERN52 = 3 };
+// KERN_HOST: the kernel of this dimension is evaluated by the caller (K_xu columns uploaded per call, grief_build_tables_kxu)
+enum KernelId : int { KERN_RBF = 0, KERN_EXPONENTIAL = 1, KERN_MATERN32 = 2, KERN_MATERN52 = 3, KERN_HOST = 4 };
 
 struct DimDesc {          // one input dimension, device-visible POD
   int m;                  // grid points
@@ -37,8 +38,9 @@ void grad_desc_destroy(GradDesc* gd);
 struct PlanOpts {
   int gemm_mode = 1;                       // 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki)
   int cluster = 0;                         // INT8 mode: CTA pairs (cta_group::2)
-  int digits_gram = 7;                     // INT8 digits per operand of A = Phi^T Phi
-  int digits_z = 7;                        // INT8 digits per operand of Z = Phi B
+  int digits_gram = 6;                     // INT8 digits per operand of A = Phi^T Phi (46-bit operands + the diagonal pair, ozaki.cu)
+  int digits_z = 4;                        // INT8 digits per operand of Zp = Phi P^-1 in the gradient pass (30-bit; the rank-one part is FP64)
+  int digits_var = 6;                      // INT8 digits per operand of Z = Phi B in grief_quadform_rows (predictive variance)
   size_t slab_budget = (size_t)4 << 30;    // bytes of Phi^T staged per pass-1 slab
 };
 PlanOpts& default_plan_opts();             // thread-local defaults for plans created on this thread
@@ -51,6 +53,7 @@ struct Plan {
   int stride = 0;                       // row stride in doubles (odd, >= width)
   int sum_m = 0, sum_u = 0;
   int max_group_dims = 0;
+  int n_host_dims = 0;                  // dimensions with KERN_HOST
   std::vector<DimDesc> dims;
   std::vector<int> group_begin;         // G+1 dimension boundaries
   std::vector<int> group_slot0;         // first table slot of each group

@@ -64,11 +64,15 @@ __device__ __forceinline__ double kern_eval_dx(int kernel, double x, double u, d
 // One block = RB data rows.  smem: sK[RB][sum_m], sF[RB][sum_u].
 // deriv_dim >= 0: the kernel of that input dimension is replaced by its derivative with respect to x, so that the
 // table products become d Phi / d x[:, deriv_dim] (models/gp_grief_model.py:127-134, kern/grief_kernel.py:113-126).
+// Kxu != nullptr: (n x sum_m) row-major, ldk doubles per row; the columns of every dimension whose kernel id is KERN_HOST hold
+// K_xu,i evaluated by the caller (any BaseKernel whose cov is host code: kern/gpy_kernel.py:45-58, kern/grid_kernel.py:148-179);
+// with deriv_dim = i they hold d K_xu,i / d x instead.
 __global__ void __launch_bounds__(256)
 k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, const double* __restrict__ qs,
          const uint8_t* __restrict__ slot_k, const int* __restrict__ slot_group, const int* __restrict__ group_begin,
          int d, int sum_m, int sum_u, int width, int stride, int max_group_dims, const double* __restrict__ X,
-         int64_t ldx, int64_t n, int64_t n_pad, double* __restrict__ T, int RB, int deriv_dim) {
+         int64_t ldx, int64_t n, int64_t n_pad, double* __restrict__ T, int RB, int deriv_dim,
+         const double* __restrict__ Kxu, int64_t ldk) {
   extern __shared__ double sm[];
   double* sK = sm;
   double* sF = sm + (size_t)RB * sum_m;
@@ -85,9 +89,12 @@ k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, cons
     const DimDesc dd = dims[i];
     const int64_t row = row0 + r;
     double v = 0.0;
-    if (row < n)
-      v = (i == deriv_dim) ? kern_eval_dx(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale)
-                           : kern_eval(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale);
+    if (row < n) {
+      if (dd.kernel == KERN_HOST) v = Kxu[row * ldk + c];
+      else
+        v = (i == deriv_dim) ? kern_eval_dx(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale)
+                             : kern_eval(dd.kernel, X[row * ldx + i], grid[c], dd.variance, dd.lengthscale);
+    }
     sK[(size_t)r * sum_m + c] = v;
   }
   __syncthreads();
@@ -127,7 +134,10 @@ k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, cons
 }
 
 int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64_t n_pad, double* T,
-                  cudaStream_t stream, int deriv_dim) {
+                  cudaStream_t stream, int deriv_dim, const double* Kxu, int64_t ldk) {
+  if (pl->n_host_dims > 0 && n > 0)
+    GRIEF_REQUIRE(Kxu != nullptr && ldk >= pl->sum_m, "tables: %d dimension(s) have host-evaluated kernels: pass K_xu (n x %d) through "
+                  "grief_build_tables_kxu", pl->n_host_dims, pl->sum_m);
   const size_t per_row = (size_t)(pl->sum_m + pl->sum_u) * sizeof(double);
   int RB = (int)std::min<size_t>(32, (160 * 1024) / per_row);
   if (RB < 1) return fail(GRIEF_ERR_UNSUPPORTED, "tables: %d grid points + %d factors per row exceed shared memory",
@@ -139,7 +149,7 @@ int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64
   prof_begin(PROF_TABLES, stream);
   k_tables<<<(unsigned)blocks, 256, smem, stream>>>(pl->d_dims, pl->d_grid, pl->d_qs, pl->d_slot_k, pl->d_slot_group,
                                                     pl->d_group_begin, pl->d, pl->sum_m, pl->sum_u, pl->width,
-                                                    pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB, deriv_dim);
+                                                    pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB, deriv_dim, Kxu, ldk);
   prof_end(PROF_TABLES, stream);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;

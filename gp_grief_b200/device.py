@@ -41,9 +41,18 @@ def topk_kron(eig_list, n_eigs):
 class DevicePlan(object):
     """One basis on the device (grief_plan). All list arguments are in INPUT-dimension order."""
 
-    def __init__(self, kernel_names, variances, lengthscales, xg, Q, eig, eig_loc, width_cap=0):
+    #: rows of K_xu evaluated on the host and uploaded per call of grief_build_tables_kxu (host-kernel dimensions only)
+    host_chunk_rows = 1 << 16
+
+    def __init__(self, kernel_names, variances, lengthscales, xg, Q, eig, eig_loc, width_cap=0, host_kernels=None):
+        """kernel_names[i]: 'RBF' | 'Exponential' | 'Matern32' | 'Matern52' (evaluated on the device) or 'host' -- then
+        host_kernels[i] is the BaseKernel whose `cov` (and `grad_x`, for d/dx tables) is called per row chunk."""
         _torch()
         d = len(xg)
+        self.host_kernels = {int(i): k for i, k in (host_kernels or {}).items()}
+        assert sorted(self.host_kernels) == [i for i, k in enumerate(kernel_names) if k == "host"], "host_kernels must match the 'host' entries"
+        self._xg = [np.asarray(g, dtype=np.float64).reshape(-1, 1) for g in xg]
+        self._grid_off = np.concatenate([[0], np.cumsum([g.size for g in self._xg])]).astype(int)
         eig_loc = np.asarray(eig_loc)
         p = eig_loc.shape[0]
         m = np.array([np.size(g) for g in xg], dtype=np.int32)
@@ -96,11 +105,48 @@ class DevicePlan(object):
         rows = nat.lib().grief_table_rows(n)
         T = torch.empty((rows, self.stride), dtype=torch.float64, device=X_dev.device)
         ldx = X_dev.stride(0) if n > 1 else self.d
+        if self.host_kernels:
+            return self._build_tables_host_kxu(X_dev, ldx, n, T, deriv_dim)
         if deriv_dim is None:
             nat.check(nat.lib().grief_build_tables(self._h, nat.dev_ptr(X_dev), ldx, n, nat.dev_ptr(T), nat.stream_ptr()))
         else:
             nat.check(nat.lib().grief_build_tables_dx(self._h, nat.dev_ptr(X_dev), ldx, n, int(deriv_dim), nat.dev_ptr(T),
                                                       nat.stream_ptr()))
+        return T
+
+    def _build_tables_host_kxu(self, X_dev, ldx, n, T, deriv_dim):
+        """Tables when some dimensions have host-only kernels (GridKernel.cov_kr, kern/grid_kernel.py:148-179, for those dimensions):
+        per chunk of rows, kern_i.cov(x[:, i], U_i) is evaluated on the host into a pinned (rows, sum m) buffer, uploaded, and
+        grief_build_tables_kxu projects / multiplies on the device.  Two pinned buffers alternate so that the host evaluation of
+        chunk c + 1 overlaps the upload and the table kernel of chunk c."""
+        torch = _torch()
+        sum_m = int(self._grid_off[-1])
+        chunk = int(self.host_chunk_rows) // 128 * 128
+        assert chunk >= 128
+        if n == 0:
+            return T
+        pins = [torch.empty((min(chunk, n), sum_m), dtype=torch.float64).pin_memory() for _ in range(2)]
+        devs = [torch.empty((min(chunk, n), sum_m), dtype=torch.float64, device=X_dev.device) for _ in range(2)]
+        done = [None, None]
+        stream = torch.cuda.current_stream()
+        dd = -1 if deriv_dim is None else int(deriv_dim)
+        for c, r0 in enumerate(range(0, n, chunk)):
+            rows = min(chunk, n - r0)
+            b = c & 1
+            if done[b] is not None:
+                done[b].synchronize()                        # the copy out of this pinned buffer has finished
+            xh = X_dev[r0:r0 + rows].cpu().numpy()
+            kb = pins[b].numpy()
+            for i, kern in self.host_kernels.items():
+                xi = np.ascontiguousarray(xh[:, (i,)])
+                Ki = kern.grad_x(xi, self._xg[i]) if i == dd else kern.cov(x=xi, z=self._xg[i])
+                kb[:rows, self._grid_off[i]:self._grid_off[i + 1]] = Ki
+            devs[b][:rows].copy_(pins[b][:rows], non_blocking=True)
+            done[b] = torch.cuda.Event()
+            done[b].record(stream)
+            Xc = X_dev[r0:r0 + rows]
+            nat.check(nat.lib().grief_build_tables_kxu(self._h, nat.dev_ptr(Xc), ldx, nat.dev_ptr(devs[b]), sum_m, rows, dd,
+                                                       nat.dev_ptr(T[r0:]), nat.stream_ptr()))
         return T
 
     def phi_rows(self, T, n):
@@ -110,7 +156,7 @@ class DevicePlan(object):
         return Phi
 
     def set_option(self, what, value):
-        """Per-plan option (nat.OPT_GEMM_MODE / OPT_DIGITS_GRAM / OPT_DIGITS_Z / OPT_SLAB_BUDGET, include/grief_b200.h)."""
+        """Per-plan option (nat.OPT_GEMM_MODE / OPT_DIGITS_GRAM / OPT_DIGITS_Z / OPT_DIGITS_VAR / OPT_SLAB_BUDGET, include/grief_b200.h)."""
         nat.check(nat.lib().grief_plan_set_option(self._h, int(what), int(value)))
 
     def get_option(self, what):
@@ -219,6 +265,45 @@ def kron_matvec(factors, x):
         Yc = y.view(-1, cols_i)
         out = gemm_nt(Yc, Kd)                      # (rest, rows_i) = Yc @ K_i^T
         y = out.t().contiguous().view(-1)
+    return y.cpu().numpy().reshape((-1, 1))
+
+
+def rowcol_kr_matvec(R, C, x):
+    """y = (R K C) x for a row- and column-partitioned Khatri-Rao product on the device (grief_rowcol_kr_matvec).
+
+    R: per factor a dense (rows, m_t) array, or a 1-D integer array of length rows (selection matrix: row i picks row R[t][i] of
+    C[t]); C: per factor a dense (m_t, cols) array (already multiplied by the Kronecker factor, if any); x: (cols,) or (cols, 1).
+    Returns a NumPy column vector (rows, 1)."""
+    torch = _torch()
+    d = len(C)
+    assert len(R) == d and d >= 1
+    keep = []                                              # device tensors must outlive the launch
+    m = np.zeros(d, dtype=np.int32)
+    Rp, Ip, Cp = (ctypes.c_void_p * d)(), (ctypes.c_void_p * d)(), (ctypes.c_void_p * d)()
+    rows = cols = None
+    for t in range(d):
+        Ct = torch.as_tensor(np.ascontiguousarray(C[t], dtype=np.float64)).cuda()
+        assert Ct.dim() == 2
+        m[t] = Ct.shape[0]
+        cols = Ct.shape[1] if cols is None else cols
+        assert Ct.shape[1] == cols, "all C factors must have the same number of columns"
+        Rt = np.asarray(R[t])
+        if Rt.ndim == 1:
+            assert np.issubdtype(Rt.dtype, np.integer) and (Rt.size == 0 or (Rt.min() >= 0 and Rt.max() < m[t]))
+            Rd = torch.as_tensor(np.ascontiguousarray(Rt, dtype=np.int32)).cuda()
+            Ip[t], Rp[t] = nat.dev_ptr(Rd), None
+        else:
+            assert Rt.ndim == 2 and Rt.shape[1] == m[t], "R[%d] must be (rows, %d)" % (t, m[t])
+            Rd = torch.as_tensor(np.ascontiguousarray(Rt, dtype=np.float64)).cuda()
+            Rp[t], Ip[t] = nat.dev_ptr(Rd), None
+        rows = Rt.shape[0] if rows is None else rows
+        assert Rt.shape[0] == rows, "all R factors must have the same number of rows"
+        Cp[t] = nat.dev_ptr(Ct)
+        keep += [Ct, Rd]
+    xd = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))).cuda()
+    assert xd.numel() == cols
+    y = torch.zeros((rows,), dtype=torch.float64, device="cuda")
+    nat.check(nat.lib().grief_rowcol_kr_matvec(d, nat.host_ptr(m), Rp, Ip, Cp, rows, cols, nat.dev_ptr(xd), nat.dev_ptr(y), nat.stream_ptr()))
     return y.cpu().numpy().reshape((-1, 1))
 
 

@@ -129,16 +129,26 @@ class GriefKernel(GridKernel):
 
     # ------------------------------------------------------------------ device side
     def _device_kernel_spec(self):
-        names, var, ls = [], [], []
-        for k in self.kern_list:
-            if getattr(k, "device_id", None) is None or k.n_dims != 1 or len(k._children) > 0:
-                raise NotImplementedError(
-                    "the B200 path evaluates 1-d RBF / Exponential / Matern32 / Matern52 kernels without children; "
-                    "got %s" % k.name)
-            names.append(k.device_id)
-            var.append(float(k.variance))
-            ls.append(float(k.lengthscale))
-        return names, var, ls
+        """(names, variances, lengthscales, host_kernels): 1-d RBF / Exponential / Matern32 / Matern52 kernels without children are
+        evaluated inside libgrief_b200; every other BaseKernel (GPyKernel, kernels with children, user subclasses) keeps its host
+        `cov` -- its K_xu columns are evaluated per row chunk on the host and uploaded (DevicePlan._build_tables_host_kxu), the rest
+        of the path is the same device code (reference: kern/grid_kernel.py:171 calls kern.cov for whatever the kernel is)."""
+        names, var, ls, host = [], [], [], {}
+        for i, k in enumerate(self.kern_list):
+            if k.n_dims != 1:
+                raise NotImplementedError("currently only 1-dimensional grids allowed (kernel %s has n_dims=%d)" % (k.name, k.n_dims))
+            if getattr(k, "device_id", None) is None or len(k._children) > 0:
+                names.append("host"); var.append(1.0); ls.append(1.0)
+                host[i] = k
+            else:
+                names.append(k.device_id)
+                var.append(float(k.variance))
+                ls.append(float(k.lengthscale))
+        return names, var, ls, host
+
+    def has_host_kernels(self):
+        """True when a dimension's kernel is evaluated on the host (no analytic kernel-parameter gradient then)."""
+        return any(getattr(k, "device_id", None) is None or len(k._children) > 0 for k in self.kern_list)
 
     def device_plan(self):
         """The DevicePlan (basis description resident on the GPU) for the current hyper-parameters."""
@@ -146,12 +156,12 @@ class GriefKernel(GridKernel):
         if self._plan is None:
             from ..device import DevicePlan
             d = self.grid_dim
-            names, var, ls = self._device_kernel_spec()
+            names, var, ls, host = self._device_kernel_spec()
             xg = [np.asarray(self.grid.xg[i], dtype=float).reshape(-1) for i in range(d)]
             Q = [np.asarray(self._Quu.K[d - 1 - i]) for i in range(d)]          # factor k <-> input dimension d-1-k
             eig = [np.asarray(self._eigs.K[d - 1 - i]) for i in range(d)]
             loc = np.asarray(self._eig_pos)[:, ::-1]
-            self._plan = DevicePlan(names, var, ls, xg, Q, eig, loc)
+            self._plan = DevicePlan(names, var, ls, xg, Q, eig, loc, host_kernels=host)
         return self._plan
 
     def base_parameter_map(self):

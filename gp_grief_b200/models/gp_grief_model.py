@@ -78,7 +78,7 @@ class GPGriefModel(BaseModel):
         if self.kern.opt_kernel_params:
             self.dependent_attributes = np.unique(np.concatenate(
                 (self.dependent_attributes, ['_A', '_Phi', '_X_last_pred', '_Phi_last_pred'])))
-            analytic_ok = not self.kern.has_aliased_kernels()
+            analytic_ok = not self.kern.has_aliased_kernels() and not self.kern.has_host_kernels()
             self.grad_method = 'adjoint' if analytic_ok else 'finite_difference'
         else:
             self.grad_method = 'adjoint'
@@ -155,8 +155,9 @@ class GPGriefModel(BaseModel):
         self.parameters
         self._cov_setup()
 
-    #: (digits of A = Phi^T Phi, digits of Z = Phi B) for the INT8 tensor-core arithmetic, or None for the library defaults
-    #: (include/grief_b200.h, GRIEF_OPT_DIGITS_*).  8 D - 2 bits per operand below its row maximum.
+    #: (digits of A = Phi^T Phi, digits of Zp = Phi P^-1 in the gradient pass[, digits of the predictive-variance product]) for the
+    #: INT8 tensor-core arithmetic, or None for the library defaults 6 / 4 / 6 (include/grief_b200.h, GRIEF_OPT_DIGITS_*).
+    #: 8 D - 2 bits per operand below its row maximum.
     gemm_digits = None
 
     def _plan(self):
@@ -166,6 +167,8 @@ class GPGriefModel(BaseModel):
         if self.gemm_digits is not None:
             plan.set_option(nat.OPT_DIGITS_GRAM, self.gemm_digits[0])
             plan.set_option(nat.OPT_DIGITS_Z, self.gemm_digits[1])
+            if len(self.gemm_digits) > 2:
+                plan.set_option(nat.OPT_DIGITS_VAR, self.gemm_digits[2])
         return plan
 
     def _stats(self):
@@ -244,9 +247,9 @@ class GPGriefModel(BaseModel):
         if self.noise_var_constraint != 'fixed':
             gradient[0] = out['grad_noise']
         if need_theta:
-            if self.kern.has_aliased_kernels():
-                raise NotImplementedError("analytic kernel-parameter gradient needs distinct kernel objects per dimension; "
-                                          "use grad_method='finite_difference'")
+            if self.kern.has_aliased_kernels() or self.kern.has_host_kernels():
+                raise NotImplementedError("analytic kernel-parameter gradient needs distinct in-house kernel objects (RBF, Exponential, "
+                                          "Matern32, Matern52, no children) per dimension; use grad_method='finite_difference'")
             pmap = self.kern.base_parameter_map()
             active = [pmap[i] for i in theta_free]
             from ..kern.grief_kernel import DegenerateEigenpairError

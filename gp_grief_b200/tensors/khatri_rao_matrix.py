@@ -4,7 +4,9 @@
 `RowColKhatriRaoMatrix` is the R*K*C product with memory-bounded row chunking.  Both are host NumPy
 containers: the GRIEF hot path never goes through them (the device builds Phi tiles directly from the
 per-dimension factors, csrc/phi_stage.cu) -- exactly as in the reference, whose GriefKernel imports
-RowColKhatriRaoMatrix but calls expand_SKC instead.
+RowColKhatriRaoMatrix but calls expand_SKC instead.  `RowColKhatriRaoMatrix(..., device=True)` runs its mat-vec
+(and that of its transpose) on the GPU through grief_rowcol_kr_matvec (csrc/krmatvec.cu), without forming any
+block of rows; `device=True` without a CUDA device raises.
 """
 import numpy as np
 import scipy.sparse as sparse
@@ -34,7 +36,8 @@ class KhatriRaoMatrix(BlockMatrix):
 class RowColKhatriRaoMatrix(object):
     """R K C with R a row-partitioned and C a column-partitioned Khatri-Rao matrix, K a Kronecker matrix."""
 
-    def __init__(self, R, K, C, nGb=1.):
+    def __init__(self, R, K, C, nGb=1., device=False):
+        self.device = bool(device)
         self.shape = (R[0].shape[0], C[0].shape[1])
         self.d = len(R)
         self.R = R
@@ -59,8 +62,27 @@ class RowColKhatriRaoMatrix(object):
     @property
     def T(self):
         if isinstance(self.R[0], (SelectionMatrix, SelectionMatrixSparse)):
-            return RowColKhatriRaoMatrixTransposed(R=self.R, K=None, C=self.C, nGb=self.nGb)
-        return RowColKhatriRaoMatrix(R=[Ci.T for Ci in self.C], K=None, C=[Ri.T for Ri in self.R], nGb=self.nGb)
+            return RowColKhatriRaoMatrixTransposed(R=self.R, K=None, C=self.C, nGb=self.nGb, device=self.device)
+        return RowColKhatriRaoMatrix(R=[Ci.T for Ci in self.C], K=None, C=[Ri.T for Ri in self.R], nGb=self.nGb, device=self.device)
+
+    @staticmethod
+    def _dense(M):
+        """Dense array of a factor (sparse matrices and boolean selection matrices are expanded)."""
+        if isinstance(M, SelectionMatrix):
+            M = M.sel
+        return np.asarray(M.toarray() if sparse.issparse(M) else M, dtype=float)
+
+    def _device_factors(self):
+        """(R, C) for device.rowcol_kr_matvec: selection matrices become index vectors, everything else dense."""
+        R = []
+        for Ri in self.R:
+            if isinstance(Ri, SelectionMatrixSparse):
+                R.append(np.asarray(Ri.indicies, dtype=np.int64))
+            elif isinstance(Ri, SelectionMatrix):
+                R.append(np.asarray(Ri.sel.indices, dtype=np.int64))        # CSR with one entry per row
+            else:
+                R.append(self._dense(Ri))
+        return R, [self._dense(Ci) for Ci in self.C]
 
     def _rows_1d(self, i_d, i_rows):
         if sparse.issparse(self.C[i_d]):
@@ -86,8 +108,12 @@ class RowColKhatriRaoMatrix(object):
         return self.get_rows(i_rows=slice(None), logged=logged)
 
     def __mul__(self, x):
-        """Memory-bounded mat-vec: at most n_rows_at_once rows of the product exist at a time."""
+        """Memory-bounded mat-vec: at most n_rows_at_once rows of the product exist at a time (host), or none at all (device)."""
         assert x.shape == (self.shape[1], 1)
+        if self.device:
+            from ..device import rowcol_kr_matvec
+            R, C = self._device_factors()
+            return rowcol_kr_matvec(R, C, x)
         y = np.zeros((self.shape[0], 1))
         for start in range(0, self.shape[0], int(self.n_rows_at_once)):
             i_rows = np.arange(start, min(start + self.n_rows_at_once, self.shape[0]))
@@ -103,6 +129,11 @@ class RowColKhatriRaoMatrixTransposed(RowColKhatriRaoMatrix):
         self.shape = self.shape[::-1]
         self._set_chunk()
 
+    def _device_factors(self):
+        """The transpose as a plain R' C' product: R'_t = C_t^T (dense), C'_t = R_t^T (dense; a selection matrix is expanded)."""
+        return [self._dense(Ci).T for Ci in self.C], [self._dense(Ri.mul(np.identity(Ri.shape[1])) if isinstance(Ri, SelectionMatrixSparse)
+                                                                  else Ri).T for Ri in self.R]
+
     def get_rows(self, i_rows):
         cols = None
         for i_d in range(self.d):
@@ -113,4 +144,4 @@ class RowColKhatriRaoMatrixTransposed(RowColKhatriRaoMatrix):
 
     @property
     def T(self):
-        return RowColKhatriRaoMatrix(R=self.R, K=None, C=self.C, nGb=self.nGb)
+        return RowColKhatriRaoMatrix(R=self.R, K=None, C=self.C, nGb=self.nGb, device=self.device)

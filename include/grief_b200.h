@@ -94,6 +94,10 @@ int grief_topk_kron(int d, const int32_t* m_host, const double* raw0_host, const
  * Describe one basis.  Replaces the state GriefKernel._setup_inducing_cov leaves behind
  * (kern/grief_kernel.py:168-190: _Quu, _log_lam, _Sp) in the form the row kernels consume.
  *   m[d], kernel_id[d], variance[d], lengthscale[d], grid_concat[sum m]   per input dimension
+ *                        kernel_id: GRIEF_KERNEL_RBF / _EXPONENTIAL / _MATERN32 / _MATERN52 are evaluated on the device;
+ *                        GRIEF_KERNEL_HOST marks a dimension whose kernel only the caller can evaluate (a GPy kernel, a kernel
+ *                        with children, any Python cov: kern/gpy_kernel.py:45-58) -- its K_xu columns come in through
+ *                        grief_build_tables_kxu, variance / lengthscale are ignored
  *   u[d]                 number of distinct selected eigen-indices of the dimension
  *                        (SelectionMatrixSparse.unique, tensors/selection_matrix.py:78-79)
  *   qs_concat            per dimension an (m_i, u_i) row-major matrix: column k is the Schur vector of
@@ -108,7 +112,13 @@ int grief_plan_create(grief_plan** plan, int d, const int32_t* m, const int32_t*
                       const double* variance, const double* lengthscale, const double* grid_concat,
                       const int32_t* u, const double* qs_concat, int p, const int32_t* uinv, int width_cap);
 void grief_plan_destroy(grief_plan* plan);
-/* layout queries: what = 0 groups G, 1 table width, 2 row stride (doubles), 3 p, 4 p_pad, 5 d */
+#define GRIEF_KERNEL_RBF 0
+#define GRIEF_KERNEL_EXPONENTIAL 1
+#define GRIEF_KERNEL_MATERN32 2
+#define GRIEF_KERNEL_MATERN52 3
+#define GRIEF_KERNEL_HOST 4
+/* layout queries: what = 0 groups G, 1 table width, 2 row stride (doubles), 3 p, 4 p_pad, 5 d, 6 sum of the grid sizes m_i
+ * (columns of K_xu in grief_build_tables_kxu; dimension i starts at m_0 + ... + m_{i-1}), 7 number of host-evaluated dimensions */
 int grief_plan_info(const grief_plan* plan, int what);
 /* rows the table buffer must hold for n data rows (n rounded up to the MMA chunk) */
 int64_t grief_table_rows(int64_t n);
@@ -130,6 +140,18 @@ int grief_build_tables(const grief_plan* plan, const double* X_dev, int64_t ldx,
  */
 int grief_build_tables_dx(const grief_plan* plan, const double* X_dev, int64_t ldx, int64_t n, int dim, double* T_dev, void* stream);
 
+/*
+ * Tables for a plan with host-evaluated dimensions (GRIEF_KERNEL_HOST): GridKernel.cov_kr (kern/grid_kernel.py:148-179) calls
+ * kern.cov(x[:, i], U_i) per dimension -- for kernels that exist only as host code (GPyKernel, kern/gpy_kernel.py:45-58) the caller
+ * evaluates those (n, m_i) blocks, uploads them, and the device does the rest (projection on the scaled eigenvectors, group
+ * products).  Dimensions with device kernels are still evaluated on the device from X_dev.
+ *   Kxu_dev, ldk   (n, ldk) row-major, ldk >= sum m_i; columns [off_i, off_i + m_i) = K_xu,i of a host dimension i (others unused)
+ *   deriv_dim      -1, or the dimension whose kernel is replaced by its x-derivative (a host dimension then passes d K_xu,i / d x)
+ * Row chunks may be built one call at a time (T_dev + r0 * stride, r0 a multiple of 128).
+ */
+int grief_build_tables_kxu(const grief_plan* plan, const double* X_dev, int64_t ldx, const double* Kxu_dev, int64_t ldk, int64_t n,
+                           int deriv_dim, double* T_dev, void* stream);
+
 /* Phi (n, p) row-major from the tables: GriefKernel.cov(x)[0] (kern/grief_kernel.py:68-111). Small n only. */
 int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, double* Phi_dev, void* stream);
 
@@ -145,9 +167,14 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
  *          (D = 7: the accuracy class of DGEMM)
  *       3  as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2; correct and
  *          tested, not faster on a power-capped B200
- *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (3..7).  A feeds a Cholesky factorisation: keep it at DGEMM class unless the caller's
- *                          tolerance allows less
- *   GRIEF_OPT_DIGITS_Z     D of Z = Phi B (pass 2: B = P^-1, and the predictive variance), 3..7
+ *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (3..7, default 6: 46-bit operands, 22 digit products).  A feeds a Cholesky
+ *                          factorisation; measured against the FP64 mode at n = 10^6..10^7, p = 4096: LML identical to 1e-15 with
+ *                          D = 6 and D = 7, 1.5e-13 with D = 5
+ *   GRIEF_OPT_DIGITS_Z     D of Zp = Phi P^-1 in grief_grad_theta (3..7, default 4: 30-bit operands, 10 digit products).  The
+ *                          gradient sums n p products of Zp, so its truncation errors average out: 1.5e-13 of the largest gradient
+ *                          component with D = 4, 2e-15 with D >= 5, 6e-11 with D = 3 (same measurement)
+ *   GRIEF_OPT_DIGITS_VAR   D of Z = Phi B in grief_quadform_rows (3..7, default 6): a predictive variance sums only p products
+ *   GPGriefModel audits these choices a posteriori against the FP64 mode on a row sample (models/gp_grief_model.py, arithmetic_audit).
  *   GRIEF_OPT_SLAB_BUDGET  bytes of HBM for the Phi^T slab that pass 1 stages per GEMM launch (default 4 GiB; 0 restores it).  Smaller
  *                          budgets mean more, shorter launches; results are identical up to the order of the fixed-order accumulation
  * grief_set_slab_budget / grief_set_gemm_mode / grief_get_gemm_mode are the round-1 spellings of the default setters.
@@ -156,6 +183,7 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
 #define GRIEF_OPT_DIGITS_GRAM 1
 #define GRIEF_OPT_DIGITS_Z 2
 #define GRIEF_OPT_SLAB_BUDGET 3
+#define GRIEF_OPT_DIGITS_VAR 4
 int grief_set_default_option(int what, int64_t value);
 int64_t grief_get_default_option(int what);
 int grief_plan_set_option(grief_plan* plan, int what, int64_t value);
@@ -239,6 +267,19 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
 size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n);
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb,
                         double* q_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Row- and column-partitioned Khatri-Rao mat-vec, RowColKhatriRaoMatrix.__mul__ (tensors/khatri_rao_matrix.py:156-167, with get_rows
+ * :110-138 fused in): y[i] = sum_j x[j] * prod_t (R_t C_t)[i, j].  No row block of the product is materialised.
+ *   d, m[d]        number of factors (<= 32) and their inner sizes
+ *   R_dev[d]       host array of DEVICE pointers: R_t (rows, m_t) row-major, or NULL for a factor given by ridx_dev[t]
+ *   ridx_dev[d]    host array of DEVICE pointers (or NULL): int32 (rows,), R_t is the selection matrix whose row i picks row
+ *                  ridx_t[i] of C_t (SelectionMatrixSparse, tensors/selection_matrix.py:55-107); exactly one of R_dev[t] / ridx_dev[t]
+ *   C_dev[d]       C_t (m_t, cols) row-major (K_t C_t when the product has a Kronecker middle factor, khatri_rao_matrix.py:77-82)
+ *   x_dev (cols), y_dev (rows)
+ */
+int grief_rowcol_kr_matvec(int d, const int32_t* m, const double* const* R_dev, const int32_t* const* ridx_dev,
+                           const double* const* C_dev, int64_t rows, int64_t cols, const double* x_dev, double* y_dev, void* stream);
 
 /*
  * C (M x N, ldc) = beta * C + alpha * A (M x K, lda) * B (N x K, ldb)^T, all row-major on the device; the TMA-fed FP64 DMMA

@@ -265,8 +265,74 @@ def automobile_case():
     print("c1_automobile n=%d d=%d lml=%.15e dsig=%.15e ties=%d" % (x[i_train].shape[0], d, out["lml"], g[0], out["n_ties"]))
 
 
+def composite_kernel_case(name, x, y, xg, op, parent, child, n_eigs, noise_var, xnew, type2=False):
+    """Kernels WITH CHILDREN (kern/basekernel.py:131-190: `k1 * k2`, `k1 + k2`): no closed formula inside libgrief_b200, so the
+    new implementation evaluates their K_xu on the host and uploads it (grief_build_tables_kxu).  parent / child:
+    (kernel class name, variance, [lengthscale per dimension])."""
+    d = x.shape[1]
+    kern_list = []
+    for i in range(d):
+        k1 = KERNELS[parent[0]](1, variance=parent[1], lengthscale=parent[2][i])
+        k2 = KERNELS[child[0]](1, variance=child[1], lengthscale=child[2][i])
+        kern_list.append(k1 * k2 if op == "mul" else k1 + k2)
+    xg_obj = np.empty(len(xg), dtype=object)
+    for i, g in enumerate(xg):
+        xg_obj[i] = np.asarray(g, float).reshape(-1, 1)
+    grid = InducingGrid(xg=xg_obj)
+    if type2:
+        kern = GriefKernel(kern_list, grid, n_eigs=n_eigs, reweight_eig_funs=False, opt_kernel_params=True)
+    else:
+        kern = GriefKernel(kern_list, grid, n_eigs=n_eigs)
+        for k in kern.kern_list:      # GriefKernel fixes the parents' parameters only (grief_kernel.py:44-52): fix the children's too
+            for _, ch in k._children:
+                for key in ch.constraint_map:
+                    ch.constraint_map[key] = np.tile('fixed', np.shape(ch.constraint_map[key]))
+    m = GPGriefModel(x, y, kern, noise_var=noise_var)
+    params = m.parameters
+    out = {"x": x, "y": y, "op": np.array(op), "parent_name": np.array(parent[0]), "parent_variance": np.float64(parent[1]),
+           "parent_lengthscales": np.asarray(parent[2], float), "child_name": np.array(child[0]),
+           "child_variance": np.float64(child[1]), "child_lengthscales": np.asarray(child[2], float),
+           "n_eigs": np.int64(kern.n_eigs), "noise_var": np.float64(noise_var), "type2": np.bool_(type2),
+           "n_grid_dims": np.int64(d), "parameters": params,
+           "constraints": np.array([c.decode() if isinstance(c, bytes) else str(c) for c in m.constraints])}
+    for i in range(d):
+        out["xg_%d" % i] = np.asarray(grid.xg[i], float).reshape(-1)
+    out["lml"] = np.float64(np.asarray(m._compute_log_likelihood(params)).squeeze())
+    out.update(kernel_state(kern))
+    out["A"] = m._A
+    out["log_det"] = np.float64(m._cov_log_det())
+    if type2:
+        ll, g = m._finite_diff_gradient(params.copy())
+        out["grad_fd"] = g
+    else:
+        m.grad_method = "adjoint"
+        ll, g = m._adjoint_gradient(params.copy())
+        out["grad_adjoint"] = g
+    m.parameters = params
+    yhat, yvar = m.predict(xnew)
+    out["xnew"] = xnew
+    out["yhat"] = yhat.squeeze()
+    out["yvar_diag"] = np.diag(yvar).copy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("%-28s n=%d d=%d p=%d lml=%.15e" % (name, x.shape[0], d, kern.n_eigs, out["lml"]))
+
+
+def composite_cases():
+    x, y = synthetic_xy(800, 3, chunk=1 << 10)
+    xnew = synthetic_xy(12, 3, chunk_id0=10 ** 6)[0]
+    composite_kernel_case("host_t1_sum_n800_d3_m9_p36", x, y, linspace_grid(3, 9), "add", ("RBF", 1.0, [0.35, 0.5, 0.65]),
+                          ("Matern32", 0.4, [0.8, 0.6, 0.9]), 36, 0.15, xnew)
+    composite_kernel_case("host_t1_prod_n800_d3_m9_p36", x, y, linspace_grid(3, 9), "mul", ("RBF", 1.1, [0.45, 0.5, 0.7]),
+                          ("Exponential", 1.0, [1.5, 2.0, 1.2]), 36, 0.15, xnew)
+    composite_kernel_case("host_t2_sum_n500_d2_m8_p24", x[:500, :2], y[:500], linspace_grid(2, 8), "add", ("RBF", 1.0, [0.35, 0.5]),
+                          ("Matern52", 0.5, [0.7, 0.9]), 24, 0.2, xnew[:, :2], type2=True)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--composite-only" in sys.argv:
+        composite_cases()
+        return
     kron_eigs_case()
     web_case()
 
@@ -307,6 +373,7 @@ def main():
                    [0.4, 0.5, 0.6], 48, 0.1, type2=True, keep_phi=False)
 
     automobile_case()
+    composite_cases()
 
     # top-p selection at the benchmark configurations
     topk_case("topk_c2_d6_m10_p1024", 6, 10, 1024)

@@ -34,13 +34,16 @@ def _dist2(x, z):
 
 
 def kernel_cov(name, x, z, variance, lengthscale):
-    """k(x, z) for the in-house kernels.
+    """k(x, z) for the in-house kernels (name: str), or for any kernel given as a callable cov(x, z) (GPyKernel,
+    kernels with children: kern/gpy_kernel.py:45-58, kern/basekernel.py:131-146).
 
     RBF          kern/stationary.py:121-127 (incl. the lengthscale < 1e-6 guard at :121-122)
     Exponential  kern/stationary.py:172-173
     Matern32     kern/stationary.py:213-214
     Matern52     kern/stationary.py:254-256
     """
+    if callable(name):                       # any other kernel: kern.cov(x, z) as kern/grid_kernel.py:99,171 would call it
+        return np.asarray(name(np.asarray(x, float).reshape(-1, 1), np.asarray(z, float).reshape(-1, 1)), dtype=float)
     d2 = _dist2(x, z)
     if name == "RBF":
         if lengthscale < 1e-6:

@@ -267,3 +267,65 @@ def test_d_yhat_d_x_on_device(kname):
         Xm[:, dim] -= h
         fd = (mdl.predict(Xp, compute_var=None) - mdl.predict(Xm, compute_var=None)) / (2 * h)
         np.testing.assert_allclose(g_dev, fd, rtol=0, atol=2e-5 * max(1.0, np.abs(fd).max()))
+
+
+@pytest.mark.gpu
+def test_rowcol_khatri_rao_matvec_on_device_reference_test():
+    """tests/test_tensors/test_RowColKhatriRaoMatrix.py:9-48 of the reference with device=True: A x, A^T x and the
+    RowColKhatriRaoMatrixTransposed form through grief_rowcol_kr_matvec."""
+    import gp_grief_b200 as gp
+    from gp_grief_b200.tensors import KronMatrix, KhatriRaoMatrix, RowColKhatriRaoMatrix, RowColKhatriRaoMatrixTransposed
+    np.random.seed(0)
+    N, p, d = 5, 6, 3
+    grid_shape = np.random.randint(low=2, high=15, size=d)
+    R = np.empty(d, dtype=object)
+    R[:] = [np.random.rand(p, m) - 0.5 for m in grid_shape]
+    K = np.empty(d, dtype=object)
+    K[:] = [np.random.rand(m, m) - 0.5 for m in grid_shape]
+    C = np.empty(d, dtype=object)
+    C[:] = [np.random.rand(m, N) - 0.5 for m in grid_shape]
+    for i in range(d):
+        R[i][0, :] = 0.
+    vec = np.random.rand(N, 1) - 0.5
+    vecT = np.random.rand(p, 1) - 0.5
+    A = RowColKhatriRaoMatrix(R=R, K=K, C=C, device=True)
+    AT = RowColKhatriRaoMatrixTransposed(R=R, K=K, C=C, device=True)
+    Rk, Ck, Kk = KhatriRaoMatrix(R, partition=0), KhatriRaoMatrix(C, partition=1), KronMatrix(K)
+    assert_array_almost_equal(A * vec, Rk * (Kk * (Ck * vec)))
+    assert_array_almost_equal(A.T * vecT, Ck.T * (Kk.T * (Rk.T * vecT)))
+    assert_array_almost_equal(AT * vecT, Ck.T * (Kk.T * (Rk.T * vecT)))
+    assert A.T.device and AT.T.device
+    host = RowColKhatriRaoMatrix(R=R, K=K, C=C)
+    assert_allclose(A * vec, host * vec, rtol=0, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_rowcol_khatri_rao_matvec_on_device_large_and_selection_rows():
+    """Ragged sizes (rows not a multiple of 64, columns not a multiple of 64), dense and selection-matrix row factors mixed, the
+    GRIEF use (kern/grief_kernel.py:96-104 through expand_SKC: R = selection of eigenvector rows, C = Q^T K_ux)."""
+    import gp_grief_b200 as gp
+    from gp_grief_b200.tensors import RowColKhatriRaoMatrix, RowColKhatriRaoMatrixTransposed, SelectionMatrixSparse
+    rng = np.random.default_rng(12)
+    rows, cols = 1000 + 37, 333
+    ms = [5, 17, 1, 30]
+    C = [rng.standard_normal((m, cols)) for m in ms]
+    x = rng.standard_normal((cols, 1))
+    R_dense = [rng.standard_normal((rows, m)) for m in ms]
+    A = RowColKhatriRaoMatrix(R=R_dense, K=None, C=C, device=True)
+    ref = np.prod([r.dot(c) for r, c in zip(R_dense, C)], axis=0).dot(x)
+    assert_allclose(A * x, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    v = rng.standard_normal((rows, 1))
+    refT = np.prod([r.dot(c) for r, c in zip(R_dense, C)], axis=0).T.dot(v)
+    assert_allclose(A.T * v, refT, rtol=0, atol=1e-12 * np.abs(refT).max())
+    # selection-matrix rows (index vectors on the device), mixed with one dense factor
+    sel = [SelectionMatrixSparse((rng.integers(0, m, size=rows), m)) for m in ms]
+    R_mix = [sel[0], R_dense[1], sel[2], sel[3]]
+    G = np.prod([C[t][sel[t].indicies, :] if t != 1 else R_dense[1].dot(C[1]) for t in range(4)], axis=0)
+    Am = RowColKhatriRaoMatrix(R=R_mix, K=None, C=C, device=True)
+    assert_allclose(Am * x, G.dot(x), rtol=0, atol=1e-12 * np.abs(G.dot(x)).max())
+    R_sel = sel
+    Gs = np.prod([C[t][sel[t].indicies, :] for t in range(4)], axis=0)
+    As = RowColKhatriRaoMatrix(R=R_sel, K=None, C=C, device=True)
+    assert_allclose(As * x, Gs.dot(x), rtol=0, atol=1e-12 * np.abs(Gs.dot(x)).max())
+    assert isinstance(As.T, RowColKhatriRaoMatrixTransposed)
+    assert_allclose(As.T * v, Gs.T.dot(v), rtol=0, atol=1e-12 * np.abs(Gs.T.dot(v)).max())

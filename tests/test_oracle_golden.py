@@ -98,3 +98,35 @@ def test_log_kron_reference_test():
     np.random.seed(0)
     a, b = np.random.rand(5), np.random.rand(7)
     assert_allclose(orc.log_kron(np.log(a), b), np.log(np.kron(a, b)), rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["host_t1_sum_n800_d3_m9_p36", "host_t1_prod_n800_d3_m9_p36", "host_t2_sum_n500_d2_m8_p24"])
+def test_oracle_with_composite_kernels(name):
+    """Kernels with children (kern/basekernel.py:131-190) given to the oracle as callables: pins `kernel_cov`'s callable branch
+    to the reference's output for `k1 + k2` / `k1 * k2` kernels (oracle/gen_golden.py:composite_cases)."""
+    g = load_golden(name)
+    d = int(g["n_grid_dims"])
+
+    def composite(i):
+        def cov(x, z):
+            kp = orc.kernel_cov(str(g["parent_name"]), x, z, float(g["parent_variance"]), g["parent_lengthscales"][i])
+            kc = orc.kernel_cov(str(g["child_name"]), x, z, float(g["child_variance"]), g["child_lengthscales"][i])
+            return kp * kc if str(g["op"]) == "mul" else kp + kc
+        return cov
+
+    names = [composite(i) for i in range(d)]
+    xg = [g["xg_%d" % i] for i in range(d)]
+    p = int(g["n_eigs"])
+    basis = orc.setup_inducing_cov(names, [1.0] * d, [1.0] * d, xg, p)
+    for k in range(d):
+        assert_array_equal(basis.Q[k], g["Q_%d" % k])
+        assert_array_equal(basis.eig_loc[:, k], g["sel_%d" % k])
+    assert_array_equal(basis.log_lam, g["log_lam"])
+    Phi = orc.grief_phi(basis, names, [1.0] * d, [1.0] * d, xg, g["x"])
+    f = orc.fit_from_phi(Phi, g["y"], np.ones(p), float(g["noise_var"]))
+    assert_allclose(f.lml, float(g["lml"]), rtol=1e-13)
+    assert_allclose(f.A, g["A"], rtol=1e-12, atol=1e-12 * np.abs(g["A"]).max())
+    Phin = orc.grief_phi(basis, names, [1.0] * d, [1.0] * d, xg, g["xnew"])
+    yhat, yvar = orc.predict(f, Phin)
+    assert_allclose(yhat, g["yhat"], rtol=1e-10, atol=1e-12)
+    assert_allclose(np.diag(yvar), g["yvar_diag"], rtol=1e-11)

@@ -68,7 +68,8 @@ def test_fused_phi_t_y_over_several_slabs_and_ragged_rows():
 @pytest.mark.parametrize("kernel", ["RBF", "Matern32"])
 def test_digit_count_controls_the_error_of_both_products(kernel):
     """8 D - 2 bits per operand below its row maximum: the error of A = Phi^T Phi and of q = diag(Phi B Phi^T) must shrink by
-    ~2^8 per digit and stay under the documented bound; D = 7 is the DGEMM-class default."""
+    ~2^8 per digit and stay under the documented bound; D = 7 is the DGEMM class, the defaults are 6 / 4 / 6 (Gram / gradient pass /
+    predictive variance)."""
     import torch
     rng = np.random.default_rng(8)
     plan, basis, c = _random_plan(d=4, m=7, p=260, kernel=kernel)
@@ -80,11 +81,11 @@ def test_digit_count_controls_the_error_of_both_products(kernel):
     B = rng.standard_normal((plan.p, plan.p))
     B = torch.from_numpy(B + B.T).cuda()
     q_ref = ((Phi @ B) * Phi).sum(1).cpu().numpy()
-    assert plan.get_option(nat.OPT_DIGITS_GRAM) == 7 and plan.get_option(nat.OPT_DIGITS_Z) == 7
+    assert (plan.get_option(nat.OPT_DIGITS_GRAM), plan.get_option(nat.OPT_DIGITS_Z), plan.get_option(nat.OPT_DIGITS_VAR)) == (6, 4, 6)
     errs_a, errs_q = [], []
     for D in (3, 4, 5, 6, 7):
         plan.set_option(nat.OPT_DIGITS_GRAM, D)
-        plan.set_option(nat.OPT_DIGITS_Z, D)
+        plan.set_option(nat.OPT_DIGITS_VAR, D)
         A = plan.gram(T, n).cpu().numpy()
         assert_array_equal(A, A.T)
         q = plan.quadform_rows(T, n, B).cpu().numpy()
@@ -99,14 +100,17 @@ def test_digit_count_controls_the_error_of_both_products(kernel):
     with pytest.raises(ValueError):
         plan.set_option(nat.OPT_DIGITS_Z, 8)
     with pytest.raises(ValueError):
+        plan.set_option(nat.OPT_DIGITS_VAR, 8)
+    with pytest.raises(ValueError):
         plan.set_option(nat.OPT_DIGITS_GRAM, 2)
 
 
-@pytest.mark.parametrize("digits", [(6, 6), (6, 5), (7, 5)])
+@pytest.mark.parametrize("digits", [(7, 7), (6, 5), (6, 4), (5, 4)])
 @pytest.mark.parametrize("name", ["syn_t2_n2000_d4_m8_p64", "syn_t2_matern52_n1500_d3_m10_p48", "syn_t1_n3000_d6_m10_p256_w",
                                   "c1_automobile"])
 def test_reduced_digit_models_stay_within_the_north_star_tolerance(name, digits):
-    """The reference goldens (LML, gradients) at <= 1e-9 relative with fewer int8 digit products (21 / 15 instead of 28)."""
+    """The reference goldens (LML, gradients) at <= 1e-9 relative with fewer int8 digit products than the 28 + 28 of the DGEMM
+    class (default (6, 4): 22 + 10)."""
     g = load_golden(name)
     m = ta.build_model(g)
     m.gemm_digits = digits
@@ -133,8 +137,8 @@ def test_options_are_per_plan_not_process_wide():
     plan_a.set_option(nat.OPT_GEMM_MODE, 0)
     plan_a.set_option(nat.OPT_DIGITS_GRAM, 5)
     assert plan_b.get_option(nat.OPT_GEMM_MODE) == before == 1          # neither the other plan nor the defaults moved
-    assert plan_b.get_option(nat.OPT_DIGITS_GRAM) == 7
-    assert nat.lib().grief_get_default_option(nat.OPT_DIGITS_GRAM) == 7
+    assert plan_b.get_option(nat.OPT_DIGITS_GRAM) == 6
+    assert nat.lib().grief_get_default_option(nat.OPT_DIGITS_GRAM) == 6
     n = 5000
     X = torch.from_numpy(rng.random((n, c["d"]))).cuda()
     Ta, Tb = plan_a.build_tables(X), plan_b.build_tables(X)
@@ -144,9 +148,9 @@ def test_options_are_per_plan_not_process_wide():
     try:
         nat.check(nat.lib().grief_set_default_option(nat.OPT_DIGITS_Z, 6))
         plan_c, _, _ = _random_plan(p=150, seed=1)
-        assert plan_c.get_option(nat.OPT_DIGITS_Z) == 6 and plan_b.get_option(nat.OPT_DIGITS_Z) == 7
+        assert plan_c.get_option(nat.OPT_DIGITS_Z) == 6 and plan_b.get_option(nat.OPT_DIGITS_Z) == 4
     finally:
-        nat.check(nat.lib().grief_set_default_option(nat.OPT_DIGITS_Z, 7))
+        nat.check(nat.lib().grief_set_default_option(nat.OPT_DIGITS_Z, 4))
     with pytest.raises(ValueError):
         nat.check(nat.lib().grief_set_default_option(99, 1))
 
