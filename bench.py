@@ -407,7 +407,9 @@ def run_ours(args):
         model.parameters = prm
 
     # ---- parity blocks (outside the timed region) ----
-    check = {"lml": lml_val, "grad_finite": bool(np.all(np.isfinite(grad[~np.isnan(grad)])))}
+    check = {"lml": lml_val, "grad_finite": bool(np.all(np.isfinite(grad[~np.isnan(grad)]))),
+             # a-posteriori audit of the digit counts, done by the model at its first evaluation (models/gp_grief_model.py)
+             "arithmetic_audit": model.arithmetic_audit}
     if not args.no_check:
         # (a) the timed arithmetic against the FP64 DMMA mode at FULL n: same step, same rows, all ranks
         if args.gemm != "fp64":
@@ -536,8 +538,10 @@ def run_ours(args):
     digits_of = {"k_zgemm": dz, "k_gram": dg}
     gk = {"int8": "k_ozaki<1,D>", "int8x2": "k_ozaki<2,D> (cta_group::2 pairs)", "fp64": "k_gemm_nt"}[args.gemm]
     label = {"k_zgemm": gk + " [Z = Phi*P^-1, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
-             "k_build_phi": "k_build_phi [Phi slab, pass 2]", "k_build_phi_t": "k_build_phi_t (+ slot maxima, fused Phi^T y) [Phi^T slab, pass 1]",
-             "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)"}
+             "k_build_phi": "k_build_phi (+ row maxima, fused residual a = (y - Phi b) / noise) [Phi slab, pass 2]", "k_build_phi_t": "k_build_phi_t (+ slot maxima, fused Phi^T y) [Phi^T slab, pass 1]",
+             "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)",
+             "k_contract": "k_contract_back [W = dL/dT from Z^T, lane = row trie sweep]",
+             "k_dtables": "k_contract_tail [W -> V -> parameter sums]"}
     non_gemm = 0.0
     for name in ("k_zgemm", "k_gram", "k_contract", "k_build_phi", "k_build_phi_t", "solve", "k_dtables", "k_tables", "phi_t_y", "k_topk"):
         t_ms, cnt = prof.get(name, (0.0, 0))

@@ -60,6 +60,10 @@ SIGNATURES = {
     "grief_set_slab_budget": (None, [c_size]),
     "grief_set_gemm_mode": (None, [c_int]),
     "grief_get_gemm_mode": (c_int, []),
+    "grief_comm_unique_id": (c_int, [c_void]),
+    "grief_comm_create": (c_int, [c_void, c_void, c_int, c_int]),
+    "grief_comm_allreduce_sum": (c_int, [c_void, c_void, c_i64, c_void]),
+    "grief_comm_destroy": (None, [c_void]),
     "grief_rowcol_kr_matvec": (c_int, [c_int, c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
     "grief_gemm_nt": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
     "grief_solve_lml": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void, c_void, c_dbl, c_i64, c_void, c_void,

@@ -28,8 +28,9 @@ int grad_desc_create(GradDesc** out, const Plan* pl, int n_active, const int32_t
 int grad_desc_n_active(const GradDesc* gd);
 int contract_acc_len(const Plan* pl);
 int contract_total_warps(const Plan* pl, int sms);
-int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* y,
-                    const double* bvec, double noise_var, int64_t rows_blk, int64_t rows_valid, double* acc, int sms, cudaStream_t stream);
+size_t contract_w_doubles(const Plan* pl, int64_t rows);
+int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* a,
+                    const double* bvec, int64_t rows_blk, int64_t rows_valid, double* Wbuf, double* acc, int sms, cudaStream_t stream);
 int launch_grad_finish(const Plan* pl, const GradDesc* gd, const double* acc, int sms, double* out, cudaStream_t stream);
 int launch_rowdot(const Plan* pl, const double* Zt, int64_t ldz, const double* T, int64_t rows_blk, int64_t rows_valid, double* out,
                   cudaStream_t stream);
@@ -37,9 +38,17 @@ int launch_permute_b(const Plan* pl, const double* B, int64_t ldb, double* Bperm
 int launch_permute_vec(const Plan* pl, const double* in, double scale, double* out, cudaStream_t stream);
 size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows);
 int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, int digits, cudaStream_t stream);
+struct ResidualArgs {      // optional by-product of the slab builder: a = (y - Phi bvec) / noise_var for the slab's rows
+  const double* bvec = nullptr; const double* y = nullptr; int64_t y_rows = 0; double inv_noise = 0.0; double* a_out = nullptr;
+};
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
-                 int64_t ldz, int digits, cudaStream_t stream, int* launches);
+                 int64_t ldz, int digits, const ResidualArgs* res, cudaStream_t stream, int* launches);
 int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
+struct Comm;
+int comm_unique_id(char* id_out);
+int comm_create(Comm** out, const char* id, int world, int rank);
+int comm_allreduce_sum(Comm* c, double* buf, int64_t count, cudaStream_t stream);
+void comm_destroy(Comm* c);
 int launch_rowcol_kr_matvec(int d, const int32_t* m, const double* const* R, const int32_t* const* ridx, const double* const* C, int64_t rows,
                             int64_t cols, const double* x, double* y, cudaStream_t stream);
 
@@ -284,13 +293,14 @@ int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const 
   return grad_desc_create(&pl->grad, pl, n_active, dims, kinds, dqs_concat);
 }
 
-// workspace of grief_grad_theta: [Zp^T slab] [GEMM scratch] [per-warp accumulators] [b in sorted order] [permuted P^-1]
+// workspace of grief_grad_theta: [Zp^T slab] [GEMM scratch] [W slab] [a slab] [per-warp accumulators] [b in sorted order] [permuted P^-1]
 size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
   if (!pl->grad) return 0;
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) +
+         align256(contract_w_doubles(pl, slab) * sizeof(double)) + align256((size_t)slab * sizeof(double)) +
          align256((size_t)contract_total_warps(pl, sms) * contract_acc_len(pl) * sizeof(double)) + align256((size_t)pl->p_pad * sizeof(double)) +
          align256((size_t)pl->p_pad * pl->p_pad * sizeof(double));
 }
@@ -313,6 +323,8 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   char* q = reinterpret_cast<char*>(workspace_dev);
   double* Zt = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
   void* zscr = q; q += align256(zgemm_scratch_bytes(pl, slab));
+  double* Wbuf = reinterpret_cast<double*>(q); q += align256(contract_w_doubles(pl, slab) * sizeof(double));
+  double* avec = reinterpret_cast<double*>(q); q += align256((size_t)slab * sizeof(double));
   double* acc = reinterpret_cast<double*>(q); q += align256(acc_doubles * sizeof(double));
   double* bvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p_pad * sizeof(double));
   double* Bperm = reinterpret_cast<double*>(q);
@@ -328,12 +340,14 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);        // multiple of 128, covered by the zero-padded tables
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Zt, slab, pl->opts.digits_z, stream, &g_launches);
+    ResidualArgs res;                                           // a = (y - Phi b) / noise_var comes out of the slab builder's sweep
+    res.bvec = bvec; res.y = y_dev + r0; res.y_rows = rows_valid; res.inv_noise = 1.0 / noise_var; res.a_out = avec;
+    rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Zt, slab, pl->opts.digits_z, &res, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
-    rc = launch_contract(pl, Zt, slab, T_dev + (size_t)r0 * pl->stride, X_dev + (size_t)r0 * ldx, ldx, y_dev + r0, bvec, noise_var, rows_blk,
-                         rows_valid, acc, sms, stream);
+    rc = launch_contract(pl, Zt, slab, T_dev + (size_t)r0 * pl->stride, X_dev + (size_t)r0 * ldx, ldx, avec, bvec, rows_blk, rows_valid, Wbuf,
+                         acc, sms, stream);
     if (rc != GRIEF_OK) return rc;
-    g_launches += 1;
+    g_launches += 2;
   }
   rc = launch_grad_finish(pl, gd, acc, sms, grad_dev, stream);
   if (rc == GRIEF_OK) g_launches += 1;
@@ -369,7 +383,7 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   for (int64_t r0 = 0; r0 < n128; r0 += slab) {
     const int64_t rows_blk = std::min(slab, n128 - r0);
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
-    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, slab, pl->opts.digits_var, stream, &g_launches);
+    int rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Z, slab, pl->opts.digits_var, nullptr, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_rowdot(pl, Z, slab, T_dev + (size_t)r0 * pl->stride, rows_blk, rows_valid, q_dev + r0, stream);
     if (rc != GRIEF_OK) return rc;
@@ -377,6 +391,24 @@ int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, 
   }
   return pl->opts.gemm_mode == 1 ? ozaki_check(pl->d_err, stream) : GRIEF_OK;
 }
+
+int grief_comm_unique_id(char* id_out) {
+  GRIEF_REQUIRE(id_out != nullptr, "grief_comm_unique_id: null pointer");
+  return comm_unique_id(id_out);
+}
+int grief_comm_create(grief_comm** comm, const char* id, int world_size, int rank) {
+  GRIEF_REQUIRE(comm && id, "grief_comm_create: null pointer");
+  Comm* c = nullptr;
+  int rc = comm_create(&c, id, world_size, rank);
+  if (rc != GRIEF_OK) return rc;
+  *comm = reinterpret_cast<grief_comm*>(c);
+  return GRIEF_OK;
+}
+int grief_comm_allreduce_sum(grief_comm* comm, double* buf_dev, int64_t count, void* stream) {
+  GRIEF_REQUIRE(comm != nullptr, "grief_comm_allreduce_sum: null communicator");
+  return comm_allreduce_sum(reinterpret_cast<Comm*>(comm), buf_dev, count, (cudaStream_t)stream);
+}
+void grief_comm_destroy(grief_comm* comm) { comm_destroy(reinterpret_cast<Comm*>(comm)); }
 
 int grief_rowcol_kr_matvec(int d, const int32_t* m, const double* const* R_dev, const int32_t* const* ridx_dev, const double* const* C_dev,
                            int64_t rows, int64_t cols, const double* x_dev, double* y_dev, void* stream) {

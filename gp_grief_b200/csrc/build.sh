@@ -7,7 +7,7 @@ mkdir -p "${OUT}" "${HERE}/build"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
        --expt-relaxed-constexpr -I"${HERE}/../../include")
-SRCS=(plan rows phi_stage solve dense ozaki topk grad krmatvec abi)
+SRCS=(plan rows phi_stage solve dense ozaki topk grad krmatvec comm abi)
 OBJS=()
 pids=()
 for s in "${SRCS[@]}"; do
@@ -21,5 +21,5 @@ for i in "${!pids[@]}"; do
 done
 [ "${fail}" = 0 ] || exit 1
 "${NVCC}" -shared -o "${OUT}/libgrief_b200.so" "${OBJS[@]}" -gencode arch=compute_100a,code=sm_100a \
-  -L/usr/local/cuda/lib64 -lcudart -lcuda -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+  -L/usr/local/cuda/lib64 -lcudart -lcuda -ldl -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
 echo "built ${OUT}/libgrief_b200.so"

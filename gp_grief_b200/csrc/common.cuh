@@ -11,8 +11,7 @@
 namespace grief {
 
 // ---- error plumbing -------------------------------------------------------------------------
-// error codes: the public GRIEF_ERR_* macros of include/grief_b200.h (+ one internal code)
-#define GRIEF_ERR_NCCL 6
+// error codes: the public GRIEF_ERR_* macros of include/grief_b200.h
 
 void set_last_error(const std::string& msg);
 int fail(int code, const char* fmt, ...);

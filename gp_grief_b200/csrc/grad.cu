@@ -15,10 +15,17 @@
 //   F_i[n,k] = sum_u K_i(x_n,u) Qs_i[u,k]   =>   dL/dtheta = sum_n sum_u dK_i(x_n,u)/dtheta * (sum_k V_i[n,k] Qs_i[u,k])
 //                                                          + sum_{u,k} dQs_i[u,k]/dtheta * M_i[u,k],   M_i[u,k] = sum_n K_i(x_n,u) V_i[n,k]
 // with dQs/dtheta (eigenvector / eigenvalue perturbation of the m_i x m_i grid problem) supplied by the host.
-// k_contract_rows: one warp per 32 data rows, LANE = ROW.  The sorted columns form a trie over the key positions (consecutive
-// columns share their leading slots); every lane walks it in the same order, so there is no divergence and no cross-lane traffic:
-// prefix products and per-level partial sums live in registers, W lives in shared memory as [slot][lane] (conflict-free).  ~15
-// instructions per (row, column) instead of the ~110 of the round-1 kernel (warp per row, lane = column, one FMA per parameter),
+// Three kernels per slab of rows share the work (each at the occupancy its state allows):
+//   k_build_phi (phi_stage.cu)   the slab builder that feeds the GEMM also forms f = Phi b from the values it has in registers and
+//                                writes a = (y - f) / sigma^2 per row: no separate forward sweep.
+//   k_contract_back              one warp per 32 data rows, LANE = ROW.  The sorted columns form a trie over the key positions
+//                                (consecutive columns share their leading slots); every lane walks it in the same order, so there is
+//                                no divergence and no cross-lane traffic: prefix products and per-level partial sums live in registers,
+//                                W lives in shared memory as [slot][lane] (conflict-free) and is written out as [row group][slot][32].
+//                                Per-row state (table row + W row, 1.6 KB) limits this kernel to 4 warps per SM, so it does nothing
+//                                but the sweep over Zp^T.
+//   k_contract_tail              W -> V -> parameter sums and the M_i matrices, 8 warps per SM (needs F, V and K_i of a row only).
+// ~15 instructions per (row, column) instead of the ~110 of the round-1 kernel (warp per row, lane = column, one FMA per parameter),
 // and the 4 KB/row derivative table of k_dtables is gone.
 #include <vector>
 
@@ -120,8 +127,9 @@ __device__ __forceinline__ void kern_eval_d(int kernel, double x, double u, doub
   }
 }
 
-// ---- column sweep helpers (lane = row; all control flow is warp-uniform) ----
-// Key position k of sorted column c: slot ss[c * G + k]; level[c] = first key position where column c differs from c - 1 (G if equal).
+// ---- backward sweep (lane = row; all control flow is warp-uniform) ----
+// Sorted column c has its key-order slots packed one byte each in plan->d_sorted_pack ((G + 3) / 4 words, key position k in byte
+// 3 - k % 4 of word k / 4); the first key position where c differs from c - 1 is a count-leading-zeros of the XOR.
 template <int G>
 struct Trie {
   double pfx[G > 1 ? G - 1 : 1];     // pfx[k] = h_0 * ... * h_k of the open path (levels 0 .. G-2)
@@ -129,36 +137,32 @@ struct Trie {
   int sk[G > 1 ? G - 1 : 1];         // its slot
 };
 
-struct ContractParams {
+struct BackParams {
   const double* Zt; int64_t ldz;     // Zp^T slab: [p_pad][ldz], rows of the slab contiguous
   const double* T; int stride;       // slab rows x stride
-  const double* X; int64_t ldx;      // slab rows x ldx
-  const double* y;                   // slab rows
+  const double* a;                   // slab rows: (y - Phi b) / noise_var (0 for rows that do not exist), written by k_build_phi
   const double* bvec;                // p_pad: b in sorted column order (0 for padding columns)
-  const uint16_t* ss; const uint8_t* level;      // sorted slots (key order), level
-  const DimDesc* dims; const double* grid; const double* qs; const uint8_t* slot_k; const int* slot_group; const int* group_begin;
-  int d, p_pad, width, sum_u, max_group_dims, m_max;
-  int64_t rows_valid;                // rows of the slab that exist (the rest are zero-padded tables)
+  const uint32_t* pack;              // p_pad x NW packed key-order slots
+  int p_pad;
   int n_rg;                          // 32-row groups in the slab
-  double inv_noise;
-  double* acc; int acc_len;          // [total warps][acc_len]: M_i (sum m_i u_i doubles, layout of qs) then (gl_i, gv_i) per dimension
-  int regionA;                       // doubles of the per-warp scratch that starts as the table rows
+  double* W;                         // out: [n_rg][stride][32]  dL/dT of every row
 };
 
+// One warp per 32 data rows.  The table rows sit in shared memory as [lane][stride] (odd stride: conflict-free), W as [slot][lane].
+// Every lane walks the trie of sorted columns in the same order: prefix products and per-level partial sums live in registers, only
+// the last key position costs a shared-memory read-modify-write per column.  Two batches of NB columns of Zp^T are in flight per warp.
 template <int G>
-__global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
+__global__ void __launch_bounds__(128) k_contract_back(const BackParams P) {
   extern __shared__ double sm[];
+  constexpr int NW = (G + 3) / 4, NB = 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  double* sA = sm + (size_t)warp * (P.regionA + P.stride * 32);      // table rows [32][stride]; later F, V, K scratch
-  double* sW = sA + P.regionA;                                        // [stride][32]
-  const int wg = blockIdx.x * nw + warp, wtot = gridDim.x * nw;
-  double* acc_out = P.acc + (size_t)wg * P.acc_len;
   const int stride = P.stride;
-  constexpr int NB = 16;
+  double* sA = sm + (size_t)warp * (2 * stride * 32);                 // table rows [32][stride]
+  double* sW = sA + (size_t)stride * 32;                              // [stride][32]
+  const int wg = blockIdx.x * nw + warp, wtot = gridDim.x * nw;
   for (int rg = wg; rg < P.n_rg; rg += wtot) {
     __syncwarp();
     const int64_t row = (int64_t)rg * 32 + lane;
-    const bool valid = row < P.rows_valid;
     {
       const double* src = P.T + (size_t)rg * 32 * stride;
       for (int e = lane; e < 32 * stride; e += 32) sA[e] = src[e];
@@ -166,48 +170,20 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
     }
     __syncwarp();
     const double* trow = sA + (size_t)lane * stride;
+    const double a_n = P.a[row];
     Trie<G> tr;
-    // ---- forward sweep: f = Phi[row, :] . b ----
-    double f = 0.0;
-    for (int c0 = 0; c0 < P.p_pad; c0 += NB) {
-      int lv[NB], sl[NB];
-      double bv[NB];
-#pragma unroll
-      for (int e = 0; e < NB; ++e) {
-        lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(P.level + c0 + e);
-        sl[e] = __ldg(P.ss + (size_t)(c0 + e) * G + (G - 1));
-        bv[e] = __ldg(P.bvec + c0 + e);
-      }
-#pragma unroll
-      for (int e = 0; e < NB; ++e) {
-        if constexpr (G > 1) {
-          if (lv[e] < G - 1) {
-#pragma unroll
-            for (int k = 0; k < G - 1; ++k)
-              if (k >= lv[e]) {
-                const double h = trow[__ldg(P.ss + (size_t)(c0 + e) * G + k)];
-                tr.pfx[k] = k > 0 ? tr.pfx[k - 1] * h : h;
-              }
-          }
-          f = fma(tr.pfx[G - 2] * trow[sl[e]], bv[e], f);
-        } else {
-          f = fma(trow[sl[e]], bv[e], f);
-        }
-      }
-    }
-    const double a_n = valid ? (P.y[row] - f) * P.inv_noise : 0.0;
-    // ---- backward sweep: W[slot] += dL/dT ----
     double S[G > 1 ? G - 1 : 1];
 #pragma unroll
     for (int k = 0; k < (G > 1 ? G - 1 : 1); ++k) S[k] = 0.0;
-    // Zp^T is streamed from HBM: the loads of batch c0 + NB are issued before batch c0 is consumed (two batches of NB columns in
-    // flight per warp).  With four warps per SM (shared memory holds their tables and W) nothing else hides the DRAM latency.
+    uint32_t prev[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) prev[w] = 0;
     const double* zcol = P.Zt + row;
     double znext[NB];
 #pragma unroll
     for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)e * P.ldz);
     for (int c0 = 0; c0 < P.p_pad; c0 += NB) {
-      int lv[NB], sl[NB];
+      uint32_t wd[NB][NW];
       double zt[NB];
 #pragma unroll
       for (int e = 0; e < NB; ++e) zt[e] = znext[e];
@@ -217,18 +193,26 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
       }
 #pragma unroll
       for (int e = 0; e < NB; ++e) {
-        lv[e] = (c0 + e == 0) ? 0 : (int)__ldg(P.level + c0 + e);
-        sl[e] = __ldg(P.ss + (size_t)(c0 + e) * G + (G - 1));
+#pragma unroll
+        for (int w = 0; w < NW; ++w) wd[e][w] = __ldg(P.pack + (size_t)(c0 + e) * NW + w);
         zt[e] = fma(a_n, __ldg(P.bvec + c0 + e), -zt[e]);
       }
 #pragma unroll
       for (int e = 0; e < NB; ++e) {
+        const int sl = (int)((wd[e][(G - 1) >> 2] >> (8 * (3 - ((G - 1) & 3)))) & 0xFFu);
         if constexpr (G > 1) {
-          if (lv[e] < G - 1) {
-            if (c0 + e > 0) {                  // close the open nodes of levels G-2 .. lv
+          int lv = G;                                  // first key position where this column differs from the previous one
+#pragma unroll
+          for (int w = NW - 1; w >= 0; --w) {
+            const uint32_t x = wd[e][w] ^ prev[w];
+            if (x) lv = 4 * w + (__clz(x) >> 3);
+          }
+          if (c0 + e == 0) lv = 0;
+          if (lv < G - 1) {
+            if (c0 + e > 0) {                          // close the open nodes of levels G-2 .. lv
 #pragma unroll
               for (int k = G - 2; k >= 0; --k)
-                if (k >= lv[e]) {
+                if (k >= lv) {
                   const double up = k > 0 ? tr.pfx[k - 1] : 1.0;
                   sW[tr.sk[k] * 32 + lane] += up * S[k];
                   if (k > 0) S[k - 1] = fma(tr.hk[k], S[k], S[k - 1]);
@@ -236,21 +220,23 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
                 }
             }
 #pragma unroll
-            for (int k = 0; k < G - 1; ++k)      // open levels lv .. G-2 for this column
-              if (k >= lv[e]) {
-                tr.sk[k] = __ldg(P.ss + (size_t)(c0 + e) * G + k);
+            for (int k = 0; k < G - 1; ++k)            // open levels lv .. G-2 for this column
+              if (k >= lv) {
+                tr.sk[k] = (int)((wd[e][k >> 2] >> (8 * (3 - (k & 3)))) & 0xFFu);
                 tr.hk[k] = trow[tr.sk[k]];
                 tr.pfx[k] = k > 0 ? tr.pfx[k - 1] * tr.hk[k] : tr.hk[k];
               }
           }
-          sW[sl[e] * 32 + lane] += tr.pfx[G - 2] * zt[e];
-          S[G - 2] = fma(trow[sl[e]], zt[e], S[G - 2]);
+          sW[sl * 32 + lane] += tr.pfx[G - 2] * zt[e];
+          S[G - 2] = fma(trow[sl], zt[e], S[G - 2]);
+#pragma unroll
+          for (int w = 0; w < NW; ++w) prev[w] = wd[e][w];
         } else {
-          sW[sl[e] * 32 + lane] += zt[e];
+          sW[sl * 32 + lane] += zt[e];
         }
       }
     }
-    if constexpr (G > 1) {                       // close what is still open
+    if constexpr (G > 1) {                             // close what is still open
 #pragma unroll
       for (int k = G - 2; k >= 0; --k) {
         const double up = k > 0 ? tr.pfx[k - 1] : 1.0;
@@ -259,10 +245,37 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
       }
     }
     __syncwarp();
-    // ---- tail: W -> V (per-dimension factors) -> parameter sums; the table rows are dead, their space is scratch ----
-    double* sF = sA;                               // [sum_u][32]
-    double* sV = sF + (size_t)P.sum_u * 32;        // [sum_u][32]
-    double* sK = sV + (size_t)P.sum_u * 32;        // [m_max][33]
+    double* dst = P.W + (size_t)rg * stride * 32;
+    for (int e = lane; e < 32 * stride; e += 32) dst[e] = sW[e];
+  }
+}
+
+// ---- tail: W -> V (per-dimension factors) -> parameter sums ----
+struct TailParams {
+  const double* W;                   // [n_rg][stride][32]
+  const double* X; int64_t ldx;      // slab rows x ldx
+  const DimDesc* dims; const double* grid; const double* qs; const uint8_t* slot_k; const int* slot_group; const int* group_begin;
+  int d, stride, width, sum_u, max_group_dims, m_max;
+  int64_t rows_valid;                // rows of the slab that exist (the rest are zero-padded tables)
+  int n_rg;
+  double* acc; int acc_len;          // [total warps][acc_len]: M_i (sum m_i u_i doubles, layout of qs) then (gl_i, gv_i) per dimension
+};
+
+// One warp per 32 data rows, lane = row.  Per warp: F [sum_u][32], V [sum_u][32], K [m_max][33] in shared memory.
+__global__ void __launch_bounds__(256) k_contract_tail(const TailParams P) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int per_warp = 64 * P.sum_u + 33 * P.m_max;
+  double* sF = sm + (size_t)warp * per_warp;     // [sum_u][32]
+  double* sV = sF + (size_t)P.sum_u * 32;        // [sum_u][32]
+  double* sK = sV + (size_t)P.sum_u * 32;        // [m_max][33]
+  const int wg = blockIdx.x * nw + warp, wtot = gridDim.x * nw;
+  double* acc_out = P.acc + (size_t)wg * P.acc_len;
+  for (int rg = wg; rg < P.n_rg; rg += wtot) {
+    __syncwarp();
+    const int64_t row = (int64_t)rg * 32 + lane;
+    const bool valid = row < P.rows_valid;
+    const double* Wl = P.W + (size_t)rg * P.stride * 32 + lane;
     for (int i = 0; i < P.d; ++i) {                // F_i[k] = sum_g K_i(x, u_g) Qs_i[g, k]
       const DimDesc dd = P.dims[i];
       const double x = valid ? P.X[row * P.ldx + i] : 0.0;
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(128) k_contract_rows(const ContractParams P) {
       const int g = __ldg(P.slot_group + s);
       const int b0 = __ldg(P.group_begin + g), b1 = __ldg(P.group_begin + g + 1);
       const uint8_t* ks = P.slot_k + (size_t)s * P.max_group_dims;
-      const double w = sW[s * 32 + lane];
+      const double w = __ldcs(Wl + (size_t)s * 32);
       for (int i = b0; i < b1; ++i) {
         double prod = w;
         for (int i2 = b0; i2 < b1; ++i2)
@@ -414,14 +427,18 @@ static int plan_m_max(const Plan* pl) {
   for (auto& dd : pl->dims) mm = std::max(mm, dd.m);
   return mm;
 }
-// warps per CTA that fit shared memory; per warp: region A (table rows [32][stride], later F [sum_u][32], V [sum_u][32], K [m_max][33])
-// and W [stride][32]
-static int contract_warps(const Plan* pl, size_t* smem_out, int* regionA_out) {
-  const int regionA = std::max(pl->stride * 32, 64 * pl->sum_u + 33 * plan_m_max(pl));
-  const size_t per_warp = ((size_t)regionA + (size_t)pl->stride * 32) * sizeof(double);
-  int nw = (int)std::min<size_t>(4, (220 * 1024) / per_warp);
+// backward kernel: warps per CTA that fit shared memory (per warp: table rows [32][stride] and W [stride][32])
+static int back_warps(const Plan* pl, size_t* smem_out) {
+  const size_t per_warp = (size_t)2 * pl->stride * 32 * sizeof(double);
+  const int nw = (int)std::min<size_t>(4, (224 * 1024) / per_warp);
   if (smem_out) *smem_out = per_warp * std::max(nw, 1);
-  if (regionA_out) *regionA_out = regionA;
+  return nw;
+}
+// tail kernel: per warp F [sum_u][32], V [sum_u][32], K [m_max][33]
+static int tail_warps(const Plan* pl, size_t* smem_out) {
+  const size_t per_warp = ((size_t)64 * pl->sum_u + (size_t)33 * plan_m_max(pl)) * sizeof(double);
+  const int nw = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
+  if (smem_out) *smem_out = per_warp * std::max(nw, 1);
   return nw;
 }
 int contract_acc_len(const Plan* pl) {
@@ -429,47 +446,58 @@ int contract_acc_len(const Plan* pl) {
   for (auto& dd : pl->dims) qtot += dd.m * dd.u;
   return qtot + 2 * pl->d;
 }
-int contract_total_warps(const Plan* pl, int sms) { return sms * std::max(1, contract_warps(pl, nullptr, nullptr)); }
+// accumulator rows of the tail kernel (one per warp of its grid)
+int contract_total_warps(const Plan* pl, int sms) { return sms * std::max(1, tail_warps(pl, nullptr)); }
+// doubles of the W slab for a slab of `rows` table rows
+size_t contract_w_doubles(const Plan* pl, int64_t rows) { return (size_t)rows * pl->stride; }
 
 template <int G>
-static int launch_contract_g(const ContractParams& P, int blocks, int threads, size_t smem, cudaStream_t stream) {
-  GRIEF_CUDA(cudaFuncSetAttribute(k_contract_rows<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_contract_rows<G><<<blocks, threads, smem, stream>>>(P);
+static int launch_back_g(const BackParams& P, int blocks, int threads, size_t smem, cudaStream_t stream) {
+  GRIEF_CUDA(cudaFuncSetAttribute(k_contract_back<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_contract_back<G><<<blocks, threads, smem, stream>>>(P);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }
 
-// Zt: Zp^T slab (p_pad x ldz).  acc: contract_total_warps x contract_acc_len doubles, zeroed by the caller before the first slab.
-int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* y,
-                    const double* bvec, double noise_var, int64_t rows_blk, int64_t rows_valid, double* acc, int sms, cudaStream_t stream) {
+// Zt: Zp^T slab (p_pad x ldz); a: (y - Phi b) / noise_var of the slab's rows (from the builder); Wbuf: contract_w_doubles(rows_blk)
+// doubles; acc: contract_total_warps x contract_acc_len doubles, zeroed by the caller before the first slab.
+int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* a,
+                    const double* bvec, int64_t rows_blk, int64_t rows_valid, double* Wbuf, double* acc, int sms, cudaStream_t stream) {
   if (rows_blk == 0) return GRIEF_OK;
-  size_t smem = 0;
-  int regionA = 0;
-  const int nw = contract_warps(pl, &smem, &regionA);
-  if (nw < 1) return fail(GRIEF_ERR_UNSUPPORTED, "contract: a table row of %d entries does not fit shared memory", pl->stride);
-  ContractParams P;
-  P.Zt = Zt; P.ldz = ldz; P.T = T; P.stride = pl->stride; P.X = X; P.ldx = ldx; P.y = y; P.bvec = bvec;
-  P.ss = pl->d_sorted_slot; P.level = pl->d_sorted_level;
-  P.dims = pl->d_dims; P.grid = pl->d_grid; P.qs = pl->d_qs; P.slot_k = pl->d_slot_k; P.slot_group = pl->d_slot_group; P.group_begin = pl->d_group_begin;
-  P.d = pl->d; P.p_pad = pl->p_pad; P.width = pl->width; P.sum_u = pl->sum_u; P.max_group_dims = pl->max_group_dims;
-  P.m_max = plan_m_max(pl);
-  P.rows_valid = rows_valid; P.n_rg = (int)(rows_blk / 32); P.inv_noise = 1.0 / noise_var;
-  P.acc = acc; P.acc_len = contract_acc_len(pl); P.regionA = regionA;
+  size_t smem_b = 0, smem_t = 0;
+  const int nwb = back_warps(pl, &smem_b), nwt = tail_warps(pl, &smem_t);
+  if (nwb < 1) return fail(GRIEF_ERR_UNSUPPORTED, "contract: a table row of %d entries does not fit shared memory", pl->stride);
+  if (nwt < 1) return fail(GRIEF_ERR_UNSUPPORTED, "contract: %d factors per row do not fit shared memory", pl->sum_u);
+  BackParams B;
+  B.Zt = Zt; B.ldz = ldz; B.T = T; B.stride = pl->stride; B.a = a; B.bvec = bvec; B.pack = pl->d_sorted_pack; B.p_pad = pl->p_pad;
+  B.n_rg = (int)(rows_blk / 32); B.W = Wbuf;
   int rc;
   prof_begin(PROF_CONTRACT, stream);
   switch (pl->n_groups) {
-    case 1: rc = launch_contract_g<1>(P, sms, nw * 32, smem, stream); break;
-    case 2: rc = launch_contract_g<2>(P, sms, nw * 32, smem, stream); break;
-    case 3: rc = launch_contract_g<3>(P, sms, nw * 32, smem, stream); break;
-    case 4: rc = launch_contract_g<4>(P, sms, nw * 32, smem, stream); break;
-    case 5: rc = launch_contract_g<5>(P, sms, nw * 32, smem, stream); break;
-    case 6: rc = launch_contract_g<6>(P, sms, nw * 32, smem, stream); break;
-    case 7: rc = launch_contract_g<7>(P, sms, nw * 32, smem, stream); break;
-    case 8: rc = launch_contract_g<8>(P, sms, nw * 32, smem, stream); break;
+    case 1: rc = launch_back_g<1>(B, sms, nwb * 32, smem_b, stream); break;
+    case 2: rc = launch_back_g<2>(B, sms, nwb * 32, smem_b, stream); break;
+    case 3: rc = launch_back_g<3>(B, sms, nwb * 32, smem_b, stream); break;
+    case 4: rc = launch_back_g<4>(B, sms, nwb * 32, smem_b, stream); break;
+    case 5: rc = launch_back_g<5>(B, sms, nwb * 32, smem_b, stream); break;
+    case 6: rc = launch_back_g<6>(B, sms, nwb * 32, smem_b, stream); break;
+    case 7: rc = launch_back_g<7>(B, sms, nwb * 32, smem_b, stream); break;
+    case 8: rc = launch_back_g<8>(B, sms, nwb * 32, smem_b, stream); break;
     default: return fail(GRIEF_ERR_UNSUPPORTED, "contract: %d groups", pl->n_groups);
   }
   prof_end(PROF_CONTRACT, stream);
-  return rc;
+  if (rc != GRIEF_OK) return rc;
+  TailParams Q;
+  Q.W = Wbuf; Q.X = X; Q.ldx = ldx;
+  Q.dims = pl->d_dims; Q.grid = pl->d_grid; Q.qs = pl->d_qs; Q.slot_k = pl->d_slot_k; Q.slot_group = pl->d_slot_group; Q.group_begin = pl->d_group_begin;
+  Q.d = pl->d; Q.stride = pl->stride; Q.width = pl->width; Q.sum_u = pl->sum_u; Q.max_group_dims = pl->max_group_dims; Q.m_max = plan_m_max(pl);
+  Q.rows_valid = rows_valid; Q.n_rg = (int)(rows_blk / 32);
+  Q.acc = acc; Q.acc_len = contract_acc_len(pl);
+  GRIEF_CUDA(cudaFuncSetAttribute(k_contract_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+  prof_begin(PROF_DTABLES, stream);
+  k_contract_tail<<<sms, nwt * 32, smem_t, stream>>>(Q);
+  prof_end(PROF_DTABLES, stream);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
 }
 
 int launch_grad_finish(const Plan* pl, const GradDesc* gd, const double* acc, int sms, double* out, cudaStream_t stream) {

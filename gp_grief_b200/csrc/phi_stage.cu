@@ -108,14 +108,31 @@ __global__ void k_col_exps(const int* __restrict__ slot_hi, const uint16_t* __re
   } else if (c < n_pad) exps[c] = 0;
 }
 
+// digits d_s of q = rint(v * scale) as bytes of one 64-bit word: digit s (0 = most significant) is byte 6 - s  (see store_digits)
+__device__ __forceinline__ unsigned long long digit_word(double v, double scale, int sd) {
+  const unsigned long long bias = 0x0080808080808080ull >> (8 * (7 - sd));
+  return (((unsigned long long)__double2ll_rn(v * scale) + bias) ^ bias) << (8 * (7 - sd));
+}
+// byte B (0..6) of four digit words, packed into one 32-bit word (word i -> byte i): 3 PRMT
+template <int B>
+__device__ __forceinline__ uint32_t gather_byte(const unsigned long long (&w)[4]) {
+  const uint32_t x0 = B < 4 ? (uint32_t)w[0] : (uint32_t)(w[0] >> 32), x1 = B < 4 ? (uint32_t)w[1] : (uint32_t)(w[1] >> 32);
+  const uint32_t x2 = B < 4 ? (uint32_t)w[2] : (uint32_t)(w[2] >> 32), x3 = B < 4 ? (uint32_t)w[3] : (uint32_t)(w[3] >> 32);
+  constexpr uint32_t sel = (uint32_t)(B & 3) | ((uint32_t)(4 + (B & 3)) << 4);
+  return __byte_perm(__byte_perm(x0, x1, sel), __byte_perm(x2, x3, sel), 0x5410);
+}
+
 // Phi^T slab, c = sorted column, one CTA per 128 table rows.  Lane = data row; each of the 16 warps owns p_pad / 16 consecutive
-// sorted columns and walks them for the four 32-row groups.  Consecutive sorted columns share their leading slots: the product P
-// of the first G-1 factors stays in a register per row group and is rebuilt only where sorted_level says a leading factor changed
-// (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
+// sorted columns and walks them for the four 32-row groups at once.  Consecutive sorted columns share their leading slots: the
+// product P of the first G-1 factors stays in a register per row group and is rebuilt only where sorted_level says a leading factor
+// changed (warp-uniform branch) -- ~1.5 gathers and 1.3 DMULs per element.
 //   DIG = false: out[c * ld + row]                                  (FP64 slab)
-//   DIG = true:  planes[s][c][row] (row stride ld bytes, plane stride p_pad * ld), scaled by 2^(8 sd - 2 - exps[c])
+//   DIG = true:  planes[s][c][k] (row stride ld bytes, plane stride p_pad * ld), scaled by 2^(8 sd - 2 - exps[c]); within every block
+//                of 128 data rows the K position is k = 4 * lane + row_group (data row = 32 * row_group + lane): a lane then stores
+//                the digit s of its four rows as ONE 32-bit word and a warp writes 128 contiguous bytes per (column, digit).  The
+//                Gram sums over K, and both operands of that product are this same slab: any fixed permutation of K is exact.
 // y != nullptr: the values are already in registers, so r_ws[block][c] = sum over the block's rows of y[row] * Phi[row][c] is formed
-// here (fixed order: lanes by butterfly, row groups in sequence) instead of rebuilding Phi a second time for Phi^T y.
+// here (fixed order: the four row groups in sequence, lanes by butterfly) instead of rebuilding Phi a second time for Phi^T y.
 template <int G, bool DIG>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __restrict__ T, int stride,
                                                                const uint16_t* __restrict__ sorted_slot,
@@ -131,19 +148,18 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
   const int cpw = p_pad / (kBuildThreads / 32);        // columns per warp (p_pad is a multiple of 128)
   const int c_begin = warp * cpw;
   constexpr int NB = 8, RG = kBuildRows / 32;
+  static_assert(RG == 4, "four row groups of 32 rows");
   const int64_t rb = blockIdx.x;
   stage_table_rows(sT, bar, T, stride, rb, 0);
   const size_t grow0 = (size_t)rb * kBuildRows + lane;
-  static_assert(RG == 4, "four row groups of 32 rows");
-  double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;       // y of this lane's row in each row group
-  if (y != nullptr) {
-    const int64_t row = (int64_t)grow0;
-    y0 = row < y_rows ? y[row] : 0.0;
-    y1 = row + 32 < y_rows ? y[row + 32] : 0.0;
-    y2 = row + 64 < y_rows ? y[row + 64] : 0.0;
-    y3 = row + 96 < y_rows ? y[row + 96] : 0.0;
-  }
-  double P0 = 1.0, P1 = 1.0, P2 = 1.0, P3 = 1.0;       // running prefix products, one per row group
+  double yv[RG];                                        // y of this lane's row in each row group
+#pragma unroll
+  for (int rg = 0; rg < RG; ++rg) yv[rg] = (y != nullptr && (int64_t)grow0 + 32 * rg < y_rows) ? y[grow0 + 32 * rg] : 0.0;
+  const double* trow[RG];
+#pragma unroll
+  for (int rg = 0; rg < RG; ++rg) trow[rg] = sT + (size_t)(rg * 32 + lane) * stride;
+  double P[RG] = {1.0, 1.0, 1.0, 1.0};                  // running prefix products, one per row group
+  const size_t plane_stride = (size_t)p_pad * ld;
   for (int c0 = c_begin; c0 < c_begin + cpw; c0 += NB) {
     int lv[NB], sl[NB];
     double dot[NB];
@@ -151,42 +167,48 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
     for (int e = 0; e < NB; ++e) {
       lv[e] = (c0 + e == c_begin) ? 0 : (int)__ldg(sorted_level + c0 + e);
       sl[e] = __ldg(sorted_slot + (size_t)(c0 + e) * G + (G - 1));
-      dot[e] = 0.0;
     }
-#pragma unroll 1
-    for (int rg = 0; rg < RG; ++rg) {                   // not unrolled: one copy of the body keeps the kernel below 128 registers
-      const double* trow = sT + (size_t)(rg * 32 + lane) * stride;
-      double P = rg == 0 ? P0 : (rg == 1 ? P1 : (rg == 2 ? P2 : P3));
-      const double yr = rg == 0 ? y0 : (rg == 1 ? y1 : (rg == 2 ? y2 : y3));
-      double last[NB];
 #pragma unroll
-      for (int e = 0; e < NB; ++e) last[e] = trow[sl[e]];
+    for (int e = 0; e < NB; ++e) {
+      if constexpr (G > 1) {
+        if (lv[e] < G - 1) {                             // warp-uniform: a leading factor changed
+          int lead[G - 1];
 #pragma unroll
-      for (int e = 0; e < NB; ++e) {
-        if constexpr (G > 1) {
-          if (lv[e] < G - 1) {
-            double q = trow[__ldg(sorted_slot + (size_t)(c0 + e) * G)];
+          for (int g = 0; g < G - 1; ++g) lead[g] = __ldg(sorted_slot + (size_t)(c0 + e) * G + g);
 #pragma unroll
-            for (int g = 1; g < G - 1; ++g) q *= trow[__ldg(sorted_slot + (size_t)(c0 + e) * G + g)];
-            P = q;
+          for (int rg = 0; rg < RG; ++rg) {
+            double q = trow[rg][lead[0]];
+#pragma unroll
+            for (int g = 1; g < G - 1; ++g) q *= trow[rg][lead[g]];
+            P[rg] = q;
           }
-          last[e] *= P;
         }
       }
-      if (rg == 0) P0 = P; else if (rg == 1) P1 = P; else if (rg == 2) P2 = P; else P3 = P;
-      const size_t grow = grow0 + rg * 32;
+      double v[RG];
+#pragma unroll
+      for (int rg = 0; rg < RG; ++rg) v[rg] = G > 1 ? P[rg] * trow[rg][sl[e]] : trow[rg][sl[e]];
       if constexpr (!DIG) {
 #pragma unroll
-        for (int e = 0; e < NB; ++e) out[(size_t)(c0 + e) * ld + grow] = last[e];
+        for (int rg = 0; rg < RG; ++rg) out[(size_t)(c0 + e) * ld + grow0 + rg * 32] = v[rg];
       } else {
+        const double scale = digit_scale(sd, __ldg(exps + c0 + e));
+        unsigned long long w[RG];
 #pragma unroll
-        for (int e = 0; e < NB; ++e)
-          store_digits(last[e], digit_scale(sd, __ldg(exps + c0 + e)), sd, planes + (size_t)(c0 + e) * ld + grow, (size_t)p_pad * ld);
+        for (int rg = 0; rg < RG; ++rg) w[rg] = digit_word(v[rg], scale, sd);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(planes + (size_t)(c0 + e) * ld + (size_t)rb * kBuildRows) + lane;
+        const size_t ps4 = plane_stride / 4;             // ld is a multiple of 128
+        dst[0 * ps4] = gather_byte<6>(w);
+        dst[1 * ps4] = gather_byte<5>(w);
+        dst[2 * ps4] = gather_byte<4>(w);
+        if (sd > 3) dst[3 * ps4] = gather_byte<3>(w);
+        if (sd > 4) dst[4 * ps4] = gather_byte<2>(w);
+        if (sd > 5) dst[5 * ps4] = gather_byte<1>(w);
+        if (sd > 6) dst[6 * ps4] = gather_byte<0>(w);
       }
-      if (y != nullptr) {                                // warp-uniform
+      double dsum = 0.0;
 #pragma unroll
-        for (int e = 0; e < NB; ++e) dot[e] = fma(yr, last[e], dot[e]);
-      }
+      for (int rg = 0; rg < RG; ++rg) dsum = fma(yv[rg], v[rg], dsum);
+      dot[e] = dsum;
     }
     if (y != nullptr) {                                  // warp-uniform
       double mine = 0.0;
@@ -222,69 +244,149 @@ __global__ void k_unpermute_vec(const double* __restrict__ in, const int* __rest
   if (c < p_pad && perm[c] >= 0) out[perm[c]] = in[c];
 }
 
-// Phi slab, row-major, lane = sorted column (coalesced stores); the G slots of a column are loaded once and reused for the
-// warp's eight rows.
+// ---- lane = data row walk over a range of sorted columns ----
+// pack: plan->d_sorted_pack, (G + 3) / 4 words per sorted column, key position k in byte 3 - k % 4 of word k / 4.  Consecutive sorted
+// columns share their leading slots; the product P of the first G-1 factors is rebuilt only where the packed words differ above the
+// last key position (all lanes read the same words: the branch is warp-uniform).  emit(c0, v) receives NB consecutive values.
+template <int G>
+__device__ __forceinline__ int pack_slot(const uint32_t* w, int k) { return (int)((w[k >> 2] >> (8 * (3 - (k & 3)))) & 0xFFu); }
+template <int G, int NB, typename Emit>
+__device__ __forceinline__ void walk_sorted_columns(const double* __restrict__ trow, const uint32_t* __restrict__ pack, int c_begin,
+                                                    int c_end, Emit&& emit) {
+  constexpr int NW = (G + 3) / 4;
+  uint32_t prev[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) prev[w] = 0;
+  double P = 1.0;
+  for (int c0 = c_begin; c0 < c_end; c0 += NB) {
+    uint32_t wd[NB][NW];
+#pragma unroll
+    for (int e = 0; e < NB; ++e)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) wd[e][w] = __ldg(pack + (size_t)(c0 + e) * NW + w);
+    double v[NB];
+#pragma unroll
+    for (int e = 0; e < NB; ++e) {
+      if constexpr (G > 1) {
+        // does any key position 0 .. G-2 differ from the previous column?  (the last position is byte 3 - (G-1) % 4 of the last word)
+        bool lead_changed = (c0 + e == c_begin);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          uint32_t x = wd[e][w] ^ prev[w];
+          if (w == NW - 1) x &= ~(0xFFu << (8 * (3 - ((G - 1) & 3))));
+          lead_changed |= (x != 0);
+        }
+        if (lead_changed) {
+          double q = trow[pack_slot<G>(wd[e], 0)];
+#pragma unroll
+          for (int g = 1; g < G - 1; ++g) q *= trow[pack_slot<G>(wd[e], g)];
+          P = q;
+        }
+        v[e] = P * trow[pack_slot<G>(wd[e], G - 1)];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) prev[w] = wd[e][w];
+      } else {
+        v[e] = trow[pack_slot<G>(wd[e], 0)];
+      }
+    }
+    emit(c0, v);
+  }
+}
+
+// Phi slab, row-major [row][sorted column], one CTA per 128 table rows.  Lane = data row: warp w works on row group w & 3 (32 rows)
+// and on the column quarter w >> 2, walking its columns with the shared prefix product (walk_sorted_columns: ~1.3 gathers and DMULs
+// per element instead of G).  A lane holds 16 consecutive columns of its row at a time and writes 16 contiguous bytes per digit
+// plane (DIG) or 128 contiguous bytes (FP64).
 //   DIG = false: out[row * ldo + c]
-//   DIG = true:  exps[row] from the row maximum (first sweep, registers only), then planes[s][row][c] (second sweep)
+//   DIG = true:  first sweep -> row maximum -> exps[row]; second sweep -> planes[s][row][c], scaled by 2^(8 sd - 2 - exps[row])
+// bvec != nullptr: f[row] = sum_c Phi[row][c] * bvec[c] is accumulated in the first sweep (the values are in registers) and
+// a_out[row] = (y[row] - f[row]) * inv_noise is written -- the residual scaled by the noise that the contraction kernel needs
+// (grad.cu); column quarters are summed in fixed order.
 template <int G, bool DIG>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __restrict__ T, int stride,
-                                                             const uint16_t* __restrict__ sorted_slot, int p_pad,
+                                                             const uint32_t* __restrict__ pack, int p_pad,
                                                              double* __restrict__ out, int64_t ldo, int* __restrict__ exps,
-                                                             int8_t* __restrict__ planes, size_t plane_stride, int sd, int* __restrict__ err) {
+                                                             int8_t* __restrict__ planes, size_t plane_stride, int sd, int* __restrict__ err,
+                                                             const double* __restrict__ bvec, const double* __restrict__ y, int64_t y_rows,
+                                                             double inv_noise, double* __restrict__ a_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
+  double* s_f = sT + (size_t)kBuildRows * stride;                     // [4 quarters][128 rows]
+  int* s_hi = reinterpret_cast<int*>(s_f + 4 * kBuildRows);           // [4 quarters][128 rows]
   init_stage_barrier(bar);
   stage_table_rows(sT, bar, T, stride, blockIdx.x, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int RW = kBuildRows / (kBuildThreads / 32);   // 8 rows per warp
-  const double* tbase = sT + (size_t)warp * RW * stride;
-  const size_t row0 = (size_t)blockIdx.x * kBuildRows + warp * RW;
-  double scale[RW];
-  if constexpr (DIG) {
-    int hi[RW];
+  const int rg = warp & 3, quarter = warp >> 2;
+  const int r_blk = rg * 32 + lane;
+  const double* trow = sT + (size_t)r_blk * stride;
+  const size_t grow = (size_t)blockIdx.x * kBuildRows + r_blk;
+  const int cq = p_pad / 4;                                           // p_pad is a multiple of 128
+  const int c_begin = quarter * cq, c_end = c_begin + cq;
+  constexpr int NB = 16;
+  const bool want_f = bvec != nullptr;
+  double scale = 1.0, f = 0.0;
+  if (DIG) {                                                          // sweep 1: row maximum (and f)
+    int hi = 0;
+    walk_sorted_columns<G, NB>(trow, pack, c_begin, c_end, [&](int c0, const double (&v)[NB]) {
 #pragma unroll
-    for (int r = 0; r < RW; ++r) hi[r] = 0;
-    for (int c = lane; c < p_pad; c += 32) {
-      int sl[G];
+      for (int e = 0; e < NB; ++e) hi = max(hi, abs_hi(v[e]));
+      if (want_f) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) sl[g] = __ldg(sorted_slot + (size_t)c * G + g);
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        double v = tbase[r * stride + sl[0]];
-#pragma unroll
-        for (int g = 1; g < G; ++g) v *= tbase[r * stride + sl[g]];
-        hi[r] = max(hi[r], abs_hi(v));
+        for (int e = 0; e < NB; ++e) f = fma(v[e], __ldg(bvec + c0 + e), f);
       }
-    }
+    });
+    s_hi[quarter * kBuildRows + r_blk] = hi;
+    __syncthreads();
+    int mh = 0;
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
-      const int mh = __reduce_max_sync(0xffffffffu, hi[r]);
-      const int e = exp_from_hi(mh);
-      if (lane == 0) {
-        exps[row0 + r] = e;
-        if (mh >= 0x7ff00000) atomicExch(err, 4);   // Inf / NaN in the row
-      }
-      scale[r] = digit_scale(sd, e);
+    for (int q = 0; q < 4; ++q) mh = max(mh, s_hi[q * kBuildRows + r_blk]);
+    const int e = exp_from_hi(mh);
+    if (quarter == 0) {
+      exps[grow] = e;
+      if (mh >= 0x7ff00000) atomicExch(err, 4);                       // Inf / NaN in the row
     }
+    scale = digit_scale(sd, e);
   }
-  for (int c = lane; c < p_pad; c += 32) {
-    int sl[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) sl[g] = __ldg(sorted_slot + (size_t)c * G + g);
-    double v[RW];
-#pragma unroll
-    for (int r = 0; r < RW; ++r) v[r] = tbase[r * stride + sl[0]];
-#pragma unroll
-    for (int g = 1; g < G; ++g)
-#pragma unroll
-      for (int r = 0; r < RW; ++r) v[r] *= tbase[r * stride + sl[g]];
+  walk_sorted_columns<G, NB>(trow, pack, c_begin, c_end, [&](int c0, const double (&v)[NB]) {
     if constexpr (!DIG) {
+      if (want_f) {
 #pragma unroll
-      for (int r = 0; r < RW; ++r) out[(row0 + r) * ldo + c] = v[r];
+        for (int e = 0; e < NB; ++e) f = fma(v[e], __ldg(bvec + c0 + e), f);
+      }
+      double2* dst = reinterpret_cast<double2*>(out + grow * ldo + c0);
+#pragma unroll
+      for (int e = 0; e < NB; e += 2) dst[e >> 1] = make_double2(v[e], v[e + 1]);
     } else {
+      unsigned long long w[NB];
 #pragma unroll
-      for (int r = 0; r < RW; ++r) store_digits(v[r], scale[r], sd, planes + (row0 + r) * (size_t)p_pad + c, plane_stride);
+      for (int e = 0; e < NB; ++e) w[e] = digit_word(v[e], scale, sd);
+      int8_t* base = planes + grow * (size_t)p_pad + c0;
+#define GRIEF_PLANE(S_, B_)                                                                                                        \
+  do {                                                                                                                             \
+    uint4 q4;                                                                                                                      \
+    { const unsigned long long t4[4] = {w[0], w[1], w[2], w[3]}; q4.x = gather_byte<B_>(t4); }                                    \
+    { const unsigned long long t4[4] = {w[4], w[5], w[6], w[7]}; q4.y = gather_byte<B_>(t4); }                                    \
+    { const unsigned long long t4[4] = {w[8], w[9], w[10], w[11]}; q4.z = gather_byte<B_>(t4); }                                  \
+    { const unsigned long long t4[4] = {w[12], w[13], w[14], w[15]}; q4.w = gather_byte<B_>(t4); }                                \
+    *reinterpret_cast<uint4*>(base + (size_t)(S_) * plane_stride) = q4;                                                           \
+  } while (0)
+      GRIEF_PLANE(0, 6);
+      GRIEF_PLANE(1, 5);
+      GRIEF_PLANE(2, 4);
+      if (sd > 3) GRIEF_PLANE(3, 3);
+      if (sd > 4) GRIEF_PLANE(4, 2);
+      if (sd > 5) GRIEF_PLANE(5, 1);
+      if (sd > 6) GRIEF_PLANE(6, 0);
+#undef GRIEF_PLANE
+    }
+  });
+  if (want_f) {                                                       // warp-uniform
+    s_f[quarter * kBuildRows + r_blk] = f;
+    __syncthreads();
+    if (quarter == 0) {
+      const double ft = ((s_f[r_blk] + s_f[kBuildRows + r_blk]) + s_f[2 * kBuildRows + r_blk]) + s_f[3 * kBuildRows + r_blk];
+      a_out[grow] = (int64_t)grow < y_rows ? (y[grow] - ft) * inv_noise : 0.0;
     }
   }
 }
@@ -296,12 +398,13 @@ struct BuildArgs {
   double* out = nullptr; int64_t ld = 0;     // FP64 slab; ld also = bytes per plane row of the transposed digits
   int* exps = nullptr;                       // read (transposed digits) or written (row-major digits)
   int8_t* planes = nullptr; size_t plane_stride = 0;
-  const double* y = nullptr; int64_t y_rows = 0; double* r_ws = nullptr;   // transposed only: fused Phi^T y partials
+  const double* y = nullptr; int64_t y_rows = 0; double* r_ws = nullptr;   // transposed: fused Phi^T y partials (y, y_rows, r_ws)
+  const double* bvec = nullptr; double inv_noise = 0.0; double* a_out = nullptr;   // row-major: a = (y - Phi bvec) * inv_noise (y, y_rows too)
 };
 
 template <int G>
 static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
-  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double);
+  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double) + (a.transposed ? 0 : 4 * kBuildRows * (sizeof(double) + sizeof(int)));
   const unsigned grid = (unsigned)(rows / kBuildRows);
   GRIEF_REQUIRE(smem <= 227 * 1024, "build_phi: %zu bytes of shared memory", smem);
 #define GRIEF_BT(DIG_)                                                                                                              \
@@ -313,8 +416,9 @@ static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const B
 #define GRIEF_BN(DIG_)                                                                                                              \
   do {                                                                                                                              \
     GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, DIG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-    k_build_phi<G, DIG_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->p_pad, a.out, a.ld, a.exps,   \
-                                                               a.planes, a.plane_stride, a.sd, pl->d_err);                          \
+    k_build_phi<G, DIG_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_pack, pl->p_pad, a.out, a.ld, a.exps,   \
+                                                               a.planes, a.plane_stride, a.sd, pl->d_err, a.bvec, a.y, a.y_rows,    \
+                                                               a.inv_noise, a.a_out);                                               \
   } while (0)
   if (a.transposed) {
     if (a.digits) GRIEF_BT(true); else GRIEF_BT(false);
@@ -551,16 +655,20 @@ int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_
 }
 
 // Zt (p_pad x ldz, TRANSPOSED: sorted column c of Z = Phi(slab) * B is row c of Zt, the slab's data rows are contiguous) -- the
-// layout its consumers (k_contract_rows, k_rowdot_t: lane = data row) read with full coalescing.  B symmetric, given as Bperm
+// layout its consumers (k_contract_back, k_rowdot_t: lane = data row) read with full coalescing.  B symmetric, given as Bperm
 // (p_pad x p_pad, launch_permute_b).  scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
+struct ResidualArgs {      // optional by-product of the slab builder: a = (y - Phi bvec) / noise_var for the slab's rows
+  const double* bvec = nullptr; const double* y = nullptr; int64_t y_rows = 0; double inv_noise = 0.0; double* a_out = nullptr;
+};
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Zt,
-                 int64_t ldz, int digits, cudaStream_t stream, int* launches) {
+                 int64_t ldz, int digits, const ResidualArgs* res, cudaStream_t stream, int* launches) {
   GRIEF_REQUIRE(slab_rows % kBuildRows == 0, "zgemm: slab_rows=%lld is not a multiple of %d", (long long)slab_rows, kBuildRows);
   GRIEF_REQUIRE(ldz >= slab_rows, "zgemm: ldz=%lld must be >= slab_rows=%lld", (long long)ldz, (long long)slab_rows);
   if (slab_rows == 0) return GRIEF_OK;
   const bool i8 = pl->opts.gemm_mode == 1;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
   BuildArgs ba;
+  if (res) { ba.bvec = res->bvec; ba.y = res->y; ba.y_rows = res->y_rows; ba.inv_noise = res->inv_noise; ba.a_out = res->a_out; }
   if (i8) {      // row exponents + digit planes [sd][slab_rows][p_pad] straight from the tables
     ba.digits = true; ba.sd = digits; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
   } else {

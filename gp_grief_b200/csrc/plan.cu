@@ -66,18 +66,7 @@ void prof_read(double* ms, int* count) {
 
 Plan::~Plan() {
   if (grad) grad_desc_destroy(grad);
-  cudaFree(d_dims);
-  cudaFree(d_grid);
-  cudaFree(d_qs);
-  cudaFree(d_slot_k);
-  cudaFree(d_slot_group);
-  cudaFree(d_group_begin);
-  cudaFree(d_col_slot);
-  cudaFree(d_sorted_slot);
-  cudaFree(d_sorted_level);
-  cudaFree(d_sorted_gslot);
-  cudaFree(d_perm);
-  cudaFree(d_err);
+  cudaFree(d_pool);          // every d_* array of the plan lives in this one allocation
 }
 
 static inline uint64_t mix64(uint64_t h, uint64_t v) {
@@ -87,13 +76,27 @@ static inline uint64_t mix64(uint64_t h, uint64_t v) {
   return h;
 }
 
-template <typename T>
-static int upload(T** dst, const std::vector<T>& src) {
-  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
-  GRIEF_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
-  if (!src.empty()) GRIEF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return GRIEF_OK;
-}
+// All device arrays of a plan are carved out of ONE allocation and filled by ONE host-to-device copy: a plan is rebuilt at every
+// new hyper-parameter value, and a dozen cudaMalloc + cudaMemcpy pairs cost ~6 ms of serial time per evaluation on every rank.
+struct PoolBuilder {
+  std::vector<unsigned char> host;
+  struct Fix { void** dst; size_t off; };
+  std::vector<Fix> fixes;
+  template <typename T>
+  void add(T** dst, const std::vector<T>& src) {
+    const size_t off = (host.size() + 255) / 256 * 256;
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    host.resize(off + bytes, 0);
+    if (!src.empty()) std::memcpy(host.data() + off, src.data(), src.size() * sizeof(T));
+    fixes.push_back({reinterpret_cast<void**>(dst), off});
+  }
+  int commit(void** pool) {
+    GRIEF_CUDA(cudaMalloc(pool, std::max<size_t>(host.size(), 256)));
+    GRIEF_CUDA(cudaMemcpy(*pool, host.data(), host.size(), cudaMemcpyHostToDevice));
+    for (auto& f : fixes) *f.dst = static_cast<unsigned char*>(*pool) + f.off;
+    return GRIEF_OK;
+  }
+};
 
 int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, const double* variance,
                 const double* lengthscale, const double* grid_concat, const int32_t* u,
@@ -272,22 +275,34 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
       sorted_level[c] = (uint8_t)lv;
     }
   }
+  // packed form for the lane = row kernels: word w of sorted column c holds the slots of key positions 4w .. 4w+3, most significant
+  // byte first (a slot index is < 256: kTableCap); the first differing key position of two consecutive columns is then a
+  // count-leading-zeros of the XOR of their words
+  static_assert(kTableCap + 20 < 256, "slot indices must fit one byte");
+  pl->pack_words = (G + 3) / 4;
+  std::vector<uint32_t> sorted_pack((size_t)pl->p_pad * pl->pack_words, 0);
+  for (int c = 0; c < pl->p_pad; ++c)
+    for (int k = 0; k < G; ++k)
+      sorted_pack[(size_t)c * pl->pack_words + k / 4] |= (uint32_t)(sorted_slot[(size_t)c * G + k] & 0xFF) << (8 * (3 - k % 4));
 
   // ---- upload ----
   std::vector<double> grid(grid_concat, grid_concat + pl->sum_m);
   std::vector<double> qs(qs_concat, qs_concat + qoff);
-  int rc = upload(&pl->d_dims, pl->dims);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_grid, grid);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_qs, qs);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_slot_k, slot_k);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_slot_group, slot_group);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_group_begin, pl->group_begin);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_col_slot, pl->col_slot_h);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_slot, sorted_slot);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_level, sorted_level);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_sorted_gslot, sorted_gslot);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_perm, pl->perm_h);
-  if (rc == GRIEF_OK) rc = upload(&pl->d_err, std::vector<int>(1, 0));
+  PoolBuilder pool;
+  pool.add(&pl->d_dims, pl->dims);
+  pool.add(&pl->d_grid, grid);
+  pool.add(&pl->d_qs, qs);
+  pool.add(&pl->d_slot_k, slot_k);
+  pool.add(&pl->d_slot_group, slot_group);
+  pool.add(&pl->d_group_begin, pl->group_begin);
+  pool.add(&pl->d_col_slot, pl->col_slot_h);
+  pool.add(&pl->d_sorted_slot, sorted_slot);
+  pool.add(&pl->d_sorted_level, sorted_level);
+  pool.add(&pl->d_sorted_gslot, sorted_gslot);
+  pool.add(&pl->d_sorted_pack, sorted_pack);
+  pool.add(&pl->d_perm, pl->perm_h);
+  pool.add(&pl->d_err, std::vector<int>(1, 0));
+  int rc = pool.commit(&pl->d_pool);
   if (rc != GRIEF_OK) {
     delete pl;
     return rc;

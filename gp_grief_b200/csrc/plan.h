@@ -59,7 +59,8 @@ struct Plan {
   std::vector<int> group_slot0;         // first table slot of each group
   std::vector<int> group_size;          // distinct sub-tuples per group
   std::vector<uint16_t> col_slot_h;     // p_pad x G slot index per column and group
-  // ---- device buffers (owned) ----
+  // ---- device buffers (all carved out of d_pool) ----
+  void* d_pool = nullptr;
   DimDesc* d_dims = nullptr;
   double* d_grid = nullptr;             // concatenated grids
   double* d_qs = nullptr;               // concatenated m_i x u_i scaled eigenvectors (row-major [g][k])
@@ -72,6 +73,8 @@ struct Plan {
   uint16_t* d_sorted_slot = nullptr;    // p_pad x G: slots of sorted column c, listed in key order
   uint8_t* d_sorted_level = nullptr;    // p_pad: first key position where sorted column c differs from c-1 (G: identical)
   uint16_t* d_sorted_gslot = nullptr;   // p_pad x G: slots of sorted column c in GROUP order (consumers of Z, which is in sorted order)
+  uint32_t* d_sorted_pack = nullptr;    // p_pad x pack_words: the key-order slots of sorted column c, one byte each, 4 per word (MSB first)
+  int pack_words = 1;                   // (G + 3) / 4
   int* d_perm = nullptr;                // p_pad: external column of sorted column c (-1 for padding columns)
   std::vector<int> perm_h;
   int device = 0;

@@ -325,6 +325,42 @@ def sumsq(y_dev):
     return out
 
 
+class NativeComm(object):
+    """grief_comm: the library's own NCCL communicator (one rank per process / GPU), for hosts without torch.distributed.
+    `NativeComm.unique_id()` on rank 0 gives the 128 bytes every rank passes to the constructor."""
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        nat.check(nat.lib().grief_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, unique_id, world_size, rank):
+        _torch()
+        assert len(unique_id) == 128
+        h = ctypes.c_void_p()
+        nat.check(nat.lib().grief_comm_create(ctypes.byref(h), ctypes.c_char_p(unique_id), int(world_size), int(rank)))
+        self._h, self.world_size, self.rank = h, int(world_size), int(rank)
+
+    def all_reduce(self, t):
+        """In-place sum over ranks of a contiguous float64 CUDA tensor, on the current stream."""
+        torch = _torch()
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        nat.check(nat.lib().grief_comm_allreduce_sum(self._h, nat.dev_ptr(t), t.numel(), nat.stream_ptr()))
+        return t
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().grief_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceSolver(object):
     """grief_ctx: the p x p stage (Cholesky, solve, LML, w / noise gradients, pass-2 operand)."""
 

@@ -160,16 +160,100 @@ class GPGriefModel(BaseModel):
     #: 8 D - 2 bits per operand below its row maximum.
     gemm_digits = None
 
+    #: A-posteriori audit of the INT8 digit counts (first evaluation of a model, and again after `reset_audit()`): the two O(n p^2)
+    #: products are recomputed on `audit_rows` rows in the FP64 DMMA arithmetic, the difference is pushed through the first-order
+    #: sensitivity of the FULL problem (its P^-1 and b) and extrapolated linearly to all rows -- the worst case of a systematic
+    #: truncation bias, random errors only grow like sqrt(n).  If the estimated relative effect on the LML (or on the largest
+    #: gradient component) exceeds `audit_tol`, the digit count of that product is raised and the product recomputed.  The result
+    #: is kept in `arithmetic_audit`.  audit_rows = 0 switches the audit off.
+    audit_rows = 16384
+    audit_tol = 1e-10
+    arithmetic_audit = None
+
+    def reset_audit(self):
+        """Audit the arithmetic again at the next evaluation (e.g. after moving far in hyper-parameter space)."""
+        self._audit_done = {}
+
     def _plan(self):
         """The kernel's device plan with this model's arithmetic options applied."""
         from .. import _native as nat
         plan = self.kern.device_plan()
-        if self.gemm_digits is not None:
-            plan.set_option(nat.OPT_DIGITS_GRAM, self.gemm_digits[0])
-            plan.set_option(nat.OPT_DIGITS_Z, self.gemm_digits[1])
-            if len(self.gemm_digits) > 2:
-                plan.set_option(nat.OPT_DIGITS_VAR, self.gemm_digits[2])
+        digits = self.__dict__.get('_audited_digits') or self.gemm_digits
+        if digits is not None:
+            plan.set_option(nat.OPT_DIGITS_GRAM, digits[0])
+            plan.set_option(nat.OPT_DIGITS_Z, digits[1])
+            if len(digits) > 2:
+                plan.set_option(nat.OPT_DIGITS_VAR, digits[2])
         return plan
+
+    # ------------------------------------------------------------------ a-posteriori audit of the INT8 arithmetic
+    def _audit_pending(self, what):
+        from .. import _native as nat
+        if not self.audit_rows or self.__dict__.setdefault('_audit_done', {}).get(what):
+            return False
+        return (self._plan().get_option(nat.OPT_GEMM_MODE) & 1) == 1
+
+    def _audit_max_over_ranks(self, value):
+        if self._dist is None:
+            return float(value)
+        t = self._torch.tensor([float(value)], dtype=self._torch.float64, device="cuda")
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def _raise_digits(self, which):
+        """One more digit for product `which` (0 Gram, 1 gradient pass); False when it is already at the DGEMM class."""
+        from .. import _native as nat
+        plan = self._plan()
+        cur = [plan.get_option(nat.OPT_DIGITS_GRAM), plan.get_option(nat.OPT_DIGITS_Z), plan.get_option(nat.OPT_DIGITS_VAR)]
+        if cur[which] >= 7:
+            return False
+        cur[which] += 1
+        self._audited_digits = tuple(cur)
+        return True
+
+    def _audit_gram(self, solve_out):
+        """Estimated relative LML error caused by the digit truncation of A = Phi^T Phi.
+        d LML = -1/2 [ tr(P^-1 dA) + b^T dA b / noise_var ] with dA measured on the audit rows (INT8 digits vs FP64 DMMA)."""
+        from .. import _native as nat
+        t = self._torch
+        plan = self._plan()
+        ns = int(min(self.num_local, self.audit_rows))
+        est = 0.0
+        if ns > 0:
+            T = self._dev['tables']
+            A8 = plan.gram(T, ns)
+            mode = plan.get_option(nat.OPT_GEMM_MODE)
+            plan.set_option(nat.OPT_GEMM_MODE, 0)
+            try:
+                A64 = plan.gram(T, ns)
+            finally:
+                plan.set_option(nat.OPT_GEMM_MODE, mode)
+            dA = A8 - A64
+            b = solve_out['b']
+            d_lml = -0.5 * ((solve_out['Pinv'] * dA).sum() + (dA * t.outer(b, b)).sum() / float(self.noise_var))
+            est = abs(float(d_lml)) * (self.num_local / float(ns))
+        est = self._audit_max_over_ranks(est) * (1 if self._dist is None else self._dist.get_world_size())
+        return est / max(abs(float(solve_out['lml'])), 1e-300), ns
+
+    def _audit_grad(self, solve_out, g_full):
+        """Estimated error of the kernel-parameter gradient caused by the digit truncation of Zp = Phi P^-1, relative to the
+        largest gradient component: pass 2 on the audit rows in both arithmetics, difference extrapolated linearly."""
+        from .. import _native as nat
+        plan = self._plan()
+        ns = int(min(self.num_local, self.audit_rows))
+        est = 0.0
+        if ns > 0:
+            args = (self._dev['tables'], self._X_dev, self._y_dev, ns, solve_out['Pinv'], solve_out['b'], float(self.noise_var))
+            g8 = plan.grad_theta(*args)
+            mode = plan.get_option(nat.OPT_GEMM_MODE)
+            plan.set_option(nat.OPT_GEMM_MODE, 0)
+            try:
+                g64 = plan.grad_theta(*args)
+            finally:
+                plan.set_option(nat.OPT_GEMM_MODE, mode)
+            est = float((g8 - g64).abs().max()) * (self.num_local / float(ns))
+        est = self._audit_max_over_ranks(est) * (1 if self._dist is None else self._dist.get_world_size())
+        return est / max(float(np.abs(g_full).max()), 1e-300), ns
 
     def _stats(self):
         """A = Phi^T Phi, r = Phi^T y, s = y^T y on the device (all-reduced over ranks), cached like `_A`."""
@@ -206,10 +290,28 @@ class GPGriefModel(BaseModel):
                 (have['G2'] is not None or not want_G2):
             return have
         self._w = self.kern.w
-        st = self._stats()
-        w_dev = self._torch.as_tensor(np.ascontiguousarray(self._w, dtype=np.float64)).cuda()
-        out = self._solver.solve(st['A'], st['r'], st['s'], w_dev, float(self.noise_var), self.num_data,
-                                 want_grad=want_grad or want_G2, want_G2=want_G2)
+        from .. import _native as nat
+        while True:
+            audit = self._audit_pending('gram')
+            st = self._stats()
+            w_dev = self._torch.as_tensor(np.ascontiguousarray(self._w, dtype=np.float64)).cuda()
+            out = self._solver.solve(st['A'], st['r'], st['s'], w_dev, float(self.noise_var), self.num_data,
+                                     want_grad=want_grad or want_G2 or audit, want_G2=want_G2)
+            if not audit:
+                break
+            rel, ns = self._audit_gram(out)
+            digits = self._plan().get_option(nat.OPT_DIGITS_GRAM)
+            rec = dict(self.arithmetic_audit or {})
+            rec['gram'] = {"digits": digits, "rows": ns, "estimated_lml_rel_error": rel, "tol": float(self.audit_tol)}
+            self.arithmetic_audit = rec
+            if rel <= self.audit_tol or not self._raise_digits(0):
+                self._audit_done['gram'] = True
+                break
+            logger.warning("INT8 Gram with %d digits: estimated relative LML error %.2e > %.1e on %d audit rows; recomputing with %d digits",
+                           digits, rel, self.audit_tol, ns, digits + 1)
+            for k in ('stats', 'plan_id'):          # the tables stay valid: only the product is redone
+                dev.pop(k, None)
+            self._host.pop('_A', None)
         dev['solve'] = out
         for k in ('_P', '_Pchol', '_alpha', '_alpha_p'):
             self._host.pop(k, None)
@@ -267,14 +369,29 @@ class GPGriefModel(BaseModel):
     def _theta_gradient(self, active, solve_out):
         """d LML / d theta for the active base-kernel parameters [(dim, kind)] (pass 2 on the device)."""
         t = self._torch
+        from .. import _native as nat
         plan = self._plan()
         dqs = self.kern.scaled_eigvec_derivatives(active)
         plan.grad_setup([a[0] for a in active], [0 if a[1] == 'variance' else 1 for a in active], dqs)
-        g = plan.grad_theta(self._dev['tables'], self._X_dev, self._y_dev, self.num_local, solve_out['Pinv'],
-                            solve_out['b'], float(self.noise_var))
-        if self._dist is not None:
-            self._dist.all_reduce(g)
-        return g.cpu().numpy()
+        while True:
+            g = plan.grad_theta(self._dev['tables'], self._X_dev, self._y_dev, self.num_local, solve_out['Pinv'],
+                                solve_out['b'], float(self.noise_var))
+            if self._dist is not None:
+                self._dist.all_reduce(g)
+            g = g.cpu().numpy()
+            if not self._audit_pending('grad') or len(active) == 0:
+                return g
+            rel, ns = self._audit_grad(solve_out, g)
+            digits = plan.get_option(nat.OPT_DIGITS_Z)
+            rec = dict(self.arithmetic_audit or {})
+            rec['grad'] = {"digits": digits, "rows": ns, "estimated_grad_error_over_max_abs": rel, "tol": float(self.audit_tol)}
+            self.arithmetic_audit = rec
+            if rel <= self.audit_tol or not self._raise_digits(1):
+                self._audit_done['grad'] = True
+                return g
+            logger.warning("INT8 gradient pass with %d digits: estimated gradient error %.2e of the largest component > %.1e on %d audit "
+                           "rows; recomputing with %d digits", digits, rel, self.audit_tol, ns, digits + 1)
+            plan = self._plan()
 
     # ------------------------------------------------------------------ prediction
     def predict_precompute(self, Xnew):

@@ -34,6 +34,7 @@ extern "C" {
 #define GRIEF_ERR_NOT_PD 3       /* -> numpy.linalg.LinAlgError (what scipy cho_factor raises)   */
 #define GRIEF_ERR_UNSUPPORTED 4  /* -> NotImplementedError                                      */
 #define GRIEF_ERR_LIBRARY 5      /* -> RuntimeError (driver entry point missing)                */
+#define GRIEF_ERR_NCCL 6         /* -> RuntimeError (NCCL not loadable, or a failed collective)  */
 
 #define GRIEF_KERN_RBF 0         /* kern/stationary.py:108-134 */
 #define GRIEF_KERN_EXPONENTIAL 1 /* kern/stationary.py:161-175 */
@@ -267,6 +268,21 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
 size_t grief_quadform_workspace_bytes(const grief_plan* plan, int64_t n);
 int grief_quadform_rows(const grief_plan* plan, const double* T_dev, int64_t n, const double* B_dev, int64_t ldb,
                         double* q_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * Row-shard exchange for hosts without torch.distributed (rows of X shard over the GPUs of one box, one process per
+ * GPU; only the packed statistics (A | r | s) -- one contiguous buffer, p^2 + p + 1 doubles -- and the kernel-parameter gradient are
+ * all-reduced).  NCCL is loaded with dlopen at the first call: the library has no link-time dependency on it.  The Python layer
+ * uses the caller's torch.distributed process group instead (gp_grief_b200/models/gp_grief_model.py: distributed=True).
+ *   grief_comm_unique_id      rank 0: 128 bytes to hand to every rank (file, socket, MPI_Bcast, ...)      [ncclGetUniqueId]
+ *   grief_comm_create         every rank, with its CUDA device current                                   [ncclCommInitRank]
+ *   grief_comm_allreduce_sum  in place, FP64, on the caller's stream; a no-op for world_size 1           [ncclAllReduce]
+ */
+typedef struct grief_comm grief_comm;
+int grief_comm_unique_id(char* id_out128);
+int grief_comm_create(grief_comm** comm, const char* id128, int world_size, int rank);
+int grief_comm_allreduce_sum(grief_comm* comm, double* buf_dev, int64_t count, void* stream);
+void grief_comm_destroy(grief_comm* comm);
 
 /*
  * Row- and column-partitioned Khatri-Rao mat-vec, RowColKhatriRaoMatrix.__mul__ (tensors/khatri_rao_matrix.py:156-167, with get_rows

@@ -194,3 +194,40 @@ def test_empty_row_shard_evaluates_to_the_prior_terms():
     out = model._cov_setup(want_grad=True)
     g = model._theta_gradient([(0, 'lengthscale'), (1, 'variance')], out)
     assert_array_equal(g, np.zeros(2))
+
+
+def test_arithmetic_audit_accepts_the_defaults_and_escalates_when_asked(caplog):
+    """GPGriefModel audits the INT8 digit counts a posteriori against the FP64 arithmetic on a row sample (first evaluation):
+    the defaults pass with a wide margin; an impossible tolerance drives both products to 7 digits (DGEMM class) with a warning,
+    and the results still match the reference."""
+    g = load_golden("syn_t2_n2000_d4_m8_p64")
+    m = ta.build_model(g)
+    ll, grad = m.log_likelihood(return_gradient=True)
+    au = m.arithmetic_audit
+    assert au["gram"]["digits"] == 6 and au["grad"]["digits"] == 4 and au["gram"]["rows"] == 2000
+    assert au["gram"]["estimated_lml_rel_error"] < 1e-12 and au["grad"]["estimated_grad_error_over_max_abs"] < 1e-10
+    assert_allclose(float(np.asarray(ll).squeeze()), float(g["lml"]), rtol=1e-9)
+    # second evaluation at new parameters: no second audit
+    prm = m.parameters.copy()
+    prm[2] *= 1.01
+    m.parameters = prm
+    m.arithmetic_audit = None
+    m.log_likelihood(return_gradient=True)
+    assert m.arithmetic_audit is None
+    # impossible tolerance: escalate to 7 digits
+    m2 = ta.build_model(g)
+    m2.audit_tol = 1e-300
+    with caplog.at_level(logging.WARNING):
+        ll2, grad2 = m2.log_likelihood(return_gradient=True)
+    assert "recomputing with 7 digits" in caplog.text
+    plan = m2._plan()
+    assert plan.get_option(nat.OPT_DIGITS_GRAM) == 7 and plan.get_option(nat.OPT_DIGITS_Z) == 7
+    assert m2.arithmetic_audit["gram"]["digits"] == 7 and m2.arithmetic_audit["grad"]["digits"] == 7
+    assert_allclose(float(np.asarray(ll2).squeeze()), float(g["lml"]), rtol=1e-9)
+    ok = ~np.isnan(grad)
+    assert_allclose(grad2[ok], grad[ok], rtol=0, atol=1e-9 * np.abs(grad[ok]).max())
+    # the audit can be switched off, and is skipped in the FP64 arithmetic
+    m3 = ta.build_model(g)
+    m3.audit_rows = 0
+    m3.log_likelihood(return_gradient=True)
+    assert m3.arithmetic_audit is None
