@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--gemm", default="int8", choices=["int8", "int8x2", "fp64"],
                     help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores or the FP64 DMMA GEMM")
     ap.add_argument("--digits", default="", help="'Dgram,Dz': int8 digits per operand of the two products (default: library defaults)")
+    ap.add_argument("--slab-mb", type=int, default=0, help="HBM budget (MiB) of the Phi^T slab staged per pass-1 GEMM launch (0: library default 4096)")
     ap.add_argument("--power-trace", default="", help="write the clock / power samples of the timed region to this JSON file")
     return ap.parse_args()
 
@@ -300,6 +301,8 @@ def run_ours(args):
         dg, dz = [int(t) for t in args.digits.split(",")]
         nat.check(lib.grief_set_default_option(nat.OPT_DIGITS_GRAM, dg))
         nat.check(lib.grief_set_default_option(nat.OPT_DIGITS_Z, dz))
+    if args.slab_mb:
+        nat.check(lib.grief_set_default_option(nat.OPT_SLAB_BUDGET, args.slab_mb << 20))
     dg, dz = int(lib.grief_get_default_option(nat.OPT_DIGITS_GRAM)), int(lib.grief_get_default_option(nat.OPT_DIGITS_Z))
     pairs = lambda D, sym=False: D * (D + 1) // 2 + (1 if (sym and D % 2 == 0) else 0)     # int8 digit GEMMs per FP64 GEMM
 
@@ -419,9 +422,12 @@ def run_ours(args):
                 setattr(model, name, None)
             l64, g64 = model.log_likelihood(return_gradient=True)
             nat.check(lib.grief_set_default_option(nat.OPT_GEMM_MODE, mode_id))
+            g64 = np.asarray(g64, dtype=float)
             check["int8_vs_fp64_full_n"] = {"rows": n_total, "step": last_step, "digits": [dg, dz], "lml_int8_tensor": lml_val, "lml_fp64_dmma": as_f(l64),
                                             "lml_rel_diff": abs(lml_val - as_f(l64)) / abs(as_f(l64)),
-                                            "grad_max_abs_diff_over_max_abs": grad_diff(grad, np.asarray(g64, dtype=float))}
+                                            "grad_max_abs_diff_over_max_abs": grad_diff(grad, g64)}
+            if type2:      # the kernel-parameter block alone (the noise component is ~100x larger and comes from the p x p stage)
+                check["int8_vs_fp64_full_n"]["grad_theta_max_abs_diff_over_max_abs_theta"] = grad_diff(grad[1:1 + 2 * d], g64[1:1 + 2 * d])
         del model
         torch.cuda.empty_cache()
         # (b) N GPUs against 1 GPU on a row sample (every rank evaluates its shard of the sample; rank 0 also evaluates all of it)

@@ -48,11 +48,11 @@ SIGNATURES = {
     "grief_sumsq": (c_int, [c_void, c_i64, c_void, c_void, c_void]),
     "grief_grad_setup": (c_int, [c_void, c_int, c_void, c_void, c_void]),
     "grief_grad_workspace_bytes": (c_size, [c_void, c_i64]),
-    "grief_grad_theta": (c_int, [c_void, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void, c_dbl, c_void,
+    "grief_grad_theta": (c_int, [c_void, c_void, c_void, c_i64, c_void, c_i64, c_void, c_i64, c_void, c_dbl, c_void, c_void,
                                  c_void, c_size, c_void]),
     "grief_quadform_workspace_bytes": (c_size, [c_void, c_i64]),
     "grief_quadform_rows": (c_int, [c_void, c_void, c_i64, c_void, c_i64, c_void, c_void, c_size, c_void]),
-    "grief_gram_ry": (c_int, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_size, c_void]),
+    "grief_gram_ry": (c_int, [c_void, c_void, c_i64, c_void, c_void, c_i64, c_void, c_void, c_void, c_size, c_void]),
     "grief_set_default_option": (c_int, [c_int, c_i64]),
     "grief_get_default_option": (c_i64, [c_int]),
     "grief_plan_set_option": (c_int, [c_void, c_int, c_i64]),

@@ -20,7 +20,7 @@ int launch_phi_vec(const Plan* pl, const double* T, int64_t n, const double* v, 
 int launch_sumsq(const double* y, int64_t n, double* out, double* ws, cudaStream_t stream);
 size_t gram_workspace_bytes(const Plan* pl, int64_t n_pad, int sms);
 int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, const double* y, int64_t n, double* r,
-                void* workspace, size_t ws_bytes, int sms, cudaStream_t stream, int* launches);
+                int* rowmax_out, void* workspace, size_t ws_bytes, int sms, cudaStream_t stream, int* launches);
 int launch_topk(int d, const int32_t* m_host, const double* raw0_host, const double* logeig_host, int p, int32_t* idx_dev,
                 double* loglam_dev, int* n_out_host, cudaStream_t stream, int* launches);
 
@@ -29,8 +29,10 @@ int grad_desc_n_active(const GradDesc* gd);
 int contract_acc_len(const Plan* pl);
 int contract_total_warps(const Plan* pl, int sms);
 size_t contract_w_doubles(const Plan* pl, int64_t rows);
+size_t kf_doubles(const Plan* pl, int64_t rows);
 int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* a,
-                    const double* bvec, int64_t rows_blk, int64_t rows_valid, double* Wbuf, double* acc, int sms, cudaStream_t stream);
+                    const double* bvec, int64_t rows_blk, int64_t rows_valid, double* Wbuf, double* KFbuf, double* acc, int sms,
+                    cudaStream_t stream);
 int launch_grad_finish(const Plan* pl, const GradDesc* gd, const double* acc, int sms, double* out, cudaStream_t stream);
 int launch_rowdot(const Plan* pl, const double* Zt, int64_t ldz, const double* T, int64_t rows_blk, int64_t rows_valid, double* out,
                   cudaStream_t stream);
@@ -40,6 +42,7 @@ size_t zgemm_scratch_bytes(const Plan* pl, int64_t slab_rows);
 int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_max, void* scratch, int digits, cudaStream_t stream);
 struct ResidualArgs {      // optional by-product of the slab builder: a = (y - Phi bvec) / noise_var for the slab's rows
   const double* bvec = nullptr; const double* y = nullptr; int64_t y_rows = 0; double inv_noise = 0.0; double* a_out = nullptr;
+  const int* row_hi = nullptr;
 };
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
                  int64_t ldz, int digits, const ResidualArgs* res, cudaStream_t stream, int* launches);
@@ -239,15 +242,15 @@ size_t grief_gram_workspace_bytes(const grief_plan* plan, int64_t n) {
 }
 int grief_gram(const grief_plan* plan, const double* T_dev, int64_t n, double* A_dev, int64_t lda, void* workspace_dev,
                size_t workspace_bytes, void* stream) {
-  return grief_gram_ry(plan, T_dev, n, nullptr, A_dev, lda, nullptr, workspace_dev, workspace_bytes, stream);
+  return grief_gram_ry(plan, T_dev, n, nullptr, A_dev, lda, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
 }
 int grief_gram_ry(const grief_plan* plan, const double* T_dev, int64_t n, const double* y_dev, double* A_dev, int64_t lda, double* r_dev,
-                  void* workspace_dev, size_t workspace_bytes, void* stream) {
+                  int32_t* rowmax_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   GRIEF_REQUIRE(plan && A_dev && workspace_dev && (T_dev || n == 0), "grief_gram: null pointer");
   GRIEF_REQUIRE(r_dev == nullptr || y_dev != nullptr || n == 0, "grief_gram_ry: r needs y");
   GRIEF_REQUIRE(lda >= plan->impl->p, "grief_gram: lda=%lld < p=%d", (long long)lda, plan->impl->p);
   GRIEF_PLAN_DEVICE(plan->impl);
-  int rc = launch_gram(plan->impl, T_dev, grief_table_rows(n), A_dev, lda, y_dev, n, r_dev, workspace_dev, workspace_bytes, sm_count(),
+  int rc = launch_gram(plan->impl, T_dev, grief_table_rows(n), A_dev, lda, y_dev, n, r_dev, rowmax_dev, workspace_dev, workspace_bytes, sm_count(),
                        (cudaStream_t)stream, &g_launches);
   if (rc == GRIEF_OK && plan->impl->opts.gemm_mode == 1) rc = ozaki_check(plan->impl->d_err, (cudaStream_t)stream);
   return rc;
@@ -293,21 +296,23 @@ int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const 
   return grad_desc_create(&pl->grad, pl, n_active, dims, kinds, dqs_concat);
 }
 
-// workspace of grief_grad_theta: [Zp^T slab] [GEMM scratch] [W slab] [a slab] [per-warp accumulators] [b in sorted order] [permuted P^-1]
+// workspace of grief_grad_theta: [Zp^T slab] [GEMM scratch] [W slab] [K_xu | F slab] [a slab] [per-warp accumulators] [b in sorted order]
+// [permuted P^-1]
 size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n) {
   const Plan* pl = plan->impl;
   if (!pl->grad) return 0;
   const int sms = sm_count();
   const int64_t slab = slab_rows_for(n, sms);
   return align256((size_t)slab * pl->p_pad * sizeof(double)) + align256(zgemm_scratch_bytes(pl, slab)) +
-         align256(contract_w_doubles(pl, slab) * sizeof(double)) + align256((size_t)slab * sizeof(double)) +
+         align256(contract_w_doubles(pl, slab) * sizeof(double)) + align256(kf_doubles(pl, slab) * sizeof(double)) +
+         align256((size_t)slab * sizeof(double)) +
          align256((size_t)contract_total_warps(pl, sms) * contract_acc_len(pl) * sizeof(double)) + align256((size_t)pl->p_pad * sizeof(double)) +
          align256((size_t)pl->p_pad * pl->p_pad * sizeof(double));
 }
 
 int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev, int64_t n,
-                     const double* Pinv_dev, int64_t ldp, const double* b_dev, double noise_var, double* grad_dev, void* workspace_dev,
-                     size_t workspace_bytes, void* stream_) {
+                     const double* Pinv_dev, int64_t ldp, const double* b_dev, double noise_var, const int32_t* rowmax_dev, double* grad_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream_) {
   GRIEF_REQUIRE(plan && plan->impl->grad, "grief_grad_theta: call grief_grad_setup first");
   GRIEF_REQUIRE(Pinv_dev && b_dev && grad_dev && workspace_dev && (n == 0 || (T_dev && X_dev && y_dev)), "grief_grad_theta: null pointer");
   GRIEF_REQUIRE(workspace_bytes >= grief_grad_workspace_bytes(plan, n), "grief_grad_theta: workspace too small");
@@ -324,6 +329,7 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
   double* Zt = reinterpret_cast<double*>(q); q += align256((size_t)slab * pl->p_pad * sizeof(double));
   void* zscr = q; q += align256(zgemm_scratch_bytes(pl, slab));
   double* Wbuf = reinterpret_cast<double*>(q); q += align256(contract_w_doubles(pl, slab) * sizeof(double));
+  double* KFbuf = reinterpret_cast<double*>(q); q += align256(kf_doubles(pl, slab) * sizeof(double));
   double* avec = reinterpret_cast<double*>(q); q += align256((size_t)slab * sizeof(double));
   double* acc = reinterpret_cast<double*>(q); q += align256(acc_doubles * sizeof(double));
   double* bvec = reinterpret_cast<double*>(q); q += align256((size_t)pl->p_pad * sizeof(double));
@@ -342,12 +348,13 @@ int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* 
     const int64_t rows_valid = std::max<int64_t>(0, std::min(rows_blk, n - r0));
     ResidualArgs res;                                           // a = (y - Phi b) / noise_var comes out of the slab builder's sweep
     res.bvec = bvec; res.y = y_dev + r0; res.y_rows = rows_valid; res.inv_noise = 1.0 / noise_var; res.a_out = avec;
+    res.row_hi = rowmax_dev ? rowmax_dev + r0 : nullptr;
     rc = launch_zgemm(pl, T_dev + (size_t)r0 * pl->stride, rows_blk, Bperm, zscr, slab, Zt, slab, pl->opts.digits_z, &res, stream, &g_launches);
     if (rc != GRIEF_OK) return rc;
     rc = launch_contract(pl, Zt, slab, T_dev + (size_t)r0 * pl->stride, X_dev + (size_t)r0 * ldx, ldx, avec, bvec, rows_blk, rows_valid, Wbuf,
-                         acc, sms, stream);
+                         KFbuf, acc, sms, stream);
     if (rc != GRIEF_OK) return rc;
-    g_launches += 2;
+    g_launches += 3;
   }
   rc = launch_grad_finish(pl, gd, acc, sms, grad_dev, stream);
   if (rc == GRIEF_OK) g_launches += 1;

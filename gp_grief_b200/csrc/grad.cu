@@ -127,6 +127,28 @@ __device__ __forceinline__ void kern_eval_d(int kernel, double x, double u, doub
   }
 }
 
+// d k / d lengthscale from the kernel VALUE k (the tail kernel reads k from the K_xu buffer instead of evaluating exp again):
+// algebraic identities of the four formulas above
+__device__ __forceinline__ double kern_dls_from_k(int kernel, double k, double x, double u, double ls) {
+  const double diff = x - u;
+  const double d2 = diff * diff;
+  switch (kernel) {
+    case KERN_RBF: return ls < 1e-6 ? 0.0 : k * d2 / (ls * ls * ls);
+    case KERN_EXPONENTIAL: return k * (sqrt(d2) / ls) / ls;
+    case KERN_MATERN32: {
+      const double s3 = 1.7320508075688772;
+      const double r = sqrt(d2) / ls;
+      return k * 3.0 * r * r / ((1.0 + s3 * r) * ls);
+    }
+    default: {
+      const double s5 = 2.23606797749979;
+      const double r2 = d2 / (ls * ls);
+      const double r = sqrt(r2);
+      return k * (5.0 / 3.0) * r2 * (1.0 + s5 * r) / ((1.0 + s5 * r + (5.0 / 3.0) * r2) * ls);
+    }
+  }
+}
+
 // ---- backward sweep (lane = row; all control flow is warp-uniform) ----
 // Sorted column c has its key-order slots packed one byte each in plan->d_sorted_pack ((G + 3) / 4 words, key position k in byte
 // 3 - k % 4 of word k / 4); the first key position where c differs from c - 1 is a count-leading-zeros of the XOR.
@@ -178,24 +200,35 @@ __global__ void __launch_bounds__(128) k_contract_back(const BackParams P) {
     uint32_t prev[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) prev[w] = 0;
+    // everything a batch needs from global memory (Zp^T from HBM; the packed slots and b from L1 / L2) is requested one batch
+    // ahead: with four warps per SM nothing else hides those latencies
     const double* zcol = P.Zt + row;
-    double znext[NB];
+    double znext[NB], bnext[NB];
+    uint32_t wnext[NB][NW];
 #pragma unroll
-    for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)e * P.ldz);
+    for (int e = 0; e < NB; ++e) {
+      znext[e] = __ldcs(zcol + (size_t)e * P.ldz);
+      bnext[e] = __ldg(P.bvec + e);
+#pragma unroll
+      for (int w = 0; w < NW; ++w) wnext[e][w] = __ldg(P.pack + (size_t)e * NW + w);
+    }
     for (int c0 = 0; c0 < P.p_pad; c0 += NB) {
       uint32_t wd[NB][NW];
       double zt[NB];
 #pragma unroll
-      for (int e = 0; e < NB; ++e) zt[e] = znext[e];
+      for (int e = 0; e < NB; ++e) {
+        zt[e] = fma(a_n, bnext[e], -znext[e]);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) wd[e][w] = wnext[e][w];
+      }
       if (c0 + NB < P.p_pad) {
 #pragma unroll
-        for (int e = 0; e < NB; ++e) znext[e] = __ldcs(zcol + (size_t)(c0 + NB + e) * P.ldz);
-      }
+        for (int e = 0; e < NB; ++e) {
+          znext[e] = __ldcs(zcol + (size_t)(c0 + NB + e) * P.ldz);
+          bnext[e] = __ldg(P.bvec + c0 + NB + e);
 #pragma unroll
-      for (int e = 0; e < NB; ++e) {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) wd[e][w] = __ldg(P.pack + (size_t)(c0 + e) * NW + w);
-        zt[e] = fma(a_n, __ldg(P.bvec + c0 + e), -zt[e]);
+          for (int w = 0; w < NW; ++w) wnext[e][w] = __ldg(P.pack + (size_t)(c0 + NB + e) * NW + w);
+        }
       }
 #pragma unroll
       for (int e = 0; e < NB; ++e) {
@@ -253,22 +286,34 @@ __global__ void __launch_bounds__(128) k_contract_back(const BackParams P) {
 // ---- tail: W -> V (per-dimension factors) -> parameter sums ----
 struct TailParams {
   const double* W;                   // [n_rg][stride][32]
+  const double* KF;                  // [n_rg][sum_m + sum_u][32]: K_xu then F of the slab's rows (rows.cu: launch_kf)
   const double* X; int64_t ldx;      // slab rows x ldx
   const DimDesc* dims; const double* grid; const double* qs; const uint8_t* slot_k; const int* slot_group; const int* group_begin;
-  int d, stride, width, sum_u, max_group_dims, m_max;
+  int d, stride, width, sum_m, sum_u, max_group_dims, m_max, n_groups;
   int64_t rows_valid;                // rows of the slab that exist (the rest are zero-padded tables)
   int n_rg;
   double* acc; int acc_len;          // [total warps][acc_len]: M_i (sum m_i u_i doubles, layout of qs) then (gl_i, gv_i) per dimension
 };
 
-// One warp per 32 data rows, lane = row.  Per warp: F [sum_u][32], V [sum_u][32], K [m_max][33] in shared memory.
-__global__ void __launch_bounds__(256) k_contract_tail(const TailParams P) {
+// One warp per 32 data rows, lane = row.  Per warp: V [sum_u][32] and K [m_max][33] in shared memory (4 warps per CTA, as many CTAs
+// per SM as fit); per CTA the small index tables of the plan.  No kernel is evaluated here: K_xu and F come from the KF buffer
+// (written by the table kernel at full occupancy; F is read in place, it stays in L1), d k / d lengthscale follows from k algebraically.
+__global__ void __launch_bounds__(128) k_contract_tail(const TailParams P) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int per_warp = 64 * P.sum_u + 33 * P.m_max;
-  double* sF = sm + (size_t)warp * per_warp;     // [sum_u][32]
-  double* sV = sF + (size_t)P.sum_u * 32;        // [sum_u][32]
+  const int per_warp = 32 * P.sum_u + 33 * P.m_max;
+  double* sV = sm + (size_t)warp * per_warp;     // [sum_u][32]
   double* sK = sV + (size_t)P.sum_u * 32;        // [m_max][33]
+  // CTA-wide copies of the index tables: f_off per dimension, group of a slot, group boundaries, per-slot factor indices
+  int* s_foff = reinterpret_cast<int*>(sm + (size_t)nw * per_warp);             // [d]
+  int* s_sgrp = s_foff + P.d;                                                    // [width]
+  int* s_gbeg = s_sgrp + P.width;                                                // [groups + 1] (<= kMaxGroups + 1)
+  uint8_t* s_slotk = reinterpret_cast<uint8_t*>(s_gbeg + kMaxGroups + 1);        // [width][max_group_dims]
+  for (int i = threadIdx.x; i < P.d; i += blockDim.x) s_foff[i] = P.dims[i].f_off;
+  for (int s = threadIdx.x; s < P.width; s += blockDim.x) s_sgrp[s] = P.slot_group[s];
+  for (int g = threadIdx.x; g <= P.n_groups; g += blockDim.x) s_gbeg[g] = P.group_begin[g];
+  for (int e = threadIdx.x; e < P.width * P.max_group_dims; e += blockDim.x) s_slotk[e] = P.slot_k[e];
+  __syncthreads();
   const int wg = blockIdx.x * nw + warp, wtot = gridDim.x * nw;
   double* acc_out = P.acc + (size_t)wg * P.acc_len;
   for (int rg = wg; rg < P.n_rg; rg += wtot) {
@@ -276,28 +321,32 @@ __global__ void __launch_bounds__(256) k_contract_tail(const TailParams P) {
     const int64_t row = (int64_t)rg * 32 + lane;
     const bool valid = row < P.rows_valid;
     const double* Wl = P.W + (size_t)rg * P.stride * 32 + lane;
-    for (int i = 0; i < P.d; ++i) {                // F_i[k] = sum_g K_i(x, u_g) Qs_i[g, k]
-      const DimDesc dd = P.dims[i];
-      const double x = valid ? P.X[row * P.ldx + i] : 0.0;
-      for (int k = 0; k < dd.u; ++k) sF[(dd.f_off + k) * 32 + lane] = 0.0;
-      for (int g = 0; g < dd.m; ++g) {
-        double kv, dk;
-        kern_eval_d(dd.kernel, x, __ldg(P.grid + dd.grid_off + g), dd.variance, dd.lengthscale, kv, dk);
-        const double* q = P.qs + dd.q_off + (size_t)g * dd.u;
-        for (int k = 0; k < dd.u; ++k) sF[(dd.f_off + k) * 32 + lane] = fma(kv, __ldg(q + k), sF[(dd.f_off + k) * 32 + lane]);
-      }
-    }
+    const double* Kl = P.KF + (size_t)rg * (P.sum_m + P.sum_u) * 32 + lane;
+    const double* Fl = Kl + (size_t)P.sum_m * 32;
     for (int e = 0; e < P.sum_u; ++e) sV[e * 32 + lane] = 0.0;
-    for (int s = 2; s < P.width; ++s) {            // V_i[k_i(s)] += W[s] * prod_{i' != i} F_i'[k_i'(s)]
-      const int g = __ldg(P.slot_group + s);
-      const int b0 = __ldg(P.group_begin + g), b1 = __ldg(P.group_begin + g + 1);
-      const uint8_t* ks = P.slot_k + (size_t)s * P.max_group_dims;
-      const double w = __ldcs(Wl + (size_t)s * 32);
-      for (int i = b0; i < b1; ++i) {
-        double prod = w;
-        for (int i2 = b0; i2 < b1; ++i2)
-          if (i2 != i) prod *= sF[(P.dims[i2].f_off + (int)__ldg(ks + i2 - b0)) * 32 + lane];
-        sV[(P.dims[i].f_off + (int)__ldg(ks + i - b0)) * 32 + lane] += prod;
+    constexpr int SB = 4;                          // W of the next SB slots is requested while SB slots are folded in
+    double wnext[SB];
+#pragma unroll
+    for (int t = 0; t < SB; ++t) wnext[t] = (2 + t < P.width) ? __ldcs(Wl + (size_t)(2 + t) * 32) : 0.0;
+    for (int s0 = 2; s0 < P.width; s0 += SB) {     // V_i[k_i(s)] += W[s] * prod_{i' != i} F_i'[k_i'(s)]
+      double wcur[SB];
+#pragma unroll
+      for (int t = 0; t < SB; ++t) wcur[t] = wnext[t];
+#pragma unroll
+      for (int t = 0; t < SB; ++t) wnext[t] = (s0 + SB + t < P.width) ? __ldcs(Wl + (size_t)(s0 + SB + t) * 32) : 0.0;
+#pragma unroll
+      for (int t = 0; t < SB; ++t) {
+        const int s = s0 + t;
+        if (s >= P.width) break;
+        const int g = s_sgrp[s];
+        const int b0 = s_gbeg[g], b1 = s_gbeg[g + 1];
+        const uint8_t* ks = s_slotk + (size_t)s * P.max_group_dims;
+        for (int i = b0; i < b1; ++i) {
+          double prod = wcur[t];
+          for (int i2 = b0; i2 < b1; ++i2)
+            if (i2 != i) prod *= __ldg(Fl + (size_t)(s_foff[i2] + (int)ks[i2 - b0]) * 32);
+          sV[(s_foff[i] + (int)ks[i - b0]) * 32 + lane] += prod;
+        }
       }
     }
     for (int i = 0; i < P.d; ++i) {                // parameter sums of dimension i and its M matrix
@@ -305,9 +354,8 @@ __global__ void __launch_bounds__(256) k_contract_tail(const TailParams P) {
       const double x = valid ? P.X[row * P.ldx + i] : 0.0;
       double gl = 0.0, gv = 0.0;
       for (int g = 0; g < dd.m; ++g) {
-        double kv, dk;
-        kern_eval_d(dd.kernel, x, __ldg(P.grid + dd.grid_off + g), dd.variance, dd.lengthscale, kv, dk);
-        if (!valid) { kv = 0.0; dk = 0.0; }
+        const double kv = __ldcs(Kl + (size_t)(dd.grid_off + g) * 32);       // 0 for rows that do not exist
+        const double dk = kern_dls_from_k(dd.kernel, kv, x, __ldg(P.grid + dd.grid_off + g), dd.lengthscale);
         sK[g * 33 + lane] = kv;
         const double* q = P.qs + dd.q_off + (size_t)g * dd.u;
         double U = 0.0;
@@ -434,12 +482,16 @@ static int back_warps(const Plan* pl, size_t* smem_out) {
   if (smem_out) *smem_out = per_warp * std::max(nw, 1);
   return nw;
 }
-// tail kernel: per warp F [sum_u][32], V [sum_u][32], K [m_max][33]
-static int tail_warps(const Plan* pl, size_t* smem_out) {
-  const size_t per_warp = ((size_t)64 * pl->sum_u + (size_t)33 * plan_m_max(pl)) * sizeof(double);
-  const int nw = (int)std::min<size_t>(8, (200 * 1024) / per_warp);
-  if (smem_out) *smem_out = per_warp * std::max(nw, 1);
-  return nw;
+// tail kernel: CTAs of 4 warps; per warp V [sum_u][32] and K [m_max][33], per CTA the index tables; as many CTAs per SM as fit
+constexpr int kTailWarps = 4;
+static size_t tail_smem(const Plan* pl) {
+  const size_t per_warp = ((size_t)32 * pl->sum_u + (size_t)33 * plan_m_max(pl)) * sizeof(double);
+  const size_t tables = (size_t)(pl->d + pl->width + kMaxGroups + 1) * sizeof(int) + (size_t)pl->width * pl->max_group_dims + 16;
+  return per_warp * kTailWarps + tables;
+}
+static int tail_ctas_per_sm(const Plan* pl) {
+  const size_t smem = tail_smem(pl) + 1024;          // + the per-CTA reservation of the driver
+  return (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
 }
 int contract_acc_len(const Plan* pl) {
   int qtot = 0;
@@ -447,7 +499,7 @@ int contract_acc_len(const Plan* pl) {
   return qtot + 2 * pl->d;
 }
 // accumulator rows of the tail kernel (one per warp of its grid)
-int contract_total_warps(const Plan* pl, int sms) { return sms * std::max(1, tail_warps(pl, nullptr)); }
+int contract_total_warps(const Plan* pl, int sms) { return sms * tail_ctas_per_sm(pl) * kTailWarps; }
 // doubles of the W slab for a slab of `rows` table rows
 size_t contract_w_doubles(const Plan* pl, int64_t rows) { return (size_t)rows * pl->stride; }
 
@@ -460,14 +512,17 @@ static int launch_back_g(const BackParams& P, int blocks, int threads, size_t sm
 }
 
 // Zt: Zp^T slab (p_pad x ldz); a: (y - Phi b) / noise_var of the slab's rows (from the builder); Wbuf: contract_w_doubles(rows_blk)
-// doubles; acc: contract_total_warps x contract_acc_len doubles, zeroed by the caller before the first slab.
+// doubles; KFbuf: kf_doubles(rows_blk) doubles; acc: contract_total_warps x contract_acc_len doubles, zeroed by the caller before the first slab.
+int launch_kf(const Plan* pl, const double* X, int64_t ldx, int64_t n_valid, int64_t rows_blk, double* KF, cudaStream_t stream);
 int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double* T, const double* X, int64_t ldx, const double* a,
-                    const double* bvec, int64_t rows_blk, int64_t rows_valid, double* Wbuf, double* acc, int sms, cudaStream_t stream) {
+                    const double* bvec, int64_t rows_blk, int64_t rows_valid, double* Wbuf, double* KFbuf, double* acc, int sms,
+                    cudaStream_t stream) {
   if (rows_blk == 0) return GRIEF_OK;
-  size_t smem_b = 0, smem_t = 0;
-  const int nwb = back_warps(pl, &smem_b), nwt = tail_warps(pl, &smem_t);
+  size_t smem_b = 0;
+  const size_t smem_t = tail_smem(pl);
+  const int nwb = back_warps(pl, &smem_b);
   if (nwb < 1) return fail(GRIEF_ERR_UNSUPPORTED, "contract: a table row of %d entries does not fit shared memory", pl->stride);
-  if (nwt < 1) return fail(GRIEF_ERR_UNSUPPORTED, "contract: %d factors per row do not fit shared memory", pl->sum_u);
+  if (smem_t > 220 * 1024) return fail(GRIEF_ERR_UNSUPPORTED, "contract: %d factors per row do not fit shared memory", pl->sum_u);
   BackParams B;
   B.Zt = Zt; B.ldz = ldz; B.T = T; B.stride = pl->stride; B.a = a; B.bvec = bvec; B.pack = pl->d_sorted_pack; B.p_pad = pl->p_pad;
   B.n_rg = (int)(rows_blk / 32); B.W = Wbuf;
@@ -486,15 +541,17 @@ int launch_contract(const Plan* pl, const double* Zt, int64_t ldz, const double*
   }
   prof_end(PROF_CONTRACT, stream);
   if (rc != GRIEF_OK) return rc;
+  prof_begin(PROF_DTABLES, stream);
+  rc = launch_kf(pl, X, ldx, rows_valid, rows_blk, KFbuf, stream);
+  if (rc != GRIEF_OK) return rc;
   TailParams Q;
-  Q.W = Wbuf; Q.X = X; Q.ldx = ldx;
+  Q.W = Wbuf; Q.KF = KFbuf; Q.X = X; Q.ldx = ldx;
   Q.dims = pl->d_dims; Q.grid = pl->d_grid; Q.qs = pl->d_qs; Q.slot_k = pl->d_slot_k; Q.slot_group = pl->d_slot_group; Q.group_begin = pl->d_group_begin;
-  Q.d = pl->d; Q.stride = pl->stride; Q.width = pl->width; Q.sum_u = pl->sum_u; Q.max_group_dims = pl->max_group_dims; Q.m_max = plan_m_max(pl);
+  Q.d = pl->d; Q.stride = pl->stride; Q.width = pl->width; Q.sum_m = pl->sum_m; Q.sum_u = pl->sum_u; Q.max_group_dims = pl->max_group_dims; Q.m_max = plan_m_max(pl); Q.n_groups = pl->n_groups;
   Q.rows_valid = rows_valid; Q.n_rg = (int)(rows_blk / 32);
   Q.acc = acc; Q.acc_len = contract_acc_len(pl);
   GRIEF_CUDA(cudaFuncSetAttribute(k_contract_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-  prof_begin(PROF_DTABLES, stream);
-  k_contract_tail<<<sms, nwt * 32, smem_t, stream>>>(Q);
+  k_contract_tail<<<sms * tail_ctas_per_sm(pl), kTailWarps * 32, smem_t, stream>>>(Q);
   prof_end(PROF_DTABLES, stream);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;

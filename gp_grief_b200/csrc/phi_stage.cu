@@ -109,9 +109,14 @@ __global__ void k_col_exps(const int* __restrict__ slot_hi, const uint16_t* __re
 }
 
 // digits d_s of q = rint(v * scale) as bytes of one 64-bit word: digit s (0 = most significant) is byte 6 - s  (see store_digits)
+// sd <= 6: |q| <= 2^46, so q is read off the mantissa of v * scale + 1.5 * 2^52 (one DFMA; the rounding to an integer is the
+// same round-to-nearest-even as the conversion instruction, which takes a trip through a slower pipe); sd = 7 converts.
 __device__ __forceinline__ unsigned long long digit_word(double v, double scale, int sd) {
   const unsigned long long bias = 0x0080808080808080ull >> (8 * (7 - sd));
-  return (((unsigned long long)__double2ll_rn(v * scale) + bias) ^ bias) << (8 * (7 - sd));
+  long long q;
+  if (sd <= 6) q = __double_as_longlong(fma(v, scale, 6755399441055744.0)) - 0x4338000000000000ll;
+  else q = __double2ll_rn(v * scale);
+  return (((unsigned long long)q + bias) ^ bias) << (8 * (7 - sd));
 }
 // byte B (0..6) of four digit words, packed into one 32-bit word (word i -> byte i): 3 PRMT
 template <int B>
@@ -139,10 +144,12 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
                                                                const uint8_t* __restrict__ sorted_level, int p_pad,
                                                                double* __restrict__ out, int64_t ld, const int* __restrict__ exps,
                                                                int8_t* __restrict__ planes, int sd, const double* __restrict__ y,
-                                                               int64_t y_rows, double* __restrict__ r_ws) {
+                                                               int64_t y_rows, double* __restrict__ r_ws, int* __restrict__ row_hi_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
+  int* s_rowhi = reinterpret_cast<int*>(sT + (size_t)kBuildRows * stride);      // [128] row maxima (high words), row_hi_out only
+  if (row_hi_out != nullptr && threadIdx.x < kBuildRows) s_rowhi[threadIdx.x] = 0;
   init_stage_barrier(bar);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cpw = p_pad / (kBuildThreads / 32);        // columns per warp (p_pad is a multiple of 128)
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
 #pragma unroll
   for (int rg = 0; rg < RG; ++rg) trow[rg] = sT + (size_t)(rg * 32 + lane) * stride;
   double P[RG] = {1.0, 1.0, 1.0, 1.0};                  // running prefix products, one per row group
+  int rhi[RG] = {0, 0, 0, 0};                           // row maxima over this warp's columns
   const size_t plane_stride = (size_t)p_pad * ld;
   for (int c0 = c_begin; c0 < c_begin + cpw; c0 += NB) {
     int lv[NB], sl[NB];
@@ -187,6 +195,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
       double v[RG];
 #pragma unroll
       for (int rg = 0; rg < RG; ++rg) v[rg] = G > 1 ? P[rg] * trow[rg][sl[e]] : trow[rg][sl[e]];
+#pragma unroll
+      for (int rg = 0; rg < RG; ++rg) rhi[rg] = max(rhi[rg], abs_hi(v[rg]));
       if constexpr (!DIG) {
 #pragma unroll
         for (int rg = 0; rg < RG; ++rg) out[(size_t)(c0 + e) * ld + grow0 + rg * 32] = v[rg];
@@ -220,6 +230,12 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi_t(const double* __r
       if (lane < NB) r_ws[(size_t)rb * p_pad + c0 + lane] = mine;
     }
   }
+  if (row_hi_out != nullptr) {                           // warp-uniform: max over the 16 warps' column ranges, one int per row
+#pragma unroll
+    for (int rg = 0; rg < RG; ++rg) atomicMax(s_rowhi + rg * 32 + lane, rhi[rg]);
+    __syncthreads();
+    if (threadIdx.x < kBuildRows) row_hi_out[(size_t)rb * kBuildRows + threadIdx.x] = s_rowhi[threadIdx.x];
+  }
 }
 
 // r_acc[c] (+)= sum_b r_ws[b][c] over the nblk row blocks of a slab (fixed order: warp w sums b = w, w + 16, ..., then warps in sequence)
@@ -250,20 +266,37 @@ __global__ void k_unpermute_vec(const double* __restrict__ in, const int* __rest
 // last key position (all lanes read the same words: the branch is warp-uniform).  emit(c0, v) receives NB consecutive values.
 template <int G>
 __device__ __forceinline__ int pack_slot(const uint32_t* w, int k) { return (int)((w[k >> 2] >> (8 * (3 - (k & 3)))) & 0xFFu); }
-template <int G, int NB, typename Emit>
-__device__ __forceinline__ void walk_sorted_columns(const double* __restrict__ trow, const uint32_t* __restrict__ pack, int c_begin,
-                                                    int c_end, Emit&& emit) {
+template <int G, int NB, bool AUX, typename Emit>
+__device__ __forceinline__ void walk_sorted_columns(const double* __restrict__ trow, const uint32_t* __restrict__ pack,
+                                                    const double* __restrict__ aux, int c_begin, int c_end, Emit&& emit) {
+  // aux (AUX = true): a per-column vector handed to emit next to the values (requested at the start of the batch, consumed at its
+  // end).  The packed slots of batch c0 + NB are requested before batch c0 is consumed (they come from L1 / L2: ~40-250 cycles
+  // that the 16 warps of a CTA do not hide).
   constexpr int NW = (G + 3) / 4;
   uint32_t prev[NW];
 #pragma unroll
   for (int w = 0; w < NW; ++w) prev[w] = 0;
   double P = 1.0;
+  uint32_t wnext[NB][NW];
+#pragma unroll
+  for (int e = 0; e < NB; ++e)
+#pragma unroll
+    for (int w = 0; w < NW; ++w) wnext[e][w] = __ldg(pack + (size_t)(c_begin + e) * NW + w);
   for (int c0 = c_begin; c0 < c_end; c0 += NB) {
     uint32_t wd[NB][NW];
+    double av[NB];
 #pragma unroll
-    for (int e = 0; e < NB; ++e)
+    for (int e = 0; e < NB; ++e) {
 #pragma unroll
-      for (int w = 0; w < NW; ++w) wd[e][w] = __ldg(pack + (size_t)(c0 + e) * NW + w);
+      for (int w = 0; w < NW; ++w) wd[e][w] = wnext[e][w];
+      av[e] = AUX ? __ldg(aux + c0 + e) : 0.0;
+    }
+    if (c0 + NB < c_end) {
+#pragma unroll
+      for (int e = 0; e < NB; ++e)
+#pragma unroll
+        for (int w = 0; w < NW; ++w) wnext[e][w] = __ldg(pack + (size_t)(c0 + NB + e) * NW + w);
+    }
     double v[NB];
 #pragma unroll
     for (int e = 0; e < NB; ++e) {
@@ -289,7 +322,7 @@ __device__ __forceinline__ void walk_sorted_columns(const double* __restrict__ t
         v[e] = trow[pack_slot<G>(wd[e], 0)];
       }
     }
-    emit(c0, v);
+    emit(c0, v, av);
   }
 }
 
@@ -298,8 +331,10 @@ __device__ __forceinline__ void walk_sorted_columns(const double* __restrict__ t
 // per element instead of G).  A lane holds 16 consecutive columns of its row at a time and writes 16 contiguous bytes per digit
 // plane (DIG) or 128 contiguous bytes (FP64).
 //   DIG = false: out[row * ldo + c]
-//   DIG = true:  first sweep -> row maximum -> exps[row]; second sweep -> planes[s][row][c], scaled by 2^(8 sd - 2 - exps[row])
-// bvec != nullptr: f[row] = sum_c Phi[row][c] * bvec[c] is accumulated in the first sweep (the values are in registers) and
+//   DIG = true:  first sweep -> row maximum -> exps[row]; second sweep -> planes[s][row][c], scaled by 2^(8 sd - 2 - exps[row]).
+//                row_hi != nullptr: the row maxima are already known (the pass-1 builder of the same tables recorded them,
+//                k_build_phi_t) and the first sweep is skipped.
+// bvec != nullptr: f[row] = sum_c Phi[row][c] * bvec[c] is accumulated along the way (the values are in registers) and
 // a_out[row] = (y[row] - f[row]) * inv_noise is written -- the residual scaled by the noise that the contraction kernel needs
 // (grad.cu); column quarters are summed in fixed order.
 template <int G, bool DIG>
@@ -308,7 +343,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
                                                              double* __restrict__ out, int64_t ldo, int* __restrict__ exps,
                                                              int8_t* __restrict__ planes, size_t plane_stride, int sd, int* __restrict__ err,
                                                              const double* __restrict__ bvec, const double* __restrict__ y, int64_t y_rows,
-                                                             double inv_noise, double* __restrict__ a_out) {
+                                                             double inv_noise, double* __restrict__ a_out,
+                                                             const int* __restrict__ row_hi) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
@@ -323,19 +359,31 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
   const size_t grow = (size_t)blockIdx.x * kBuildRows + r_blk;
   const int cq = p_pad / 4;                                           // p_pad is a multiple of 128
   const int c_begin = quarter * cq, c_end = c_begin + cq;
-  constexpr int NB = 16;
+  constexpr int NB1 = 8;                                              // sweep 1 keeps values, b and their prefetch in registers
+  constexpr int NB = DIG ? 16 : 8;                                    // sweep 2: 16 columns = 16 bytes per digit plane and lane
   const bool want_f = bvec != nullptr;
+  const bool f_in_sweep2 = want_f && (!DIG || row_hi != nullptr);
   double scale = 1.0, f = 0.0;
-  if (DIG) {                                                          // sweep 1: row maximum (and f)
+  if (DIG && row_hi != nullptr) {                                     // row maxima recorded by pass 1: no first sweep
+    const int mh = __ldg(row_hi + grow);
+    const int e = exp_from_hi(mh);
+    if (quarter == 0) {
+      exps[grow] = e;
+      if (mh >= 0x7ff00000) atomicExch(err, 4);
+    }
+    scale = digit_scale(sd, e);
+  } else if (DIG) {                                                   // sweep 1: row maximum (and f)
     int hi = 0;
-    walk_sorted_columns<G, NB>(trow, pack, c_begin, c_end, [&](int c0, const double (&v)[NB]) {
+    auto sweep1 = [&](int, const double (&v)[NB1], const double (&bv)[NB1]) {      // bv is all zero without bvec
 #pragma unroll
-      for (int e = 0; e < NB; ++e) hi = max(hi, abs_hi(v[e]));
+      for (int e = 0; e < NB1; ++e) hi = max(hi, abs_hi(v[e]));
       if (want_f) {
 #pragma unroll
-        for (int e = 0; e < NB; ++e) f = fma(v[e], __ldg(bvec + c0 + e), f);
+        for (int e = 0; e < NB1; ++e) f = fma(v[e], bv[e], f);
       }
-    });
+    };
+    if (want_f) walk_sorted_columns<G, NB1, true>(trow, pack, bvec, c_begin, c_end, sweep1);
+    else walk_sorted_columns<G, NB1, false>(trow, pack, nullptr, c_begin, c_end, sweep1);
     s_hi[quarter * kBuildRows + r_blk] = hi;
     __syncthreads();
     int mh = 0;
@@ -348,12 +396,12 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
     }
     scale = digit_scale(sd, e);
   }
-  walk_sorted_columns<G, NB>(trow, pack, c_begin, c_end, [&](int c0, const double (&v)[NB]) {
-    if constexpr (!DIG) {
-      if (want_f) {
+  auto sweep2 = [&](int c0, const double (&v)[NB], const double (&bv)[NB]) {
+    if (f_in_sweep2) {
 #pragma unroll
-        for (int e = 0; e < NB; ++e) f = fma(v[e], __ldg(bvec + c0 + e), f);
-      }
+      for (int e = 0; e < NB; ++e) f = fma(v[e], bv[e], f);
+    }
+    if constexpr (!DIG) {
       double2* dst = reinterpret_cast<double2*>(out + grow * ldo + c0);
 #pragma unroll
       for (int e = 0; e < NB; e += 2) dst[e >> 1] = make_double2(v[e], v[e + 1]);
@@ -380,7 +428,9 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
       if (sd > 6) GRIEF_PLANE(6, 0);
 #undef GRIEF_PLANE
     }
-  });
+  };
+  if (f_in_sweep2) walk_sorted_columns<G, NB, true>(trow, pack, bvec, c_begin, c_end, sweep2);
+  else walk_sorted_columns<G, NB, false>(trow, pack, nullptr, c_begin, c_end, sweep2);
   if (want_f) {                                                       // warp-uniform
     s_f[quarter * kBuildRows + r_blk] = f;
     __syncthreads();
@@ -400,25 +450,29 @@ struct BuildArgs {
   int8_t* planes = nullptr; size_t plane_stride = 0;
   const double* y = nullptr; int64_t y_rows = 0; double* r_ws = nullptr;   // transposed: fused Phi^T y partials (y, y_rows, r_ws)
   const double* bvec = nullptr; double inv_noise = 0.0; double* a_out = nullptr;   // row-major: a = (y - Phi bvec) * inv_noise (y, y_rows too)
+  int* row_hi_out = nullptr;                 // transposed: per-row maxima (high words) of |Phi| for a later row-major build of the same tables
+  const int* row_hi = nullptr;               // row-major digits: row maxima recorded earlier (skips the maximum sweep)
 };
 
 template <int G>
 static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
-  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double) + (a.transposed ? 0 : 4 * kBuildRows * (sizeof(double) + sizeof(int)));
+  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double) +
+                      (a.transposed ? kBuildRows * sizeof(int) : 4 * kBuildRows * (sizeof(double) + sizeof(int)));
   const unsigned grid = (unsigned)(rows / kBuildRows);
   GRIEF_REQUIRE(smem <= 227 * 1024, "build_phi: %zu bytes of shared memory", smem);
 #define GRIEF_BT(DIG_)                                                                                                              \
   do {                                                                                                                              \
     GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi_t<G, DIG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
     k_build_phi_t<G, DIG_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_slot, pl->d_sorted_level, pl->p_pad,  \
-                                                                 a.out, a.ld, a.exps, a.planes, a.sd, a.y, a.y_rows, a.r_ws);       \
+                                                                 a.out, a.ld, a.exps, a.planes, a.sd, a.y, a.y_rows, a.r_ws,        \
+                                                                 a.row_hi_out);                                                     \
   } while (0)
 #define GRIEF_BN(DIG_)                                                                                                              \
   do {                                                                                                                              \
     GRIEF_CUDA(cudaFuncSetAttribute(k_build_phi<G, DIG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
     k_build_phi<G, DIG_><<<grid, kBuildThreads, smem, stream>>>(T, pl->stride, pl->d_sorted_pack, pl->p_pad, a.out, a.ld, a.exps,   \
                                                                a.planes, a.plane_stride, a.sd, pl->d_err, a.bvec, a.y, a.y_rows,    \
-                                                               a.inv_noise, a.a_out);                                               \
+                                                               a.inv_noise, a.a_out, a.row_hi);                                     \
   } while (0)
   if (a.transposed) {
     if (a.digits) GRIEF_BT(true); else GRIEF_BT(false);
@@ -519,8 +573,9 @@ k_gram_reduce(const double* __restrict__ part, const int* __restrict__ perm, int
 }
 
 // r != nullptr: r (p) = Phi^T y comes out of the builders' sweep (y: n valid rows).
+// rowmax_out != nullptr (n_pad ints): the high word of max_c |Phi[row][c]| of every table row, for launch_zgemm on the same tables.
 int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64_t lda, const double* y, int64_t n, double* r,
-                void* workspace, size_t ws_bytes, int sms, cudaStream_t stream, int* launches) {
+                int* rowmax_out, void* workspace, size_t ws_bytes, int sms, cudaStream_t stream, int* launches) {
   GRIEF_REQUIRE(n_pad % kBuildRows == 0, "gram: n_pad=%lld must be a multiple of %d", (long long)n_pad, kBuildRows);
   GRIEF_REQUIRE(ws_bytes >= gram_workspace_bytes(pl, n_pad, sms), "gram: workspace too small");
   const GramSchedule s = gram_schedule(pl, n_pad, sms);
@@ -554,6 +609,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
     BuildArgs ba;
     ba.transposed = true;
     if (r) { ba.y = y + r0; ba.y_rows = std::max<int64_t>(0, n - r0); ba.r_ws = r_ws; }
+    if (rowmax_out) ba.row_hi_out = rowmax_out + r0;
     int rc;
     prof_begin(PROF_BUILD_T, stream);
     if (i8) {      // exponents from the slot maxima of the slab's tables, then the digit planes [sd][p_pad][R] (K = data rows)
@@ -659,6 +715,7 @@ int launch_zgemm_prepare(const Plan* pl, const double* Bperm, int64_t slab_rows_
 // (p_pad x p_pad, launch_permute_b).  scratch: zgemm_scratch_bytes(pl, slab_rows_max) bytes, prepared by launch_zgemm_prepare.
 struct ResidualArgs {      // optional by-product of the slab builder: a = (y - Phi bvec) / noise_var for the slab's rows
   const double* bvec = nullptr; const double* y = nullptr; int64_t y_rows = 0; double inv_noise = 0.0; double* a_out = nullptr;
+  const int* row_hi = nullptr;      // optional input: row maxima of the slab's rows recorded by launch_gram
 };
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Zt,
                  int64_t ldz, int digits, const ResidualArgs* res, cudaStream_t stream, int* launches) {
@@ -668,7 +725,7 @@ int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const 
   const bool i8 = pl->opts.gemm_mode == 1;
   ZScratch z = carve_zscratch(pl, slab_rows_max, scratch);
   BuildArgs ba;
-  if (res) { ba.bvec = res->bvec; ba.y = res->y; ba.y_rows = res->y_rows; ba.inv_noise = res->inv_noise; ba.a_out = res->a_out; }
+  if (res) { ba.bvec = res->bvec; ba.y = res->y; ba.y_rows = res->y_rows; ba.inv_noise = res->inv_noise; ba.a_out = res->a_out; ba.row_hi = res->row_hi; }
   if (i8) {      // row exponents + digit planes [sd][slab_rows][p_pad] straight from the tables
     ba.digits = true; ba.sd = digits; ba.exps = z.ea; ba.planes = z.pa; ba.plane_stride = (size_t)slab_rows * pl->p_pad;
   } else {

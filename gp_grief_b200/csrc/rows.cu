@@ -67,26 +67,39 @@ __device__ __forceinline__ double kern_eval_dx(int kernel, double x, double u, d
 // Kxu != nullptr: (n x sum_m) row-major, ldk doubles per row; the columns of every dimension whose kernel id is KERN_HOST hold
 // K_xu,i evaluated by the caller (any BaseKernel whose cov is host code: kern/gpy_kernel.py:45-58, kern/grid_kernel.py:148-179);
 // with deriv_dim = i they hold d K_xu,i / d x instead.
+// KF != nullptr (RB must be 32): the kernel values and the factors of the block's rows are also written as
+// KF[block][c][row in block], c < sum_m: K_xu, then sum_u columns of F -- the layout the lane = row gradient kernels read coalesced
+// (grad.cu: k_contract_tail); T == nullptr skips the group products.
 __global__ void __launch_bounds__(256)
 k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, const double* __restrict__ qs,
          const uint8_t* __restrict__ slot_k, const int* __restrict__ slot_group, const int* __restrict__ group_begin,
          int d, int sum_m, int sum_u, int width, int stride, int max_group_dims, const double* __restrict__ X,
          int64_t ldx, int64_t n, int64_t n_pad, double* __restrict__ T, int RB, int deriv_dim,
-         const double* __restrict__ Kxu, int64_t ldk) {
+         const double* __restrict__ Kxu, int64_t ldk, double* __restrict__ KF) {
   extern __shared__ double sm[];
   double* sK = sm;
   double* sF = sm + (size_t)RB * sum_m;
+  DimDesc* sD = reinterpret_cast<DimDesc*>(sF + (size_t)RB * sum_u);          // [d] the dimension descriptors
+  uint8_t* dim_of_m = reinterpret_cast<uint8_t*>(sD + d);                       // [sum_m] dimension of a grid column
+  uint8_t* dim_of_u = dim_of_m + sum_m;                                         // [sum_u] dimension of a factor column
   const int64_t row0 = (int64_t)blockIdx.x * RB;
   const int rows = (int)min((int64_t)RB, n_pad - row0);
   const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < d; i += nt) sD[i] = dims[i];
+  __syncthreads();
+  for (int i = tid; i < d; i += nt) {               // lookup tables instead of a linear search per task (d is up to 64)
+    const DimDesc dd = sD[i];
+    for (int g = 0; g < dd.m; ++g) dim_of_m[dd.grid_off + g] = (uint8_t)i;
+    for (int k = 0; k < dd.u; ++k) dim_of_u[dd.f_off + k] = (uint8_t)i;
+  }
+  __syncthreads();
 
   // phase 1a: kernel values against every grid point
   for (int task = tid; task < rows * sum_m; task += nt) {
     const int r = task / sum_m;
     const int c = task - r * sum_m;
-    int i = 0;
-    while (i + 1 < d && dims[i + 1].grid_off <= c) ++i;
-    const DimDesc dd = dims[i];
+    const int i = dim_of_m[c];
+    const DimDesc dd = sD[i];
     const int64_t row = row0 + r;
     double v = 0.0;
     if (row < n) {
@@ -102,17 +115,24 @@ k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, cons
   for (int task = tid; task < rows * sum_u; task += nt) {
     const int r = task / sum_u;
     const int c = task - r * sum_u;
-    int i = 0;
-    while (i + 1 < d && dims[i + 1].f_off <= c) ++i;
-    const DimDesc dd = dims[i];
-    const int k = c - dd.f_off;
-    const double* kv = sK + (size_t)r * sum_m + dd.grid_off;
-    const double* q = qs + dd.q_off + k;
+    const int i = dim_of_u[c];
+    const int m_i = sD[i].m, u_i = sD[i].u;
+    const int k = c - sD[i].f_off;
+    const double* kv = sK + (size_t)r * sum_m + sD[i].grid_off;
+    const double* q = qs + sD[i].q_off + k;
     double acc = 0.0;
-    for (int g = 0; g < dd.m; ++g) acc = fma(kv[g], q[(size_t)g * dd.u], acc);
+    for (int g = 0; g < m_i; ++g) acc = fma(kv[g], __ldg(q + (size_t)g * u_i), acc);
     sF[(size_t)r * sum_u + c] = acc;
   }
   __syncthreads();
+  if (KF != nullptr) {
+    double* dst = KF + (size_t)blockIdx.x * (sum_m + sum_u) * 32;
+    for (int task = tid; task < (sum_m + sum_u) * 32; task += nt) {
+      const int c = task >> 5, r = task & 31;
+      dst[task] = r < rows ? (c < sum_m ? sK[(size_t)r * sum_m + c] : sF[(size_t)r * sum_u + (c - sum_m)]) : 0.0;
+    }
+  }
+  if (T == nullptr) return;
   // phase 2: group products, coalesced row-major store (pad rows >= n are written as zeros)
   for (int task = tid; task < rows * stride; task += nt) {
     const int r = task / stride;
@@ -123,11 +143,11 @@ k_tables(const DimDesc* __restrict__ dims, const double* __restrict__ grid, cons
     else if (s == 0) v = 1.0;
     else if (s == 1) v = 0.0;
     else {
-      const int g = slot_group[s];
-      const int a = group_begin[g], b = group_begin[g + 1];
+      const int g = __ldg(slot_group + s);
+      const int a = __ldg(group_begin + g), b = __ldg(group_begin + g + 1);
       const uint8_t* ks = slot_k + (size_t)s * max_group_dims;
       v = 1.0;
-      for (int i = a; i < b; ++i) v *= sF[(size_t)r * sum_u + dims[i].f_off + ks[i - a]];
+      for (int i = a; i < b; ++i) v *= sF[(size_t)r * sum_u + sD[i].f_off + __ldg(ks + i - a)];
     }
     T[row * stride + s] = v;
   }
@@ -139,18 +159,37 @@ int launch_tables(const Plan* pl, const double* X, int64_t ldx, int64_t n, int64
     GRIEF_REQUIRE(Kxu != nullptr && ldk >= pl->sum_m, "tables: %d dimension(s) have host-evaluated kernels: pass K_xu (n x %d) through "
                   "grief_build_tables_kxu", pl->n_host_dims, pl->sum_m);
   const size_t per_row = (size_t)(pl->sum_m + pl->sum_u) * sizeof(double);
-  int RB = (int)std::min<size_t>(32, (160 * 1024) / per_row);
+  const size_t lookup = (size_t)pl->d * sizeof(DimDesc) + (size_t)(pl->sum_m + pl->sum_u) + 16;
+  int RB = (int)std::min<size_t>(32, (160 * 1024 - lookup) / per_row);
   if (RB < 1) return fail(GRIEF_ERR_UNSUPPORTED, "tables: %d grid points + %d factors per row exceed shared memory",
                           pl->sum_m, pl->sum_u);
-  const size_t smem = per_row * RB;
+  const size_t smem = per_row * RB + lookup;
   GRIEF_CUDA(cudaFuncSetAttribute(k_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (n_pad + RB - 1) / RB;
   if (blocks == 0) return GRIEF_OK;
   prof_begin(PROF_TABLES, stream);
   k_tables<<<(unsigned)blocks, 256, smem, stream>>>(pl->d_dims, pl->d_grid, pl->d_qs, pl->d_slot_k, pl->d_slot_group,
                                                     pl->d_group_begin, pl->d, pl->sum_m, pl->sum_u, pl->width,
-                                                    pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB, deriv_dim, Kxu, ldk);
+                                                    pl->stride, pl->max_group_dims, X, ldx, n, n_pad, T, RB, deriv_dim, Kxu, ldk, nullptr);
   prof_end(PROF_TABLES, stream);
+  GRIEF_CUDA(cudaGetLastError());
+  return GRIEF_OK;
+}
+
+// K_xu and F of rows_blk rows (a multiple of 32; rows >= n_valid are written as zeros) in the [row group][column][32] layout.
+size_t kf_doubles(const Plan* pl, int64_t rows) { return (size_t)rows * (pl->sum_m + pl->sum_u); }
+int launch_kf(const Plan* pl, const double* X, int64_t ldx, int64_t n_valid, int64_t rows_blk, double* KF, cudaStream_t stream) {
+  if (rows_blk == 0) return GRIEF_OK;
+  GRIEF_REQUIRE(rows_blk % 32 == 0, "kf: rows=%lld is not a multiple of 32", (long long)rows_blk);
+  const size_t per_row = (size_t)(pl->sum_m + pl->sum_u) * sizeof(double);
+  const size_t lookup = (size_t)pl->d * sizeof(DimDesc) + (size_t)(pl->sum_m + pl->sum_u) + 16;
+  const size_t smem = per_row * 32 + lookup;
+  if (smem > 224 * 1024)
+    return fail(GRIEF_ERR_UNSUPPORTED, "kf: %d grid points + %d factors per row exceed shared memory", pl->sum_m, pl->sum_u);
+  GRIEF_CUDA(cudaFuncSetAttribute(k_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tables<<<(unsigned)(rows_blk / 32), 256, smem, stream>>>(pl->d_dims, pl->d_grid, pl->d_qs, pl->d_slot_k, pl->d_slot_group,
+                                                            pl->d_group_begin, pl->d, pl->sum_m, pl->sum_u, pl->width, pl->stride,
+                                                            pl->max_group_dims, X, ldx, n_valid, rows_blk, nullptr, 32, -1, nullptr, 0, KF);
   GRIEF_CUDA(cudaGetLastError());
   return GRIEF_OK;
 }

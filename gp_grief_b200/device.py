@@ -162,8 +162,9 @@ class DevicePlan(object):
     def get_option(self, what):
         return int(nat.lib().grief_plan_get_option(self._h, int(what)))
 
-    def gram(self, T, n, out=None, workspace=None, y=None, r_out=None):
-        """A = Phi^T Phi (p, p) from the tables of n rows; with y (n,) also r = Phi^T y from the same sweep (returned in r_out)."""
+    def gram(self, T, n, out=None, workspace=None, y=None, r_out=None, rowmax_out=None):
+        """A = Phi^T Phi (p, p) from the tables of n rows; with y (n,) also r = Phi^T y from the same sweep (returned in r_out) and,
+        with rowmax_out (int32, T.shape[0]), the row maxima of |Phi| that grad_theta can reuse for the same tables."""
         torch = _torch()
         A = out if out is not None else torch.empty((self.p, self.p), dtype=torch.float64, device=T.device)
         need = nat.lib().grief_gram_workspace_bytes(self._h, n)
@@ -174,8 +175,11 @@ class DevicePlan(object):
                                            workspace.numel(), nat.stream_ptr()))
             return A
         assert r_out is not None and r_out.numel() == self.p and y.numel() == n
+        if rowmax_out is not None:
+            assert rowmax_out.dtype == torch.int32 and rowmax_out.numel() >= T.shape[0] and rowmax_out.is_contiguous()
         nat.check(nat.lib().grief_gram_ry(self._h, nat.dev_ptr(T), n, nat.dev_ptr(y), nat.dev_ptr(A), A.stride(0),
-                                          nat.dev_ptr(r_out), nat.dev_ptr(workspace), workspace.numel(), nat.stream_ptr()))
+                                          nat.dev_ptr(r_out), nat.dev_ptr(rowmax_out), nat.dev_ptr(workspace), workspace.numel(),
+                                          nat.stream_ptr()))
         return A
 
     def gram_workspace_bytes(self, n):
@@ -207,8 +211,9 @@ class DevicePlan(object):
         nat.check(nat.lib().grief_grad_setup(self._h, na, nat.host_ptr(dims_a), nat.host_ptr(kinds_a), nat.host_ptr(dqs)))
         self.n_active = na
 
-    def grad_theta(self, T, X_dev, y_dev, n, Pinv, b, noise_var):
-        """d LML / d theta of the active parameters from P^-1 (p, p) and b = P^-1 r (device tensors)."""
+    def grad_theta(self, T, X_dev, y_dev, n, Pinv, b, noise_var, rowmax=None):
+        """d LML / d theta of the active parameters from P^-1 (p, p) and b = P^-1 r (device tensors); rowmax: the row maxima
+        `gram(..., rowmax_out=)` recorded for the same tables (optional, saves a sweep over Phi)."""
         torch = _torch()
         g = torch.zeros((max(self.n_active, 1),), dtype=torch.float64, device=T.device)
         need = nat.lib().grief_grad_workspace_bytes(self._h, n)
@@ -216,7 +221,7 @@ class DevicePlan(object):
         ldx = X_dev.stride(0) if n > 1 else self.d
         Pinv = _even_ld(Pinv)
         nat.check(nat.lib().grief_grad_theta(self._h, nat.dev_ptr(T), nat.dev_ptr(X_dev), ldx, nat.dev_ptr(y_dev), n,
-                                             nat.dev_ptr(Pinv), Pinv.stride(0), nat.dev_ptr(b), float(noise_var),
+                                             nat.dev_ptr(Pinv), Pinv.stride(0), nat.dev_ptr(b), float(noise_var), nat.dev_ptr(rowmax),
                                              nat.dev_ptr(g), nat.dev_ptr(ws), ws.numel(), nat.stream_ptr()))
         return g[:self.n_active]
 

@@ -206,9 +206,11 @@ int grief_gram(const grief_plan* plan, const double* T_dev, int64_t n, double* A
  * A = Phi^T Phi and r = Phi^T y (models/gp_grief_model.py:148-149 and :234) from ONE sweep over the rows: the builder that stages a
  * slab of Phi has every element in a register, so y^T Phi is accumulated there (fixed order) instead of a second pass over Phi.
  *   y_dev (n), r_dev (p) out.  r_dev == NULL: same as grief_gram.
+ *   rowmax_dev  out or NULL: int32[grief_table_rows(n)], the high word of max_j |Phi[row, j]| of every row (the same sweep sees every
+ *               element).  Handing it to grief_grad_theta for the SAME tables saves that call one of its two sweeps over Phi.
  */
 int grief_gram_ry(const grief_plan* plan, const double* T_dev, int64_t n, const double* y_dev, double* A_dev, int64_t lda,
-                  double* r_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+                  double* r_dev, int32_t* rowmax_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* out[j] = sum_n v[n] Phi[n,j]  (r = Phi^T y, models/gp_grief_model.py:234).  ws: grief_phi_t_vec_workspace_bytes */
 size_t grief_phi_t_vec_workspace_bytes(const grief_plan* plan, int64_t n);
@@ -253,12 +255,14 @@ int grief_solve_lml(grief_ctx* ctx, int p, const double* A_dev, int64_t lda, con
  *   T_dev          tables of the n rows (grief_build_tables)
  *   Pinv_dev, ldp  P^-1 from grief_solve_lml, symmetric
  *   b_dev          P^-1 r from grief_solve_lml
+ *   rowmax_dev     NULL, or the row maxima grief_gram_ry recorded for these tables (INT8 arithmetic: the row scales of the digit
+ *                  planes then need no sweep of their own; results are identical either way)
  */
 int grief_grad_setup(grief_plan* plan, int n_active, const int32_t* dims, const int32_t* kinds, const double* dqs_concat);
 size_t grief_grad_workspace_bytes(const grief_plan* plan, int64_t n);
 int grief_grad_theta(const grief_plan* plan, const double* T_dev, const double* X_dev, int64_t ldx, const double* y_dev,
                      int64_t n, const double* Pinv_dev, int64_t ldp, const double* b_dev, double noise_var,
-                     double* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+                     const int32_t* rowmax_dev, double* grad_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /*
  * q[n] = phi(x_n)^T B phi(x_n) for a symmetric (p,p) matrix B, phi built on the fly.
