@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--gemm", default="int8", choices=["int8", "int8x2", "fp64"],
                     help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores or the FP64 DMMA GEMM")
     ap.add_argument("--digits", default="", help="'Dgram,Dz': int8 digits per operand of the two products (default: library defaults)")
-    ap.add_argument("--slab-mb", type=int, default=0, help="HBM budget (MiB) of the Phi^T slab staged per pass-1 GEMM launch (0: library default 4096)")
+    ap.add_argument("--slab-mb", type=int, default=0, help="HBM budget (MiB) of the Phi^T slab staged per pass-1 GEMM launch (0: library default 1024)")
     ap.add_argument("--power-trace", default="", help="write the clock / power samples of the timed region to this JSON file")
     return ap.parse_args()
 

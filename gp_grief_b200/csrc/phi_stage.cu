@@ -260,83 +260,20 @@ __global__ void k_unpermute_vec(const double* __restrict__ in, const int* __rest
   if (c < p_pad && perm[c] >= 0) out[perm[c]] = in[c];
 }
 
-// ---- lane = data row walk over a range of sorted columns ----
-// pack: plan->d_sorted_pack, (G + 3) / 4 words per sorted column, key position k in byte 3 - k % 4 of word k / 4.  Consecutive sorted
-// columns share their leading slots; the product P of the first G-1 factors is rebuilt only where the packed words differ above the
-// last key position (all lanes read the same words: the branch is warp-uniform).  emit(c0, v) receives NB consecutive values.
+// pack: plan->d_sorted_pack, (G + 3) / 4 words per sorted column, key position k in byte 3 - k % 4 of word k / 4
 template <int G>
 __device__ __forceinline__ int pack_slot(const uint32_t* w, int k) { return (int)((w[k >> 2] >> (8 * (3 - (k & 3)))) & 0xFFu); }
-template <int G, int NB, bool AUX, typename Emit>
-__device__ __forceinline__ void walk_sorted_columns(const double* __restrict__ trow, const uint32_t* __restrict__ pack,
-                                                    const double* __restrict__ aux, int c_begin, int c_end, Emit&& emit) {
-  // aux (AUX = true): a per-column vector handed to emit next to the values (requested at the start of the batch, consumed at its
-  // end).  The packed slots of batch c0 + NB are requested before batch c0 is consumed (they come from L1 / L2: ~40-250 cycles
-  // that the 16 warps of a CTA do not hide).
-  constexpr int NW = (G + 3) / 4;
-  uint32_t prev[NW];
-#pragma unroll
-  for (int w = 0; w < NW; ++w) prev[w] = 0;
-  double P = 1.0;
-  uint32_t wnext[NB][NW];
-#pragma unroll
-  for (int e = 0; e < NB; ++e)
-#pragma unroll
-    for (int w = 0; w < NW; ++w) wnext[e][w] = __ldg(pack + (size_t)(c_begin + e) * NW + w);
-  for (int c0 = c_begin; c0 < c_end; c0 += NB) {
-    uint32_t wd[NB][NW];
-    double av[NB];
-#pragma unroll
-    for (int e = 0; e < NB; ++e) {
-#pragma unroll
-      for (int w = 0; w < NW; ++w) wd[e][w] = wnext[e][w];
-      av[e] = AUX ? __ldg(aux + c0 + e) : 0.0;
-    }
-    if (c0 + NB < c_end) {
-#pragma unroll
-      for (int e = 0; e < NB; ++e)
-#pragma unroll
-        for (int w = 0; w < NW; ++w) wnext[e][w] = __ldg(pack + (size_t)(c0 + NB + e) * NW + w);
-    }
-    double v[NB];
-#pragma unroll
-    for (int e = 0; e < NB; ++e) {
-      if constexpr (G > 1) {
-        // does any key position 0 .. G-2 differ from the previous column?  (the last position is byte 3 - (G-1) % 4 of the last word)
-        bool lead_changed = (c0 + e == c_begin);
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t x = wd[e][w] ^ prev[w];
-          if (w == NW - 1) x &= ~(0xFFu << (8 * (3 - ((G - 1) & 3))));
-          lead_changed |= (x != 0);
-        }
-        if (lead_changed) {
-          double q = trow[pack_slot<G>(wd[e], 0)];
-#pragma unroll
-          for (int g = 1; g < G - 1; ++g) q *= trow[pack_slot<G>(wd[e], g)];
-          P = q;
-        }
-        v[e] = P * trow[pack_slot<G>(wd[e], G - 1)];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) prev[w] = wd[e][w];
-      } else {
-        v[e] = trow[pack_slot<G>(wd[e], 0)];
-      }
-    }
-    emit(c0, v, av);
-  }
-}
 
-// Phi slab, row-major [row][sorted column], one CTA per 128 table rows.  Lane = data row: warp w works on row group w & 3 (32 rows)
-// and on the column quarter w >> 2, walking its columns with the shared prefix product (walk_sorted_columns: ~1.3 gathers and DMULs
-// per element instead of G).  A lane holds 16 consecutive columns of its row at a time and writes 16 contiguous bytes per digit
-// plane (DIG) or 128 contiguous bytes (FP64).
+// Phi slab, row-major [row][sorted column], one CTA per 128 table rows.  A lane owns FOUR consecutive sorted columns (one 16-byte
+// load brings their packed slots), a warp 8 rows: per row and digit plane the lane stores one 32-bit word and the warp 128 contiguous
+// bytes (FP64 mode: 1 KB).  Consecutive sorted columns mostly share their leading slots, so columns 1..3 of a lane reuse the prefix
+// product of their predecessor when the packed words agree above the last key position.
 //   DIG = false: out[row * ldo + c]
-//   DIG = true:  first sweep -> row maximum -> exps[row]; second sweep -> planes[s][row][c], scaled by 2^(8 sd - 2 - exps[row]).
-//                row_hi != nullptr: the row maxima are already known (the pass-1 builder of the same tables recorded them,
-//                k_build_phi_t) and the first sweep is skipped.
+//   DIG = true:  planes[s][row][c], scaled by 2^(8 sd - 2 - exps[row]).  The row scale needs max_c |Phi[row][c]|: taken from
+//                row_hi (recorded by the pass-1 builder of the same tables, k_build_phi_t) or, without it, from a first sweep.
 // bvec != nullptr: f[row] = sum_c Phi[row][c] * bvec[c] is accumulated along the way (the values are in registers) and
 // a_out[row] = (y[row] - f[row]) * inv_noise is written -- the residual scaled by the noise that the contraction kernel needs
-// (grad.cu); column quarters are summed in fixed order.
+// (grad.cu); lanes are summed by butterfly (fixed order).
 template <int G, bool DIG>
 __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __restrict__ T, int stride,
                                                              const uint32_t* __restrict__ pack, int p_pad,
@@ -348,95 +285,129 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_phi(const double* __res
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sT = reinterpret_cast<double*>(smem_raw + 128);
-  double* s_f = sT + (size_t)kBuildRows * stride;                     // [4 quarters][128 rows]
-  int* s_hi = reinterpret_cast<int*>(s_f + 4 * kBuildRows);           // [4 quarters][128 rows]
   init_stage_barrier(bar);
   stage_table_rows(sT, bar, T, stride, blockIdx.x, 0);
+  constexpr int NW = (G + 3) / 4;
+  constexpr int RW = kBuildRows / (kBuildThreads / 32);                // 8 rows per warp
+  constexpr uint32_t kLastMask = 0xFFu << (8 * (3 - ((G - 1) & 3)));   // the last key position inside the last packed word
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rg = warp & 3, quarter = warp >> 2;
-  const int r_blk = rg * 32 + lane;
-  const double* trow = sT + (size_t)r_blk * stride;
-  const size_t grow = (size_t)blockIdx.x * kBuildRows + r_blk;
-  const int cq = p_pad / 4;                                           // p_pad is a multiple of 128
-  const int c_begin = quarter * cq, c_end = c_begin + cq;
-  constexpr int NB1 = 8;                                              // sweep 1 keeps values, b and their prefetch in registers
-  constexpr int NB = DIG ? 16 : 8;                                    // sweep 2: 16 columns = 16 bytes per digit plane and lane
+  const double* tbase = sT + (size_t)warp * RW * stride;
+  const size_t row0 = (size_t)blockIdx.x * kBuildRows + warp * RW;
   const bool want_f = bvec != nullptr;
-  const bool f_in_sweep2 = want_f && (!DIG || row_hi != nullptr);
-  double scale = 1.0, f = 0.0;
-  if (DIG && row_hi != nullptr) {                                     // row maxima recorded by pass 1: no first sweep
-    const int mh = __ldg(row_hi + grow);
-    const int e = exp_from_hi(mh);
-    if (quarter == 0) {
-      exps[grow] = e;
-      if (mh >= 0x7ff00000) atomicExch(err, 4);
-    }
-    scale = digit_scale(sd, e);
-  } else if (DIG) {                                                   // sweep 1: row maximum (and f)
-    int hi = 0;
-    auto sweep1 = [&](int, const double (&v)[NB1], const double (&bv)[NB1]) {      // bv is all zero without bvec
+
+  // values of this lane's four columns for table row `trow`; slots come from the packed words wd[q][w]
+  auto four_values = [&](const double* trow, const uint32_t (&wd)[4][NW], double (&v)[4]) {
+    double P = 1.0;
 #pragma unroll
-      for (int e = 0; e < NB1; ++e) hi = max(hi, abs_hi(v[e]));
-      if (want_f) {
+    for (int q = 0; q < 4; ++q) {
+      if constexpr (G > 1) {
+        bool reuse = q > 0;
+        if (q > 0) {
 #pragma unroll
-        for (int e = 0; e < NB1; ++e) f = fma(v[e], bv[e], f);
+          for (int w = 0; w < NW; ++w) {
+            uint32_t x = wd[q][w] ^ wd[q - 1][w];
+            if (w == NW - 1) x &= ~kLastMask;
+            reuse = reuse && (x == 0);
+          }
+        }
+        if (!reuse) {
+          P = trow[pack_slot<G>(wd[q], 0)];
+#pragma unroll
+          for (int g = 1; g < G - 1; ++g) P *= trow[pack_slot<G>(wd[q], g)];
+        }
+        v[q] = P * trow[pack_slot<G>(wd[q], G - 1)];
+      } else {
+        v[q] = trow[pack_slot<G>(wd[q], 0)];
       }
-    };
-    if (want_f) walk_sorted_columns<G, NB1, true>(trow, pack, bvec, c_begin, c_end, sweep1);
-    else walk_sorted_columns<G, NB1, false>(trow, pack, nullptr, c_begin, c_end, sweep1);
-    s_hi[quarter * kBuildRows + r_blk] = hi;
-    __syncthreads();
-    int mh = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) mh = max(mh, s_hi[q * kBuildRows + r_blk]);
-    const int e = exp_from_hi(mh);
-    if (quarter == 0) {
-      exps[grow] = e;
-      if (mh >= 0x7ff00000) atomicExch(err, 4);                       // Inf / NaN in the row
-    }
-    scale = digit_scale(sd, e);
-  }
-  auto sweep2 = [&](int c0, const double (&v)[NB], const double (&bv)[NB]) {
-    if (f_in_sweep2) {
-#pragma unroll
-      for (int e = 0; e < NB; ++e) f = fma(v[e], bv[e], f);
-    }
-    if constexpr (!DIG) {
-      double2* dst = reinterpret_cast<double2*>(out + grow * ldo + c0);
-#pragma unroll
-      for (int e = 0; e < NB; e += 2) dst[e >> 1] = make_double2(v[e], v[e + 1]);
-    } else {
-      unsigned long long w[NB];
-#pragma unroll
-      for (int e = 0; e < NB; ++e) w[e] = digit_word(v[e], scale, sd);
-      int8_t* base = planes + grow * (size_t)p_pad + c0;
-#define GRIEF_PLANE(S_, B_)                                                                                                        \
-  do {                                                                                                                             \
-    uint4 q4;                                                                                                                      \
-    { const unsigned long long t4[4] = {w[0], w[1], w[2], w[3]}; q4.x = gather_byte<B_>(t4); }                                    \
-    { const unsigned long long t4[4] = {w[4], w[5], w[6], w[7]}; q4.y = gather_byte<B_>(t4); }                                    \
-    { const unsigned long long t4[4] = {w[8], w[9], w[10], w[11]}; q4.z = gather_byte<B_>(t4); }                                  \
-    { const unsigned long long t4[4] = {w[12], w[13], w[14], w[15]}; q4.w = gather_byte<B_>(t4); }                                \
-    *reinterpret_cast<uint4*>(base + (size_t)(S_) * plane_stride) = q4;                                                           \
-  } while (0)
-      GRIEF_PLANE(0, 6);
-      GRIEF_PLANE(1, 5);
-      GRIEF_PLANE(2, 4);
-      if (sd > 3) GRIEF_PLANE(3, 3);
-      if (sd > 4) GRIEF_PLANE(4, 2);
-      if (sd > 5) GRIEF_PLANE(5, 1);
-      if (sd > 6) GRIEF_PLANE(6, 0);
-#undef GRIEF_PLANE
     }
   };
-  if (f_in_sweep2) walk_sorted_columns<G, NB, true>(trow, pack, bvec, c_begin, c_end, sweep2);
-  else walk_sorted_columns<G, NB, false>(trow, pack, nullptr, c_begin, c_end, sweep2);
-  if (want_f) {                                                       // warp-uniform
-    s_f[quarter * kBuildRows + r_blk] = f;
-    __syncthreads();
-    if (quarter == 0) {
-      const double ft = ((s_f[r_blk] + s_f[kBuildRows + r_blk]) + s_f[2 * kBuildRows + r_blk]) + s_f[3 * kBuildRows + r_blk];
-      a_out[grow] = (int64_t)grow < y_rows ? (y[grow] - ft) * inv_noise : 0.0;
+  auto load_words = [&](int cbase, uint32_t (&wd)[4][NW]) {
+    const uint4* src = reinterpret_cast<const uint4*>(pack + (size_t)(cbase + 4 * lane) * NW);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {                                     // 4 columns x NW words = NW 16-byte loads
+      const uint4 t = __ldg(src + i);
+      const uint32_t flat[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wd[(4 * i + j) / NW][(4 * i + j) % NW] = flat[j];
+    }
+  };
+
+  double scale[RW];
+  if constexpr (DIG) {
+    int mh[RW];
+    if (row_hi != nullptr) {
+#pragma unroll
+      for (int r = 0; r < RW; ++r) mh[r] = __ldg(row_hi + row0 + r);
+    } else {                                                           // first sweep: row maxima
+#pragma unroll
+      for (int r = 0; r < RW; ++r) mh[r] = 0;
+      for (int cbase = 0; cbase < p_pad; cbase += 128) {
+        uint32_t wd[4][NW];
+        load_words(cbase, wd);
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          double v[4];
+          four_values(tbase + (size_t)r * stride, wd, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mh[r] = max(mh[r], abs_hi(v[q]));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RW; ++r) mh[r] = __reduce_max_sync(0xffffffffu, mh[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const int e = exp_from_hi(mh[r]);
+      if (lane == 0) {
+        exps[row0 + r] = e;
+        if (mh[r] >= 0x7ff00000) atomicExch(err, 4);                   // Inf / NaN in the row
+      }
+      scale[r] = digit_scale(sd, e);
+    }
+  }
+  double facc[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) facc[r] = 0.0;
+  for (int cbase = 0; cbase < p_pad; cbase += 128) {
+    uint32_t wd[4][NW];
+    load_words(cbase, wd);
+    double bq[4] = {0.0, 0.0, 0.0, 0.0};
+    if (want_f) {
+      const double2* bsrc = reinterpret_cast<const double2*>(bvec + cbase + 4 * lane);
+      const double2 b01 = __ldg(bsrc), b23 = __ldg(bsrc + 1);
+      bq[0] = b01.x; bq[1] = b01.y; bq[2] = b23.x; bq[3] = b23.y;
+    }
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      double v[4];
+      four_values(tbase + (size_t)r * stride, wd, v);
+      if (want_f) facc[r] = fma(v[3], bq[3], fma(v[2], bq[2], fma(v[1], bq[1], fma(v[0], bq[0], facc[r]))));
+      if constexpr (!DIG) {
+        double2* dst = reinterpret_cast<double2*>(out + (row0 + r) * ldo + cbase + 4 * lane);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+      } else {
+        unsigned long long w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = digit_word(v[q], scale[r], sd);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(planes + (row0 + r) * (size_t)p_pad + cbase) + lane;
+        const size_t ps4 = plane_stride / 4;
+        dst[0 * ps4] = gather_byte<6>(w);
+        dst[1 * ps4] = gather_byte<5>(w);
+        dst[2 * ps4] = gather_byte<4>(w);
+        if (sd > 3) dst[3 * ps4] = gather_byte<3>(w);
+        if (sd > 4) dst[4 * ps4] = gather_byte<2>(w);
+        if (sd > 5) dst[5 * ps4] = gather_byte<1>(w);
+        if (sd > 6) dst[6 * ps4] = gather_byte<0>(w);
+      }
+    }
+  }
+  if (want_f) {                                                        // warp-uniform
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const double ft = warp_sum(facc[r]);
+      const size_t grow = row0 + r;
+      if (lane == 0) a_out[grow] = (int64_t)grow < y_rows ? (y[grow] - ft) * inv_noise : 0.0;
     }
   }
 }
@@ -456,8 +427,7 @@ struct BuildArgs {
 
 template <int G>
 static int launch_build_g(const Plan* pl, const double* T, int64_t rows, const BuildArgs& a, cudaStream_t stream) {
-  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double) +
-                      (a.transposed ? kBuildRows * sizeof(int) : 4 * kBuildRows * (sizeof(double) + sizeof(int)));
+  const size_t smem = 128 + (size_t)kBuildRows * pl->stride * sizeof(double) + (a.transposed ? kBuildRows * sizeof(int) : 0);
   const unsigned grid = (unsigned)(rows / kBuildRows);
   GRIEF_REQUIRE(smem <= 227 * 1024, "build_phi: %zu bytes of shared memory", smem);
 #define GRIEF_BT(DIG_)                                                                                                              \
