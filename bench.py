@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--no-peaks", action="store_true", help="skip the in-run DGEMM / int8 GEMM peak measurement")
     ap.add_argument("--oracle-rows", type=int, default=1 << 15, help="rows of the oracle parity sample (<= 2e5)")
     ap.add_argument("--predict-rows", type=int, default=-1, help="rows of the prediction leg (-1: 100000 for C5, else 0)")
-    ap.add_argument("--gemm", default="int8", choices=["int8", "int8x2", "fp64"],
-                    help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores or the FP64 DMMA GEMM")
+    ap.add_argument("--gemm", default="int8", choices=["int8", "int8x2", "int8x1", "fp64"],
+                    help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores (int8 = int8x2: CTA pairs, the library "
+                         "default; int8x1: one CTA per tile) or the FP64 DMMA GEMM")
     ap.add_argument("--digits", default="", help="'Dgram,Dz': int8 digits per operand of the two products (default: library defaults)")
     ap.add_argument("--slab-mb", type=int, default=0, help="HBM budget (MiB) of the Phi^T slab staged per pass-1 GEMM launch (0: library default 1024)")
     ap.add_argument("--power-trace", default="", help="write the clock / power samples of the timed region to this JSON file")
@@ -295,7 +296,7 @@ def run_ours(args):
     if args.rows:
         n_total = int(args.rows)
     lib = nat.lib()
-    mode_id = {"int8": 1, "int8x2": 3, "fp64": 0}[args.gemm]
+    mode_id = {"int8": 3, "int8x2": 3, "int8x1": 1, "fp64": 0}[args.gemm]
     nat.check(lib.grief_set_default_option(nat.OPT_GEMM_MODE, mode_id))
     if args.digits:
         dg, dz = [int(t) for t in args.digits.split(",")]
@@ -542,7 +543,7 @@ def run_ours(args):
     # work actually issued by the GEMM launches (padded rows / columns, full diagonal tiles)
     flops = {"k_zgemm": 2.0 * rows128 * p_pad * p_pad, "k_gram": float(rows128) * p_pad * (p_pad + 128)}
     digits_of = {"k_zgemm": dz, "k_gram": dg}
-    gk = {"int8": "k_ozaki<1,D>", "int8x2": "k_ozaki<2,D> (cta_group::2 pairs)", "fp64": "k_gemm_nt"}[args.gemm]
+    gk = {"int8": "k_ozaki<2,D> (cta_group::2 pairs)", "int8x2": "k_ozaki<2,D> (cta_group::2 pairs)", "int8x1": "k_ozaki<1,D>", "fp64": "k_gemm_nt"}[args.gemm]
     label = {"k_zgemm": gk + " [Z = Phi*P^-1, pass 2]", "k_gram": gk + " [A = Phi^T Phi, lower tiles, split K]",
              "k_build_phi": "k_build_phi (+ row maxima, fused residual a = (y - Phi b) / noise) [Phi slab, pass 2]", "k_build_phi_t": "k_build_phi_t (+ slot maxima, fused Phi^T y) [Phi^T slab, pass 1]",
              "solve": "dense p x p stage (k_potf2_inv, k_gemm_nt, k_trsv_step, k_assemble, ...)",
@@ -564,8 +565,9 @@ def run_ours(args):
     gemm_rows = [r for r in kern_rows if r["slot"] in flops]
     dom = max(gemm_rows, key=lambda r: r["ms_total"]) if gemm_rows else None
     traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["k_ozaki_zgemm" if i8 else "k_gemm_nt_zgemm"]
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the same launch shape
+        key = ("k_ozaki_" if i8 else "k_gemm_nt_") + ("zgemm" if dom["slot"] == "k_zgemm" else "gram")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))[key]
         if tr["config"] == cfg:
             traffic = {"bytes_per_launch": tr["dram_bytes_read"] + tr["dram_bytes_write"], "rows_per_launch": tr["rows_per_launch"],
                        "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "source": tr["source"]}
@@ -595,7 +597,7 @@ def run_ours(args):
                 except Exception:
                     peak_i8, src = 4500.0, "nominal dense INT8 4.5 POP/s (MEASURED_PEAKS.json missing)"
             roofline = dict(common, bound="tensor",
-                            kernel="k_ozaki (tcgen05 kind::i8, TMEM accumulators, TMA digit planes): %s as %d exact int8 x int8 -> int32 digit "
+                            kernel=gk + " (tcgen05 kind::i8, TMEM accumulators, TMA digit planes): %s as %d exact int8 x int8 -> int32 digit "
                                    "GEMMs (%d digits per operand); digit planes written straight from the tables by the slab builders"
                                    % ("Z = Phi*P^-1 for pass 2, one launch per slab of 37888 rows" if dom["slot"] == "k_zgemm" else
                                       "A = Phi^T Phi for pass 1, one launch per slab", dom["int8_digit_products"], digits_of[dom["slot"]]),

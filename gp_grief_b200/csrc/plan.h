@@ -37,7 +37,7 @@ void grad_desc_destroy(GradDesc* gd);
 // defaults when the plan is created, changed with grief_plan_set_option): nothing here is process-global.
 struct PlanOpts {
   int gemm_mode = 1;                       // 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki)
-  int cluster = 0;                         // INT8 mode: CTA pairs (cta_group::2)
+  int cluster = 1;                         // INT8 mode: CTA pairs (cta_group::2, 256 x 128 tiles): the default since round 2
   int digits_gram = 6;                     // INT8 digits per operand of A = Phi^T Phi (46-bit operands + the diagonal pair, ozaki.cu)
   int digits_z = 4;                        // INT8 digits per operand of Zp = Phi P^-1 in the gradient pass (30-bit; the rank-one part is FP64)
   int digits_var = 6;                      // INT8 digits per operand of Z = Phi B in grief_quadform_rows (predictive variance)

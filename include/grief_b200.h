@@ -62,9 +62,10 @@ void grief_launch_count_reset(void);
 
 /*
  * Optional per-kernel timing for benchmarks: CUDA events are recorded on the launch stream around the kernels
- * of each slot.  Slots (grief_profile_slots() = 10): 0 Gram GEMM (pass 1), 1 Phi*B GEMM (pass 2), 2 table prepass, 3 gradient
- * contraction, 4 top-p select, 5 p x p stage, 6 stand-alone Phi^T v, 7 derivative tables, 8 Phi^T slab builder (pass 1, incl. the
- * fused Phi^T y), 9 Phi slab builder (pass 2).  grief_profile_read synchronises,
+ * of each slot.  Slots (grief_profile_slots() = 10): 0 Gram GEMM (pass 1), 1 Phi*B GEMM (pass 2), 2 table prepass, 3 backward
+ * sweep of the gradient pass (k_contract_back), 4 top-p select, 5 p x p stage, 6 stand-alone Phi^T v, 7 gradient tail (K_xu / F buffer +
+ * k_contract_tail), 8 Phi^T slab builder (pass 1, incl. the fused Phi^T y and the row maxima), 9 Phi slab builder (pass 2, incl. the
+ * fused residual).  grief_profile_read synchronises,
  * writes the accumulated milliseconds and launch counts of every slot (arrays of grief_profile_slots()) and resets.
  */
 void grief_profile_enable(int on);
@@ -162,12 +163,13 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
  * Workspace sizes depend on the options: query them after changing one.
  *   GRIEF_OPT_GEMM_MODE    arithmetic:
  *       0  FP64 DMMA GEMM (k_gemm_nt), 36 TFLOP/s
- *       1  (default) FP64 emulated on the INT8 tensor cores (tcgen05 kind::i8): every operand row is scaled by a power of two and cut
+ *       1  FP64 emulated on the INT8 tensor cores (tcgen05 kind::i8): every operand row is scaled by a power of two and cut
  *          into D balanced 8-bit digits (8 D - 2 bits + sign, round to nearest); D (D + 1) / 2 exact int8 x int8 -> int32 digit
  *          products; element errors are bounded by ~2^(1 - 8 D) of the product of the operands' row maxima times K
- *          (D = 7: the accuracy class of DGEMM)
- *       3  as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2; correct and
- *          tested, not faster on a power-capped B200
+ *          (D = 7: the accuracy class of DGEMM); one CTA per 128 x 128 tile
+ *       3  (default) as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2:
+ *          each CTA stages half of the B digits, a quarter less L2 -> SM traffic per MMA.  Same arithmetic, bit-identical results;
+ *          +12 % (Gram) / +5 % (Phi P^-1) at the round-2 digit counts (round 1, 7 digits: no gain under the power cap)
  *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (3..7, default 6: 46-bit operands, 22 digit products).  A feeds a Cholesky
  *                          factorisation; measured against the FP64 mode at n = 10^6..10^7, p = 4096: LML identical to 1e-15 with
  *                          D = 6 and D = 7, 1.5e-13 with D = 5

@@ -1,5 +1,5 @@
-"""Both arithmetic modes of the O(n p^2) products must pass the same parity tests: the main suite runs in the library default
-(INT8 tensor cores, mode 1); this file re-runs the parity subset with each mode selected explicitly."""
+"""All arithmetic modes of the O(n p^2) products must pass the same parity tests: the main suite runs in the library default
+(INT8 tensor cores with CTA pairs, mode 3); this file re-runs the parity subset with each mode selected explicitly."""
 import pytest
 
 from conftest import model_cases
@@ -12,16 +12,17 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=[1, 0, 3], ids=["int8", "fp64", "int8-cluster"])
 def int8_mode(request):
-    before = nat.lib().grief_get_gemm_mode()
+    before = nat.lib().grief_get_default_option(nat.OPT_GEMM_MODE)
     nat.lib().grief_set_gemm_mode(request.param)
     try:
         yield request.param
     finally:
-        nat.lib().grief_set_gemm_mode(before)
+        nat.check(nat.lib().grief_set_default_option(nat.OPT_GEMM_MODE, before))
 
 
 def test_default_mode_is_int8():
-    assert nat.lib().grief_get_gemm_mode() == 1
+    assert nat.lib().grief_get_gemm_mode() == 1                                    # INT8 arithmetic ...
+    assert nat.lib().grief_get_default_option(nat.OPT_GEMM_MODE) == 3              # ... on CTA pairs
 
 
 @pytest.mark.gpu

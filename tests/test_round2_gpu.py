@@ -136,7 +136,7 @@ def test_options_are_per_plan_not_process_wide():
     before = nat.lib().grief_get_default_option(nat.OPT_GEMM_MODE)
     plan_a.set_option(nat.OPT_GEMM_MODE, 0)
     plan_a.set_option(nat.OPT_DIGITS_GRAM, 5)
-    assert plan_b.get_option(nat.OPT_GEMM_MODE) == before == 1          # neither the other plan nor the defaults moved
+    assert plan_b.get_option(nat.OPT_GEMM_MODE) == before == 3          # neither the other plan nor the defaults moved
     assert plan_b.get_option(nat.OPT_DIGITS_GRAM) == 6
     assert nat.lib().grief_get_default_option(nat.OPT_DIGITS_GRAM) == 6
     n = 5000
@@ -233,7 +233,7 @@ def test_arithmetic_audit_accepts_the_defaults_and_escalates_when_asked(caplog):
     assert m3.arithmetic_audit is None
 
 
-@pytest.mark.parametrize("mode", [1, 0], ids=["int8", "fp64"])
+@pytest.mark.parametrize("mode", [3, 1, 0], ids=["int8-pairs", "int8", "fp64"])
 def test_row_maxima_from_pass_1_give_identical_gradient(mode):
     """grief_gram_ry can record max_j |Phi[row, j]| (every element passes through its registers); grief_grad_theta then skips its
     own maximum sweep.  The digit planes, hence the gradient, must be bit-identical either way."""
@@ -241,6 +241,7 @@ def test_row_maxima_from_pass_1_give_identical_gradient(mode):
     g = load_golden("syn_t2_n2000_d4_m8_p64")
     m = ta.build_model(g)
     m.audit_rows = 0
+    before = nat.lib().grief_get_default_option(nat.OPT_GEMM_MODE)
     nat.check(nat.lib().grief_set_default_option(nat.OPT_GEMM_MODE, mode))
     try:
         m.kern._plan = None
@@ -262,4 +263,4 @@ def test_row_maxima_from_pass_1_give_identical_gradient(mode):
         g_one_sweep = plan.grad_theta(*args, rowmax=rowmax).cpu().numpy()
         assert_array_equal(g_one_sweep, g_two_sweeps)
     finally:
-        nat.check(nat.lib().grief_set_default_option(nat.OPT_GEMM_MODE, 1))
+        nat.check(nat.lib().grief_set_default_option(nat.OPT_GEMM_MODE, before))
