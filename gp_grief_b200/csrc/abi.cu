@@ -200,8 +200,8 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
 static int set_opt(PlanOpts& o, int what, int64_t value) {
   switch (what) {
     case GRIEF_OPT_GEMM_MODE:
-      GRIEF_REQUIRE(value == 0 || value == 1 || value == 3, "option gemm_mode: %lld is not 0, 1 or 3", (long long)value);
-      o.gemm_mode = (int)(value & 1); o.cluster = (int)((value >> 1) & 1);
+      GRIEF_REQUIRE(value == 0 || value == 1 || value == 3 || value == 5, "option gemm_mode: %lld is not 0, 1, 3 or 5", (long long)value);
+      o.gemm_mode = (int)(value & 1); o.cluster = value == 3 ? 1 : (value == 5 ? 2 : 0);
       return GRIEF_OK;
     case GRIEF_OPT_DIGITS_GRAM:
     case GRIEF_OPT_DIGITS_Z:
@@ -218,7 +218,7 @@ static int set_opt(PlanOpts& o, int what, int64_t value) {
 }
 static int64_t get_opt(const PlanOpts& o, int what) {
   switch (what) {
-    case GRIEF_OPT_GEMM_MODE: return o.gemm_mode | (o.cluster << 1);
+    case GRIEF_OPT_GEMM_MODE: return o.gemm_mode | (o.cluster == 1 ? 2 : (o.cluster == 2 ? 4 : 0));
     case GRIEF_OPT_DIGITS_GRAM: return o.digits_gram;
     case GRIEF_OPT_DIGITS_Z: return o.digits_z;
     case GRIEF_OPT_DIGITS_VAR: return o.digits_var;

@@ -16,7 +16,7 @@
 // K = 32), warps 0-3 drain TMEM: tcgen05.ld -> f64 -> sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared
 // memory -> added to C.  The six tensor maps travel as __grid_constant__ kernel parameters (no descriptor is ever re-written in
 // global memory).  Tiles are rasterised in groups of `group_n` column tiles so that the B digits of a group stay L2-resident while
-// all row tiles pass.  k_ozaki<2, SD> computes 256 x 128 tiles with CTA pairs and tcgen05.mma.cta_group::2 (see the template comment).
+// all row tiles (or row-tile pairs) pass.  k_ozaki<2, SD> computes 256 x 128 tiles with CTA pairs and tcgen05.mma.cta_group::2 (see the template comment).
 // Measured (B200, pass-2 shape 37888 x 4096 x 4096): 14.4 ms = 88 TFLOP/s FP64-equivalent alone, 81 inside the benchmark (power
 // cap), against 35 for cuBLAS DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
 // Variants measured and not adopted (profiles/r01_gram_design_notes.md): 128 x 256 tiles with two accumulators and five work
@@ -170,6 +170,18 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
     const int within = L - grp * per_group;
     bm = within / gw;
     bn = first + (within - bm * gw);
+  }
+  if (CL == 2 && prm.group_n > 0) {                  // the same for CTA pairs: a pair (adjacent in x) walks the column tiles of a group
+    const int npairs = gridDim.x >> 1, tiles_n = gridDim.y;
+    const int L = (int)blockIdx.y * npairs + ((int)blockIdx.x >> 1);      // cluster id in launch order
+    const int per_group = prm.group_n * npairs;
+    const int grp = L / per_group;
+    const int first = grp * prm.group_n;
+    const int gw = min(prm.group_n, tiles_n - first);
+    const int within = L - grp * per_group;
+    const int pm = within / gw;
+    bn = first + (within - pm * gw);
+    bm = 2 * pm + ((int)blockIdx.x & 1);
   }
   if (prm.lower_only && bn > (CL == 2 ? (bm | 1) : bm)) return;      // uniform over the cluster
   uint32_t crank = 0;
@@ -488,9 +500,11 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
     const int gmax = (int)std::max<int64_t>(1, ((int64_t)60 << 20) / panel);
     const int ngroups = (tiles_n + gmax - 1) / gmax;
     prm.group_n = (tiles_n + ngroups - 1) / ngroups;
-    if (prm.group_n >= tiles_n) prm.group_n = 0;
   }
-  const bool pairs = opt.cluster && tiles_m >= 2;     // CTA pairs adjacent in x (cluster (2,1,1)); an odd last pair runs one CTA on zero rows
+  // CTA pairs adjacent in x (cluster (2,1,1)); an odd last pair runs one CTA on zero rows.  Pairs pay off on large grids (C3, C4, C5:
+  // +5..16 %); on a few tiles (C2: p = 1024, 8 x 8) the coarser tiles cost more in wave quantisation than they save in L2 traffic.
+  const bool pairs = tiles_m >= 2 && (opt.cluster == 2 || (opt.cluster == 1 && std::min(tiles_m, tiles_n) >= 16));
+  if (!pairs && prm.group_n >= tiles_n) prm.group_n = 0;      // one group = plain order (single CTAs: x already walks the column tiles)
   const dim3 grid = pairs ? dim3((tiles_m + 1) / 2 * 2, tiles_n, splits) : dim3(tiles_n, tiles_m, splits);
   int rc;
 #define GRIEF_OZ(SD_, GT_)                                                                                         \

@@ -37,7 +37,8 @@ void grad_desc_destroy(GradDesc* gd);
 // defaults when the plan is created, changed with grief_plan_set_option): nothing here is process-global.
 struct PlanOpts {
   int gemm_mode = 1;                       // 0: FP64 DMMA GEMM (k_gemm_nt), 1: INT8 tensor-core emulation (k_ozaki)
-  int cluster = 1;                         // INT8 mode: CTA pairs (cta_group::2, 256 x 128 tiles): the default since round 2
+  int cluster = 1;                         // INT8 mode, CTA pairs (cta_group::2, 256 x 128 tiles): 0 never, 1 (default) where both tile
+                                           // counts are >= 16, 2 wherever there are two row tiles
   int digits_gram = 6;                     // INT8 digits per operand of A = Phi^T Phi (46-bit operands + the diagonal pair, ozaki.cu)
   int digits_z = 4;                        // INT8 digits per operand of Zp = Phi P^-1 in the gradient pass (30-bit; the rank-one part is FP64)
   int digits_var = 6;                      // INT8 digits per operand of Z = Phi B in grief_quadform_rows (predictive variance)
@@ -108,7 +109,7 @@ int gemm_nt_ex(const double* A, int64_t lda, const double* B, int64_t ldb, doubl
 constexpr int kOzMinDigits = 3, kOzMaxDigits = 7;
 struct OzOpts {
   int digits = kOzMaxDigits;   // balanced 8-bit digits per operand: 8 * digits - 2 bits + sign below the row maximum
-  int cluster = 0;             // 1: CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles
+  int cluster = 0;             // CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles: 0 never, 1 for >= 16 x 16 tiles, 2 always
   int store_t = 0;             // 1: C is written transposed (element (m, n) at C[n * ldc + m])
   int diag_pair = 0;           // 1: both operands are the same matrix (Gram): keep the pair a = b = digits / 2 of group g = digits
   int* err = nullptr;          // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value

@@ -167,9 +167,11 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
  *          into D balanced 8-bit digits (8 D - 2 bits + sign, round to nearest); D (D + 1) / 2 exact int8 x int8 -> int32 digit
  *          products; element errors are bounded by ~2^(1 - 8 D) of the product of the operands' row maxima times K
  *          (D = 7: the accuracy class of DGEMM); one CTA per 128 x 128 tile
- *       3  (default) as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2:
- *          each CTA stages half of the B digits, a quarter less L2 -> SM traffic per MMA.  Same arithmetic, bit-identical results;
- *          +12 % (Gram) / +5 % (Phi P^-1) at the round-2 digit counts (round 1, 7 digits: no gain under the power cap)
+ *       3  (default) as 1, with CTA pairs (thread-block clusters of 2) computing 256 x 128 tiles through tcgen05.mma.cta_group::2
+ *          wherever the product has at least 16 x 16 tiles (p >= 2048): each CTA stages half of the B digits, a quarter less
+ *          L2 -> SM traffic per MMA.  Same arithmetic, bit-identical results; +12 % (Gram) / +5 % (Phi P^-1) at C3 and +16 % at
+ *          p = 8192 with the round-2 digit counts (round 1, 7 digits: no gain under the power cap); smaller products keep mode 1
+ *       5  as 3, with CTA pairs for every product with at least two row tiles (testing)
  *   GRIEF_OPT_DIGITS_GRAM  D of A = Phi^T Phi (3..7, default 6: 46-bit operands, 22 digit products).  A feeds a Cholesky
  *                          factorisation; measured against the FP64 mode at n = 10^6..10^7, p = 4096: LML identical to 1e-15 with
  *                          D = 6 and D = 7, 1.5e-13 with D = 5

@@ -10,7 +10,7 @@ import test_api_gpu as ta
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0, 3], ids=["int8", "fp64", "int8-cluster"])
+@pytest.fixture(params=[1, 0, 5], ids=["int8", "fp64", "int8-cluster"])       # 5: CTA pairs on every product (3 = only >= 16 x 16 tiles)
 def int8_mode(request):
     before = nat.lib().grief_get_default_option(nat.OPT_GEMM_MODE)
     nat.lib().grief_set_gemm_mode(request.param)

@@ -233,7 +233,7 @@ def test_arithmetic_audit_accepts_the_defaults_and_escalates_when_asked(caplog):
     assert m3.arithmetic_audit is None
 
 
-@pytest.mark.parametrize("mode", [3, 1, 0], ids=["int8-pairs", "int8", "fp64"])
+@pytest.mark.parametrize("mode", [5, 1, 0], ids=["int8-pairs", "int8", "fp64"])
 def test_row_maxima_from_pass_1_give_identical_gradient(mode):
     """grief_gram_ry can record max_j |Phi[row, j]| (every element passes through its registers); grief_grad_theta then skips its
     own maximum sweep.  The digit planes, hence the gradient, must be bit-identical either way."""
