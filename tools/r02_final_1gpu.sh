@@ -2,7 +2,7 @@
 # Round-2 evidence run on ONE B200: parity suite, the four 1-GPU bench lines (C3 with power trace, C2, C4, reference arm), launch list,
 # ncu --set full of every hot kernel (exported to CSV on the box).
 set -u
-O=gpurun_out/r02_final1b
+O=gpurun_out/r02_final1c
 mkdir -p $O
 nvidia-smi --query-gpu=name,power.limit,clocks.max.sm --format=csv > $O/gpu.txt 2>&1
 nproc > $O/host.txt; free -g >> $O/host.txt

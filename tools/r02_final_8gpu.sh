@@ -2,7 +2,7 @@
 # Round-2 evidence run on 8 B200s of one box: C5 (n = 50M, p = 8192, Type-I, predictive mean + variance at 100 000 rows) and C3 at N = 8;
 # the 2-GPU parity tests (torch.distributed and the library's own NCCL communicator).
 set -u
-O=gpurun_out/r02_final8b
+O=gpurun_out/r02_final8c
 mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv > $O/gpus.txt 2>&1
 timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q > $O/pytest_multi_gpu.log 2>&1
@@ -17,7 +17,7 @@ run bench_c5_n8 8 --config C5 --steps 2 --warmup 3
 run bench_c3_n8 8 --steps 3 --warmup 3
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob('gpurun_out/r02_final8b/bench*.json')):
+for f in sorted(glob.glob('gpurun_out/r02_final8c/bench*.json')):
     try:
         j=json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
