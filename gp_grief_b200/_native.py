@@ -66,6 +66,7 @@ SIGNATURES = {
     "grief_comm_destroy": (None, [c_void]),
     "grief_rowcol_kr_matvec": (c_int, [c_int, c_void, c_void, c_void, c_void, c_i64, c_i64, c_void, c_void, c_void]),
     "grief_gemm_nt": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
+    "grief_gemm_nt_t": (c_int, [c_void, c_i64, c_void, c_i64, c_void, c_i64, c_int, c_int, c_int, c_dbl, c_dbl, c_void]),
     "grief_solve_lml": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void, c_void, c_dbl, c_i64, c_void, c_void,
                                 c_void, c_void, c_void, c_void, _P(c_int), c_void]),
 }

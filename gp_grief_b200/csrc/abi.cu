@@ -46,7 +46,6 @@ struct ResidualArgs {      // optional by-product of the slab builder: a = (y - 
 };
 int launch_zgemm(const Plan* pl, const double* T_slab, int64_t slab_rows, const double* Bperm, void* scratch, int64_t slab_rows_max, double* Z,
                  int64_t ldz, int digits, const ResidualArgs* res, cudaStream_t stream, int* launches);
-int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream);
 struct Comm;
 int comm_unique_id(char* id_out);
 int comm_create(Comm** out, const char* id, int world, int rank);
@@ -431,6 +430,14 @@ int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t
   GRIEF_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N, "grief_gemm_nt: M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld",
                 M, N, K, (long long)lda, (long long)ldb, (long long)ldc);
   return gemm_nt(A_dev, lda, B_dev, ldb, C_dev, ldc, M, N, K, alpha, beta, false, false, (cudaStream_t)stream_, &g_launches, false);
+}
+
+int grief_gemm_nt_t(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* Ct_dev, int64_t ldct, int M, int N, int K,
+                    double alpha, double beta, void* stream_) {
+  GRIEF_REQUIRE(A_dev && B_dev && Ct_dev, "grief_gemm_nt_t: null pointer");
+  GRIEF_REQUIRE(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldct >= M, "grief_gemm_nt_t: M=%d N=%d K=%d lda=%lld ldb=%lld ldct=%lld",
+                M, N, K, (long long)lda, (long long)ldb, (long long)ldct);
+  return gemm_nt(A_dev, lda, B_dev, ldb, Ct_dev, ldct, M, N, K, alpha, beta, false, true, (cudaStream_t)stream_, &g_launches, false);
 }
 
 }  // extern "C"

@@ -79,56 +79,14 @@ int grad_desc_create(GradDesc** out, const Plan* pl, int n_active, const int32_t
 void grad_desc_destroy(GradDesc* gd) { delete gd; }
 int grad_desc_n_active(const GradDesc* gd) { return gd->n_active; }
 
-__global__ void k_scale_vec(const double* __restrict__ in, double scale, int n, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] * scale;
-}
-int launch_scale_vec(const double* in, double scale, int n, double* out, cudaStream_t stream) {
-  k_scale_vec<<<(n + 255) / 256, 256, 0, stream>>>(in, scale, n, out);
-  GRIEF_CUDA(cudaGetLastError());
-  return GRIEF_OK;
-}
-
-// kernel value and its lengthscale derivative (variance derivative is K / variance)
-__device__ __forceinline__ void kern_eval_d(int kernel, double x, double u, double variance, double ls, double& k,
-                                            double& dk_dls) {
-  const double diff = x - u;
-  const double d2 = diff * diff;
-  switch (kernel) {
-    case KERN_RBF: {
-      if (ls < 1e-6) { k = d2 == 0.0 ? variance : 0.0; dk_dls = 0.0; return; }
-      k = variance * exp(-0.5 * d2 / (ls * ls));
-      dk_dls = k * d2 / (ls * ls * ls);
-      return;
-    }
-    case KERN_EXPONENTIAL: {
-      const double r = sqrt(d2) / ls;
-      k = variance * exp(-r);
-      dk_dls = k * r / ls;
-      return;
-    }
-    case KERN_MATERN32: {
-      const double s3 = 1.7320508075688772;
-      const double r = sqrt(d2) / ls;
-      const double e = exp(-s3 * r);
-      k = variance * (1.0 + s3 * r) * e;
-      dk_dls = variance * 3.0 * r * r * e / ls;
-      return;
-    }
-    default: {
-      const double s5 = 2.23606797749979;
-      const double r2 = d2 / (ls * ls);
-      const double r = sqrt(r2);
-      const double e = exp(-s5 * r);
-      k = variance * (1.0 + s5 * r + (5.0 / 3.0) * r2) * e;
-      dk_dls = variance * e * (5.0 / 3.0) * r2 * (1.0 + s5 * r) / ls;
-      return;
-    }
-  }
-}
-
-// d k / d lengthscale from the kernel VALUE k (the tail kernel reads k from the K_xu buffer instead of evaluating exp again):
-// algebraic identities of the four formulas above
+// d k / d lengthscale from the kernel VALUE k (the tail kernel reads k from the K_xu buffer instead of evaluating exp again; the
+// variance derivative is k / variance).  With r = |x - u| / l:
+//   RBF          k = v exp(-r^2 / 2)                           dk/dl = k r^2 / l
+//   Exponential  k = v exp(-r)                                 dk/dl = k r / l
+//   Matern32     k = v (1 + s3 r) exp(-s3 r)                   dk/dl = v 3 r^2 exp(-s3 r) / l       = k 3 r^2 / ((1 + s3 r) l)
+//   Matern52     k = v (1 + s5 r + 5/3 r^2) exp(-s5 r)         dk/dl = v 5/3 r^2 (1 + s5 r) exp(-s5 r) / l
+//                                                                    = k 5/3 r^2 (1 + s5 r) / ((1 + s5 r + 5/3 r^2) l)
+// (kern/stationary.py:108-258 has the kernel formulas; the reference differentiates them numerically.)
 __device__ __forceinline__ double kern_dls_from_k(int kernel, double k, double x, double u, double ls) {
   const double diff = x - u;
   const double d2 = diff * diff;

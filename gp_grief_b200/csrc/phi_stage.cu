@@ -57,22 +57,6 @@ __device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7
 __device__ __forceinline__ int exp_from_hi(int hi) { return hi > 0 ? min(max((hi >> 20) - 1022, -900), 1024) : 0; }   // clamp: 2^(8 sd - 2 - e) stays finite
 // 2^(8 sd - 2 - e): multiplies a value below 2^e in magnitude into the range of sd digits
 __device__ __forceinline__ double digit_scale(int sd, int e) { return __hiloint2double((1023 + 8 * sd - 2 - e) << 20, 0); }
-// digits d_s of q = rint(v * scale), scale = 2^(8 sd - 2 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s), d_s in [-128, 127], s < sd.
-// Balanced base-256 digits without a carry chain: add 128 to every byte position (q + 0x80..80 is positive and below 2^(8 sd)),
-// then byte k of the sum, minus 128 (= XOR 0x80 read as int8), is the digit of 256^k.  Digit 0 (most significant) is moved to byte 6.
-__device__ __forceinline__ void store_digits(double v, double scale, int sd, int8_t* __restrict__ base, size_t plane_stride) {
-  const unsigned long long bias = 0x0080808080808080ull >> (8 * (7 - sd));
-  const unsigned long long w = (((unsigned long long)__double2ll_rn(v * scale) + bias) ^ bias) << (8 * (7 - sd));
-  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-  base[0 * plane_stride] = (int8_t)(hi >> 16);       // digit 0 = byte 6 (most significant)
-  base[1 * plane_stride] = (int8_t)(hi >> 8);
-  base[2 * plane_stride] = (int8_t)hi;
-  if (sd > 3) base[3 * plane_stride] = (int8_t)(lo >> 24);
-  if (sd > 4) base[4 * plane_stride] = (int8_t)(lo >> 16);
-  if (sd > 5) base[5 * plane_stride] = (int8_t)(lo >> 8);
-  if (sd > 6) base[6 * plane_stride] = (int8_t)lo;
-}
-
 // ---- exponents of the Phi^T operand rows (= basis columns) of a slab, without a pass over Phi ----
 // |Phi[n][c]| = prod_g |T[n][slot_g(c)]| <= prod_g max_n |T[n][slot_g(c)]|: one sweep over the slab's TABLE rows (stride doubles per
 // data row instead of p) gives per-slot maxima, and the product of a column's G maxima bounds the column.  The bound costs at
@@ -108,7 +92,10 @@ __global__ void k_col_exps(const int* __restrict__ slot_hi, const uint16_t* __re
   } else if (c < n_pad) exps[c] = 0;
 }
 
-// digits d_s of q = rint(v * scale) as bytes of one 64-bit word: digit s (0 = most significant) is byte 6 - s  (see store_digits)
+// digits d_s of q = rint(v * scale), scale = 2^(8 sd - 2 - e):  v 2^-e = sum_s d_s 2^(-6 - 8 s), d_s in [-128, 127], s < sd, as the bytes
+// of one 64-bit word: digit s (0 = most significant) is byte 6 - s.  Balanced base-256 digits without a carry chain: add 128 to every
+// byte position (q + 0x80..80 is positive and below 2^(8 sd)), then byte k of the sum, minus 128 (= XOR 0x80 read as int8), is the
+// digit of 256^k.
 // sd <= 6: |q| <= 2^46, so q is read off the mantissa of v * scale + 1.5 * 2^52 (one DFMA; the rounding to an integer is the
 // same round-to-nearest-even as the conversion instruction, which takes a trip through a slower pipe); sd = 7 converts.
 __device__ __forceinline__ unsigned long long digit_word(double v, double scale, int sd) {

@@ -247,7 +247,6 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   // ---- sorted column order for the tile builders ----
   std::vector<uint16_t> sorted_slot((size_t)pl->p_pad * G, 0);
   std::vector<uint8_t> sorted_level(pl->p_pad, 0);
-  std::vector<uint16_t> sorted_gslot((size_t)pl->p_pad * G, 0);     // sorted column -> slots in GROUP order
   pl->perm_h.assign(pl->p_pad, -1);
   {
     std::vector<int> key_order(G);                       // key position -> group (fewest distinct sub-tuples first)
@@ -265,7 +264,6 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
       const int j = c < p ? cols[c] : c;                 // padding columns keep their (all-constant) slots
       if (c < p) pl->perm_h[c] = j;
       for (int k = 0; k < G; ++k) sorted_slot[(size_t)c * G + k] = pl->col_slot_h[(size_t)j * G + key_order[k]];
-      for (int g = 0; g < G; ++g) sorted_gslot[(size_t)c * G + g] = pl->col_slot_h[(size_t)j * G + g];
       int lv = 0;
       if (c > 0) {
         lv = G;
@@ -298,7 +296,6 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   pool.add(&pl->d_col_slot, pl->col_slot_h);
   pool.add(&pl->d_sorted_slot, sorted_slot);
   pool.add(&pl->d_sorted_level, sorted_level);
-  pool.add(&pl->d_sorted_gslot, sorted_gslot);
   pool.add(&pl->d_sorted_pack, sorted_pack);
   pool.add(&pl->d_perm, pl->perm_h);
   pool.add(&pl->d_err, std::vector<int>(1, 0));

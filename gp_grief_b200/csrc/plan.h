@@ -74,7 +74,6 @@ struct Plan {
   // consecutive columns then share their leading slots and only the factors from `level` on are re-gathered.
   uint16_t* d_sorted_slot = nullptr;    // p_pad x G: slots of sorted column c, listed in key order
   uint8_t* d_sorted_level = nullptr;    // p_pad: first key position where sorted column c differs from c-1 (G: identical)
-  uint16_t* d_sorted_gslot = nullptr;   // p_pad x G: slots of sorted column c in GROUP order (consumers of Z, which is in sorted order)
   uint32_t* d_sorted_pack = nullptr;    // p_pad x pack_words: the key-order slots of sorted column c, one byte each, 4 per word (MSB first)
   int pack_words = 1;                   // (G + 3) / 4
   int* d_perm = nullptr;                // p_pad: external column of sorted column c (-1 for padding columns)

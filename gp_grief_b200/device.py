@@ -260,16 +260,21 @@ def kron_matvec(factors, x):
 
     factors: list of 2-D NumPy arrays, x: (N,) or (N, 1) NumPy array.  Returns a NumPy column vector.
     The running vector is kept as a (rest, cols_i) row-major matrix Yc (the memory image of the reference's F-ordered
-    reshape), factor i is applied as Yc @ K_i^T through grief_gemm_nt, and the result is transposed for the next factor.
+    reshape); factor i is applied as (Yc @ K_i^T)^T through grief_gemm_nt_t, whose transposed store leaves the result in the
+    layout the next factor needs -- each step reads and writes the running matrix once.
     """
     torch = _torch()
     y = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))).cuda()
     for Ki in reversed(list(factors)):
-        Kd = torch.as_tensor(np.ascontiguousarray(Ki, dtype=np.float64)).cuda()
+        Kd = _even_ld(torch.as_tensor(np.ascontiguousarray(Ki, dtype=np.float64)).cuda())
         rows_i, cols_i = Kd.shape
-        Yc = y.view(-1, cols_i)
-        out = gemm_nt(Yc, Kd)                      # (rest, rows_i) = Yc @ K_i^T
-        y = out.t().contiguous().view(-1)
+        Yc = _even_ld(y.view(-1, cols_i))
+        rest = Yc.shape[0]
+        out_t = torch.empty((rows_i, rest), dtype=torch.float64, device=y.device)     # = (Yc @ K_i^T)^T
+        if rest and rows_i:
+            nat.check(nat.lib().grief_gemm_nt_t(nat.dev_ptr(Yc), Yc.stride(0), nat.dev_ptr(Kd), Kd.stride(0), nat.dev_ptr(out_t), rest,
+                                                rest, rows_i, cols_i, 1.0, 0.0, nat.stream_ptr()))
+        y = out_t.view(-1)
     return y.cpu().numpy().reshape((-1, 1))
 
 

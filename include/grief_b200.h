@@ -313,6 +313,10 @@ int grief_rowcol_kr_matvec(int d, const int32_t* m, const double* const* R_dev, 
  */
 int grief_gemm_nt(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* C_dev, int64_t ldc, int M,
                   int N, int K, double alpha, double beta, void* stream);
+/* The same product stored transposed: Ct (N x M, ldct) = beta * Ct + alpha * (A B^T)^T.  The Kronecker mat-vec (tensors/kron_matrix.py:52-97)
+ * applies one factor per step to a running matrix and needs the result transposed for the next factor: this saves that pass. */
+int grief_gemm_nt_t(const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double* Ct_dev, int64_t ldct, int M,
+                    int N, int K, double alpha, double beta, void* stream);
 
 #ifdef __cplusplus
 }
