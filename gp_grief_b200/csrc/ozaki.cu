@@ -107,7 +107,8 @@ struct OzParams {
   int lower_only;                    // skip tiles entirely above the diagonal
   int accumulate;                    // 1: C += result, 0: C = result
   int store_t;                       // 1: C is stored transposed, element (m, n) at C[n * ldc + m]
-  int group_n;                       // column tiles per rasterisation group (CL = 1; 0: plain row-major tile order)
+  int group_n;                       // column tiles per rasterisation group (0: plain row-major tile order)
+  const uint32_t* tile_order;        // CL = 2, lower_only: (pair row << 16 | column tile) of cluster blockIdx.x / 2, or nullptr
   int* err;
 };
 
@@ -182,6 +183,11 @@ __global__ void __launch_bounds__(192, 1) k_ozaki(const __grid_constant__ OzMaps
     const int pm = within / gw;
     bn = first + (within - pm * gw);
     bm = 2 * pm + ((int)blockIdx.x & 1);
+  }
+  if (CL == 2 && prm.tile_order != nullptr) {        // blocked order of the lower-triangle pair tiles (plan.cu)
+    const uint32_t t = __ldg(prm.tile_order + (blockIdx.x >> 1));
+    bm = 2 * (int)(t >> 16) + ((int)blockIdx.x & 1);
+    bn = (int)(t & 0xFFFFu);
   }
   if (prm.lower_only && bn > (CL == 2 ? (bm | 1) : bm)) return;      // uniform over the cluster
   uint32_t crank = 0;
@@ -505,7 +511,10 @@ int ozaki_gemm(const int8_t* pa, int64_t rows_a_alloc, const int* ea, int M, con
   // +5..16 %); on a few tiles (C2: p = 1024, 8 x 8) the coarser tiles cost more in wave quantisation than they save in L2 traffic.
   const bool pairs = tiles_m >= 2 && (opt.cluster == 2 || (opt.cluster == 1 && std::min(tiles_m, tiles_n) >= 16));
   if (!pairs && prm.group_n >= tiles_n) prm.group_n = 0;      // one group = plain order (single CTAs: x already walks the column tiles)
-  const dim3 grid = pairs ? dim3((tiles_m + 1) / 2 * 2, tiles_n, splits) : dim3(tiles_n, tiles_m, splits);
+  const bool ordered = pairs && lower_only && opt.tile_order != nullptr && opt.n_tile_order > 0 && M == N;
+  prm.tile_order = ordered ? opt.tile_order : nullptr;
+  const dim3 grid = ordered ? dim3(2 * opt.n_tile_order, 1, splits)
+                            : (pairs ? dim3((tiles_m + 1) / 2 * 2, tiles_n, splits) : dim3(tiles_n, tiles_m, splits));
   int rc;
 #define GRIEF_OZ(SD_, GT_)                                                                                         \
   if (SD == SD_ && g_top == GT_)                                                                                   \

@@ -556,6 +556,7 @@ int launch_gram(const Plan* pl, const double* T, int64_t n_pad, double* A, int64
   }
   OzOpts oz_gram = oz_opts(pl, sd);
   oz_gram.diag_pair = 1;
+  oz_gram.tile_order = pl->d_gram_order; oz_gram.n_tile_order = pl->n_gram_order;
   GemmOpts o;
   o.lower_only = true;
   o.splits = s.splits;

@@ -283,6 +283,25 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
     for (int k = 0; k < G; ++k)
       sorted_pack[(size_t)c * pl->pack_words + k / 4] |= (uint32_t)(sorted_slot[(size_t)c * G + k] & 0xFF) << (8 * (3 - k % 4));
 
+  // ---- launch order of the Gram's lower-triangle tiles when CTA pairs (256 x 128) compute them ----
+  // (pair row pm = tile rows 2 pm, 2 pm + 1; column tile bn <= 2 pm + 1).  One K split of the digit planes (p_pad columns x ~10^4 rows
+  // x digits) is larger than L2, so what matters is how many distinct panels the ~74 pair tiles in flight touch: bands of 8 pair rows
+  // are walked in blocks of 9 column tiles (<= 72 pair tiles, 16 + 9 panels) instead of whole columns (32 + ~5 panels each time).
+  std::vector<uint32_t> gram_order;
+  {
+    const int tiles = pl->p_pad / kTileN, prow = (tiles + 1) / 2;
+    constexpr int R = 8, CW = 9;
+    for (int b0 = 0; b0 < prow; b0 += R) {
+      const int b1 = std::min(prow, b0 + R);
+      const int bn_max = std::min(tiles - 1, 2 * (b1 - 1) + 1);
+      for (int c0 = 0; c0 <= bn_max; c0 += CW)
+        for (int pm = b0; pm < b1; ++pm)
+          for (int bn = c0; bn < std::min(c0 + CW, bn_max + 1); ++bn)
+            if (bn <= std::min(tiles - 1, 2 * pm + 1)) gram_order.push_back(((uint32_t)pm << 16) | (uint32_t)bn);
+    }
+    pl->n_gram_order = (int)gram_order.size();
+  }
+
   // ---- upload ----
   std::vector<double> grid(grid_concat, grid_concat + pl->sum_m);
   std::vector<double> qs(qs_concat, qs_concat + qoff);
@@ -297,6 +316,7 @@ int plan_create(Plan** out, int d, const int32_t* m, const int32_t* kernel_id, c
   pool.add(&pl->d_sorted_slot, sorted_slot);
   pool.add(&pl->d_sorted_level, sorted_level);
   pool.add(&pl->d_sorted_pack, sorted_pack);
+  pool.add(&pl->d_gram_order, gram_order);
   pool.add(&pl->d_perm, pl->perm_h);
   pool.add(&pl->d_err, std::vector<int>(1, 0));
   int rc = pool.commit(&pl->d_pool);

@@ -76,6 +76,8 @@ struct Plan {
   uint8_t* d_sorted_level = nullptr;    // p_pad: first key position where sorted column c differs from c-1 (G: identical)
   uint32_t* d_sorted_pack = nullptr;    // p_pad x pack_words: the key-order slots of sorted column c, one byte each, 4 per word (MSB first)
   int pack_words = 1;                   // (G + 3) / 4
+  uint32_t* d_gram_order = nullptr;     // n_gram_order entries (pair row << 16 | column tile): launch order of the Gram's lower pair tiles
+  int n_gram_order = 0;
   int* d_perm = nullptr;                // p_pad: external column of sorted column c (-1 for padding columns)
   std::vector<int> perm_h;
   int device = 0;
@@ -111,6 +113,8 @@ struct OzOpts {
   int cluster = 0;             // CTA pairs with tcgen05.mma.cta_group::2 on 256 x 128 tiles: 0 never, 1 for >= 16 x 16 tiles, 2 always
   int store_t = 0;             // 1: C is written transposed (element (m, n) at C[n * ldc + m])
   int diag_pair = 0;           // 1: both operands are the same matrix (Gram): keep the pair a = b = digits / 2 of group g = digits
+  const uint32_t* tile_order = nullptr;   // lower_only with CTA pairs: (pair row << 16 | column tile) per cluster, n_tile_order entries
+  int n_tile_order = 0;
   int* err = nullptr;          // device int: 1-3 barrier time-out in k_ozaki, 4 non-finite operand value
 };
 size_t ozaki_plane_bytes(int64_t rows, int K);

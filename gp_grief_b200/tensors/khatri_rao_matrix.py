@@ -42,7 +42,11 @@ class RowColKhatriRaoMatrix(object):
         self.d = len(R)
         self.R = R
         if K is not None:
-            K = np.asarray(K)
+            if not (isinstance(K, np.ndarray) and K.dtype == object):     # a plain list of differently sized factors
+                factors = list(K)
+                K = np.empty(len(factors), dtype=object)
+                for i, Ki in enumerate(factors):
+                    K[i] = Ki
             assert len(K) == len(C) == self.d, "number of dims inconsistent"
             self.C = np.empty(self.d, dtype=object)
             for i in range(self.d):

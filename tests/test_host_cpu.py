@@ -214,3 +214,97 @@ def test_int8_digit_scheme_is_double_precision_class():
     assert np.abs(C - ref).max() / np.abs(ref).max() < 5e-15
     assert (np.abs(C - ref) / scale).max() < 2.0 ** -52
     assert np.all(C[3] == 0.0)
+
+
+def test_rowcol_khatri_rao_device_factors_are_plain_products():
+    """Host side of RowColKhatriRaoMatrix(device=True): the factor lists handed to grief_rowcol_kr_matvec must describe the same
+    matrix as expand() -- selection matrices as index vectors, the transposed form as C^T / R^T (no GPU involved)."""
+    from gp_grief_b200.tensors import RowColKhatriRaoMatrix, RowColKhatriRaoMatrixTransposed, SelectionMatrixSparse
+    rng = np.random.default_rng(5)
+    rows, cols, ms = 11, 7, [3, 5, 2]
+    C = [rng.standard_normal((m, cols)) for m in ms]
+    K = [rng.standard_normal((m, m)) for m in ms]
+    Rd = [rng.standard_normal((rows, m)) for m in ms]
+    sel = [SelectionMatrixSparse((rng.integers(0, m, size=rows), m)) for m in ms]
+
+    def dense_from(R, Cf):
+        out = 1.0
+        for r, c in zip(R, Cf):
+            r = np.asarray(r)
+            out = out * (c[r, :] if r.ndim == 1 else r.dot(c))
+        return out
+
+    A = RowColKhatriRaoMatrix(R=Rd, K=K, C=C, device=True)
+    R, Cf = A._device_factors()
+    np.testing.assert_allclose(dense_from(R, Cf), A.expand(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(A.expand(), np.prod([r.dot(k.dot(c)) for r, k, c in zip(Rd, K, C)], axis=0), rtol=0, atol=1e-13)
+    As = RowColKhatriRaoMatrix(R=sel, K=None, C=C, device=True)
+    R, Cf = As._device_factors()
+    assert all(np.asarray(r).ndim == 1 for r in R)
+    G = np.prod([C[t][sel[t].indicies, :] for t in range(3)], axis=0)
+    np.testing.assert_allclose(dense_from(R, Cf), G, rtol=0, atol=0)
+    AT = As.T
+    assert isinstance(AT, RowColKhatriRaoMatrixTransposed) and AT.device and tuple(AT.shape) == (cols, rows)
+    R, Cf = AT._device_factors()
+    np.testing.assert_allclose(dense_from(R, Cf), G.T, rtol=0, atol=0)
+    v = rng.standard_normal((rows, 1))
+    host = RowColKhatriRaoMatrixTransposed(R=sel, K=None, C=C)
+    np.testing.assert_allclose(host * v, G.T.dot(v), rtol=0, atol=1e-13)
+
+
+def test_gpy_kernel_plumbing_without_gpy(monkeypatch):
+    """GPyKernel (kern/gpy_kernel.py of the reference): constructor forms, cov with children, parameter / constraint vectors,
+    fix_variance -- against a stand-in for the GPy module; without GPy the constructor raises ImportError (no GPU involved)."""
+    import sys
+    import types
+    import gp_grief_b200 as gp
+    monkeypatch.setitem(sys.modules, "GPy", None)
+    with pytest.raises(ImportError):
+        gp.kern.GPyKernel(1, kernel="RBF")
+
+    class Param(np.ndarray):
+        def __new__(cls, value, name):
+            obj = np.asarray([value], dtype=float).view(cls)
+            obj._name = name
+            return obj
+
+        def __array_finalize__(self, obj):
+            self._name = getattr(obj, "_name", None)
+
+        @property
+        def values(self):
+            return np.asarray(self)
+
+    GPy, kmod = types.ModuleType("GPy"), types.ModuleType("GPy.kern")
+
+    class Kern(object):
+        pass
+
+    class RBF(Kern):
+        def __init__(self, input_dim, variance=1., lengthscale=1.):
+            self.variance, self.lengthscale = Param(variance, "variance"), Param(lengthscale, "lengthscale")
+            self.flattened_parameters = [self.variance, self.lengthscale]
+
+        def K(self, x, z=None):
+            z = x if z is None else z
+            return float(self.variance[0]) * np.exp(-0.5 * (x - z.T) ** 2 / float(self.lengthscale[0]) ** 2)
+
+    kmod.Kern, kmod.RBF = Kern, RBF
+    GPy.kern = kmod
+    monkeypatch.setitem(sys.modules, "GPy", GPy)
+    monkeypatch.setitem(sys.modules, "GPy.kern", kmod)
+    k = gp.kern.GPyKernel(1, kernel="RBF", lengthscale=0.4)
+    own = gp.kern.RBF(1, lengthscale=0.4)
+    x = np.linspace(0, 1, 6).reshape(-1, 1)
+    np.testing.assert_allclose(k.cov(x), own.cov(x), rtol=1e-15)
+    np.testing.assert_array_equal(k.parameters, own.parameters)
+    assert list(k.constraints) == ['+ve', '+ve'] and k.device_id is None and k.name == "GPy - RBF"
+    k.parameters = np.array([2.0, 0.7])
+    assert float(k.kern.variance[0]) == 2.0 and float(k.kern.lengthscale[0]) == 0.7
+    k.fix_variance()
+    assert list(k.constraints) == ['fixed', '+ve']
+    both = k + gp.kern.RBF(1, lengthscale=0.2)                 # a child kernel is folded into cov and the parameter vector
+    np.testing.assert_allclose(both.cov(x), k.cov(x) + gp.kern.RBF(1, lengthscale=0.2).cov(x), rtol=1e-15)
+    assert both.parameters.size == 4 and both.constraints.size == 4
+    with pytest.raises(TypeError):
+        gp.kern.GPyKernel(1, kernel=None)
