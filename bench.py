@@ -56,7 +56,7 @@ def parse():
                     help="arithmetic of the two O(n p^2) products: FP64 emulated on the INT8 tensor cores (int8 = int8x2: CTA pairs, the library "
                          "default; int8x1: one CTA per tile) or the FP64 DMMA GEMM")
     ap.add_argument("--digits", default="", help="'Dgram,Dz': int8 digits per operand of the two products (default: library defaults)")
-    ap.add_argument("--slab-mb", type=int, default=0, help="HBM budget (MiB) of the Phi^T slab staged per pass-1 GEMM launch (0: library default 1024)")
+    ap.add_argument("--slab-mb", type=int, default=0, help="HBM budget (MiB) of the Phi^T slab staged per pass-1 GEMM launch (0: library default 1280)")
     ap.add_argument("--power-trace", default="", help="write the clock / power samples of the timed region to this JSON file")
     return ap.parse_args()
 
@@ -487,12 +487,18 @@ def run_ours(args):
         m0.log_likelihood(return_gradient=True)               # evaluates repeatedly keeps its device buffers between calls)
         del m0
         barrier()
+        trace = os.environ.get("GRIEF_BENCH_E2E_TRACE") == "1" and rank == 0
         t0 = time.perf_counter()
         for s in range(steps_e2e):
+            ta = time.perf_counter()
             mm = make_model(100 + s)                           # H2D copy of X and y from pinned host memory
+            tb = time.perf_counter()
             l_, g_ = mm.log_likelihood(return_gradient=True)  # D2H of LML and gradient
             as_f(l_); np.asarray(g_)
+            tc = time.perf_counter()
             del mm
+            if trace:
+                print("e2e step %d: construct %.1f ms, evaluate %.1f ms, release %.1f ms" % (s, (tb - ta) * 1e3, (tc - tb) * 1e3, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if distributed:

@@ -210,7 +210,7 @@ static int set_opt(PlanOpts& o, int what, int64_t value) {
       return GRIEF_OK;
     case GRIEF_OPT_SLAB_BUDGET:
       GRIEF_REQUIRE(value >= 0, "option slab_budget: %lld", (long long)value);
-      o.slab_budget = value ? (size_t)value : ((size_t)1 << 30);
+      o.slab_budget = value ? (size_t)value : ((size_t)5 << 28);
       return GRIEF_OK;
     default: return fail(GRIEF_ERR_BAD_ARG, "unknown option %d", what);
   }

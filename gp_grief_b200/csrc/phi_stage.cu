@@ -478,7 +478,9 @@ GramSchedule gram_schedule(const Plan* pl, int64_t n_pad, int sms) {
   const int p_pad = pl->p_pad;
   s.nb = p_pad / kTileN;
   s.n_tiles = s.nb * (s.nb + 1) / 2;
-  const int64_t budget_rows = (int64_t)(pl->opts.slab_budget / ((size_t)p_pad * 8)) / kBuildRows * kBuildRows;
+  int64_t budget_rows = (int64_t)(pl->opts.slab_budget / ((size_t)p_pad * 8)) / kBuildRows * kBuildRows;
+  const int64_t wave_rows = (int64_t)sms * kBuildRows;              // the builder runs one CTA of 128 rows per SM: whole waves per slab
+  if (budget_rows >= wave_rows) budget_rows = budget_rows / wave_rows * wave_rows;
   s.slab_rows = std::max<int64_t>(kBuildRows, std::min<int64_t>(n_pad, std::max<int64_t>(kBuildRows, budget_rows)));
   // K splits: fill whole waves of `sms` CTAs, keep >= 256 data rows per split
   const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(s.slab_rows / 256, 64));

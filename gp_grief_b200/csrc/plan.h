@@ -42,8 +42,9 @@ struct PlanOpts {
   int digits_gram = 6;                     // INT8 digits per operand of A = Phi^T Phi (46-bit operands + the diagonal pair, ozaki.cu)
   int digits_z = 4;                        // INT8 digits per operand of Zp = Phi P^-1 in the gradient pass (30-bit; the rank-one part is FP64)
   int digits_var = 6;                      // INT8 digits per operand of Z = Phi B in grief_quadform_rows (predictive variance)
-  size_t slab_budget = (size_t)1 << 30;    // bytes of Phi^T (as FP64) staged per pass-1 slab: 32768 rows at p = 4096, so one K split
-                                           // (4096 rows x p x digits) stays L2-resident while its tiles pass
+  size_t slab_budget = (size_t)5 << 28;    // 1.25 GiB of Phi^T (as FP64) staged per pass-1 slab, rounded down to whole builder waves
+                                           // (148 x 128 rows): 37888 rows at p = 4096, so one K split
+                                           // (~12600 rows x p x digits) passes through L2 in pieces that the tiles in flight share
 };
 PlanOpts& default_plan_opts();             // thread-local defaults for plans created on this thread
 

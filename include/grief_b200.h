@@ -180,7 +180,7 @@ int grief_phi_rows(const grief_plan* plan, const double* T_dev, int64_t n, doubl
  *                          component with D = 4, 2e-15 with D >= 5, 6e-11 with D = 3 (same measurement)
  *   GRIEF_OPT_DIGITS_VAR   D of Z = Phi B in grief_quadform_rows (3..7, default 6): a predictive variance sums only p products
  *   GPGriefModel audits these choices a posteriori against the FP64 mode on a row sample (models/gp_grief_model.py, arithmetic_audit).
- *   GRIEF_OPT_SLAB_BUDGET  bytes of HBM for the Phi^T slab that pass 1 stages per GEMM launch (default 1 GiB of FP64-equivalent rows -- 32768 rows at p = 4096, so that the digit planes of one K split stay in L2 while its tiles pass; 0 restores it).  Smaller
+ *   GRIEF_OPT_SLAB_BUDGET  bytes of HBM for the Phi^T slab that pass 1 stages per GEMM launch (default 1.25 GiB of FP64-equivalent rows, rounded down to whole waves of the slab builder -- 37888 rows at p = 4096; a K split of the digit planes then passes through L2 in pieces that the tiles in flight share; 0 restores it).  Smaller
  *                          budgets mean more, shorter launches; results are identical up to the order of the fixed-order accumulation
  * grief_set_slab_budget / grief_set_gemm_mode / grief_get_gemm_mode are the round-1 spellings of the default setters.
  */
