@@ -371,6 +371,30 @@ class NativeComm(object):
             pass
 
 
+_SHARED_SOLVERS = {}
+
+
+def shared_solver():
+    """The DeviceSolver of the calling thread's current device and stream.  A grief_ctx owns the dense-stage scratch (3 p_pad^2
+    doubles: 0.4 GB at p = 4096, 1.6 GB at p = 8192); creating one per model costs a cudaMalloc of that size at its first solve and a
+    cudaFree -- a device-wide synchronisation -- when the model is released (measured: 70-180 ms per released model in a process that
+    builds a new model per evaluation).  Calls on one stream are ordered, so models of one thread can share the context."""
+    import threading
+    torch = _torch()
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream, threading.get_ident())
+    solver = _SHARED_SOLVERS.get(key)
+    if solver is None:
+        solver = _SHARED_SOLVERS[key] = DeviceSolver()
+    return solver
+
+
+def release_shared_solvers():
+    """Free the scratch of every shared solver (they are re-created on demand)."""
+    for solver in list(_SHARED_SOLVERS.values()):
+        solver.close()
+    _SHARED_SOLVERS.clear()
+
+
 class DeviceSolver(object):
     """grief_ctx: the p x p stage (Cholesky, solve, LML, w / noise gradients, pass-2 operand)."""
 

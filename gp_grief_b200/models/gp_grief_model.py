@@ -69,7 +69,6 @@ class GPGriefModel(BaseModel):
             self.num_data = int(cnt.item())
         self._X_dev = torch.as_tensor(np.ascontiguousarray(self.X, dtype=np.float64)).cuda()
         self._y_dev = torch.as_tensor(np.ascontiguousarray(self.Y[:, 0], dtype=np.float64)).cuda()
-        self._solver = device.DeviceSolver()
         self._dev = {}                                   # device-resident caches (tensors)
         self._host = {}                                  # lazily copied host views of the caches
 
@@ -302,7 +301,7 @@ class GPGriefModel(BaseModel):
             audit = self._audit_pending('gram')
             st = self._stats()
             w_dev = self._torch.as_tensor(np.ascontiguousarray(self._w, dtype=np.float64)).cuda()
-            out = self._solver.solve(st['A'], st['r'], st['s'], w_dev, float(self.noise_var), self.num_data,
+            out = self._device_mod.shared_solver().solve(st['A'], st['r'], st['s'], w_dev, float(self.noise_var), self.num_data,
                                      want_grad=want_grad or want_G2 or audit, want_G2=want_G2)
             if not audit:
                 break

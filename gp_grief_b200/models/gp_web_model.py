@@ -48,7 +48,7 @@ class GPwebModel(BaseModel):
         self.n = int(n)
         self.p = int(A.shape[0])
         self._A_dev, self._r_dev, self._s_dev = A, r, s
-        self._solver = device.DeviceSolver()
+        self._device_mod = device
         self.noise_var = np.float64(noise_var)
         self.kern = WEBKernel(initial_weights=np.ones(self.p))
         self.grad_method = 'adjoint'
@@ -75,7 +75,7 @@ class GPwebModel(BaseModel):
         if have is not None and (have['Pinv'] is not None or not want_grad):
             return have
         w = torch.as_tensor(np.ascontiguousarray(self.kern.parameters, dtype=np.float64)).cuda()
-        self._solve = self._solver.solve(self._A_dev, self._r_dev, self._s_dev, w, float(self.noise_var), self.n,
+        self._solve = self._device_mod.shared_solver().solve(self._A_dev, self._r_dev, self._s_dev, w, float(self.noise_var), self.n,
                                          want_grad=want_grad, want_G2=False)
         return self._solve
 
