@@ -8,20 +8,23 @@
 //   symmetric product A = X X^T with SD even the pair a = b = SD / 2 of the first dropped group is kept as well).  Each digit
 //   product is an exact int8 x int8 -> int32 GEMM; one accumulation covers at most 16384 values of K (7 pairs x 2^14 x 2^14 < 2^31),
 //   longer K is split over blockIdx.z.
-// Kernel: one CTA per 128 x 128 tile.  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b;
+// Kernel: one CTA per 128 x 128 tile (CL = 1) or one CTA PAIR per 256 x 128 tile (CL = 2, the default from 16 x 16 tiles on; see the
+// template comment).  TMEM holds four 128-column int32 accumulators, one per significance group g = a + b;
 // two sweeps over K (g = SD-1..SD-4 with all SD + SD digit planes, then g = SD-5..0 with digits 0..SD-5; the second sweep walks K
-// backwards so that it starts on the chunks the first one left in L2), each followed by a drain.  All digit planes a sweep needs
-// for one 32-byte K chunk sit in shared memory (3-D TMA boxes over [digit][row][32 B], SWIZZLE_32B; three 56 KB stages at SD = 7,
-// more at fewer digits); warp 4 = TMA producer, warp 5 = MMA issuer (one thread, tcgen05.mma.cta_group::1.kind::i8, M = N = 128,
-// K = 32), warps 0-3 drain TMEM: tcgen05.ld -> f64 -> sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared
-// memory -> added to C.  The six tensor maps travel as __grid_constant__ kernel parameters (no descriptor is ever re-written in
-// global memory).  Tiles are rasterised in groups of `group_n` column tiles so that the B digits of a group stay L2-resident while
-// all row tiles (or row-tile pairs) pass.  k_ozaki<2, SD> computes 256 x 128 tiles with CTA pairs and tcgen05.mma.cta_group::2 (see the template comment).
-// Measured (B200, pass-2 shape 37888 x 4096 x 4096): 14.4 ms = 88 TFLOP/s FP64-equivalent alone, 81 inside the benchmark (power
-// cap), against 35 for cuBLAS DGEMM / 36.4 for the DMMA kernel in dense.cu; max |C - C_dgemm| / max|C| ~ 2e-15.
+// backwards so that it starts on the chunks the first one left in L2), each followed by a drain; with SD <= 4 there is one sweep.
+// All digit planes a sweep needs for one 32-byte K chunk sit in shared memory (3-D TMA boxes over [digit][row][32 B], SWIZZLE_32B;
+// three 56 KB stages at SD = 7, more at fewer digits); warp 4 = TMA producer, warp 5 = MMA issuer (one thread,
+// tcgen05.mma.cta_group::{1,2}.kind::i8, M = 128 or 256, N = 128, K = 32), warps 0-3 drain TMEM: tcgen05.ld -> f64 ->
+// sum_g 2^(-12-8g) acc_g -> row / column scales -> transposed through shared memory (or stored transposed directly) -> added to C.
+// The six tensor maps travel as __grid_constant__ kernel parameters (no descriptor is ever re-written in global memory).
+// Launch order: full products are rasterised in groups of `group_n` column tiles so that the B digits of a group stay L2-resident
+// while all row tiles (or row-tile pairs) pass; the lower-triangle pair tiles of the Gram follow a blocked order table (plan.cu).
+// Measured (B200, C3, inside the benchmark under the 1000 W cap, profiles/r02_design_notes.md): Phi P^-1 (37888 x 4096 x 4096,
+// 4 digits) 2.85 POP/s int8, Gram (6 digits) 2.4 POP/s, against 2.43 POP/s for the dense int8 GEMM of cuBLASLt in the same process;
+// tensor pipe 67 % active (single CTAs: 55 %); with 7 digits max |C - C_dgemm| / max|C| ~ 2e-15 (round 1: 88 TFLOP/s FP64-equivalent
+// alone, against 35 for cuBLAS DGEMM / 36.4 for the DMMA kernel in dense.cu).
 // Variants measured and not adopted (profiles/r01_gram_design_notes.md): 128 x 256 tiles with two accumulators and five work
-// items (16.7 ms), CTA pairs with multicast B or with cta_group::2 MMAs (same time or slower, lower clock), 64-byte K stages for
-// the light sweep (slower), accumulator-interleaved MMA order (slower).
+// items, CTA pairs with multicast B, 64-byte K stages for the light sweep, accumulator-interleaved MMA order (all slower or equal).
 // Every barrier wait is bounded: a protocol failure raises an error flag (checked by the callers) instead of hanging the GPU.
 #include <cuda.h>
 

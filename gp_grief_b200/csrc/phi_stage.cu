@@ -1,19 +1,20 @@
-// The two O(n p^2) products of an evaluation, staged:  the basis matrix Phi of a slab of data rows is built by a
-// bandwidth-bound kernel into HBM, then a plain TMA-fed FP64 DMMA GEMM (dense.cu, k_gemm_nt) consumes it.
+// The two O(n p^2) products of an evaluation, staged:  the basis matrix Phi of a slab of data rows is built by a row kernel into
+// HBM (as int8 digit planes, or as FP64), then a GEMM consumes it (ozaki.cu on the INT8 tensor cores, or dense.cu on FP64 DMMA).
 //
-//   pass 1 (models/gp_grief_model.py:148-149)   A = Phi^T Phi :  Phi^T slab (p_pad x R, data rows contiguous)
-//                                               -> SYRK on the lower tiles, K = data rows split over gridDim.z
-//   pass 2 / predictive var.    Z = Phi B     :  Phi slab (R x p_pad, sorted columns contiguous)
-//                                               -> GEMM against the column-permuted symmetric B
+//   pass 1 (models/gp_grief_model.py:148-149)   A = Phi^T Phi :  Phi^T slab (p_pad x R, K = data rows contiguous)
+//                                               -> SYRK on the lower tiles, K split over gridDim.z; r = Phi^T y and the row maxima
+//                                                  of |Phi| fall out of the builder's sweep
+//   pass 2 / predictive var.    Z = Phi B     :  Phi slab (R x p_pad, K = sorted columns contiguous)
+//                                               -> GEMM against the column-permuted symmetric B, stored transposed; the residual
+//                                                  a = (y - Phi b) / sigma^2 falls out of the builder's sweep
 //
-// Two arithmetic modes (per plan, PlanOpts): 1 (default) -- the builders emit power-of-two row scales and 4..7 int8 digit planes
-// and k_ozaki (ozaki.cu) multiplies them on the tcgen05 INT8 tensor cores; 0 -- the builders emit the FP64 slab for k_gemm_nt.
-// r = Phi^T y is formed inside the pass-1 builder (the values are in registers there).
+// Two arithmetic modes (per plan, PlanOpts): INT8 (default) -- the builders emit power-of-two row scales and 3..7 int8 digit planes
+// and k_ozaki multiplies them exactly; FP64 -- the builders emit the FP64 slab for k_gemm_nt.
 //
 // Why staged and not fused (round-1 measurements, profiles/r01_gram_design_notes.md): DMUL, DFMA and DMMA share ONE FP64
 // pipe per SM sub-partition.  With the Phi tiles built inside the GEMM CTAs the builder's DMULs queue behind the DMMAs
 // (32 % of warp samples in stall_math) and the kernels stop at 25-28 TFLOP/s; the same DMMA loop fed by TMA alone runs at
-// 36 TFLOP/s.  The slab costs 7-8 B written + read per element of Phi, a few % of the GEMM time, on an HBM that is otherwise
+// 36 TFLOP/s.  The slab costs 4-6 B written + read per element of Phi, a few % of the GEMM time, on an HBM that is otherwise
 // idle during these passes.
 #include <cuda.h>
 
