@@ -1,16 +1,19 @@
 """GP-GRIEF regression model on the B200 (reference: gp_grief/models/gp_grief_model.py).
 
 Same class, constructor and methods as the reference.  Data rows live on the GPU; one evaluation is
-    prepass tables  ->  Gram A = Phi^T Phi, r = Phi^T y, s = y^T y   (csrc/rows.cu, csrc/phi_stage.cu, csrc/dense.cu)
+    prepass tables  ->  Gram A = Phi^T Phi, r = Phi^T y, s = y^T y   (csrc/rows.cu, csrc/phi_stage.cu, csrc/ozaki.cu | dense.cu)
     [all-reduce of (A | r | s) when the rows are sharded over ranks]
-    Cholesky / solve / LML / d/dw / d/dnoise_var                           (csrc/solve.cu)
-    analytic d/d(kernel hyper-parameters)                                  (csrc/phi_stage.cu, csrc/dense.cu, csrc/grad.cu)
+    Cholesky / solve / LML / d/dw / d/dnoise_var                           (csrc/solve.cu, csrc/dense.cu)
+    analytic d/d(kernel hyper-parameters), reverse mode                    (csrc/phi_stage.cu, csrc/ozaki.cu | dense.cu, csrc/grad.cu)
 and Phi (n x p) is never formed.  Differences from the reference that a caller can observe:
   * `_Phi`, `_alpha` are computed on demand (they are n-sized); `_A`, `_P`, `_Pchol` are host copies.
   * with `opt_kernel_params=True` and distinct in-house kernels the default `grad_method` is the analytic
     'adjoint' path; the reference can only finite-difference there (gp_grief_model.py:71-74,194-196).
-    Set `m.grad_method = 'finite_difference'` to reproduce the reference's gradient bit-for-bit in method.
+    Set `m.grad_method = 'finite_difference'` to reproduce the reference's gradient bit-for-bit in method; kernels that exist only
+    as host code (GPyKernel, kernels with children) always take that route, as in the reference.
   * `predict(Xnew, compute_var='diag')` returns the marginal variances without the M x M covariance.
+  * the two O(n p^2) products run as exact int8 digit GEMMs on the tensor cores (`gemm_digits`); the first evaluation of a model
+    audits the digit counts against the FP64 arithmetic on a row sample (`arithmetic_audit`, `audit_rows`, `audit_tol*`).
 There is no CPU path: constructing the model without a CUDA device raises.
 """
 from logging import getLogger
